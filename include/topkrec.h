@@ -1,0 +1,145 @@
+/* topkrec.h -- C ABI of libtopkrec.so, the B200 (sm_100a) engine under the two
+ * hot paths of domainxz/top-k-rec.
+ *
+ * The reference has NO FFI: the seams this ABI sits under are Python calls into
+ * third-party numerics.  Each entry point cites the reference line it replaces:
+ *
+ *   tkr_bpr_step / _host   <- sess.run([solver, obj], feed_dict={u,i,j})   single/bpr.py:141
+ *                             (graph = single/bpr.py:71-101, RMSProp :100; SGD = old/methods/bpr.py:57-61)
+ *   tkr_bpr_sample         <- BPR._uniform_user_sampling                    single/bpr.py:155-165
+ *   tkr_vbpr_step          <- sess.run(..., feed_dict={u,i,j,ic,jc})        single/vbpr.py:114 (graph :29-74)
+ *   tkr_score_topk / _host <- np.dot + np.argsort + rated-filter walk       evaluate.py:78,81,96-105
+ *   tkr_topk_merge         <- (no reference equivalent: merges item-sharded candidates so the
+ *                              sharded result equals the single-process one)
+ *
+ * Conventions
+ *   - Caller owns every buffer.  Pointers are DEVICE pointers unless the
+ *     parameter name ends in _host.  The library never allocates persistent
+ *     memory; scratch comes from the caller (`*_workspace_bytes`).
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered and
+ *     asynchronous unless the name ends in _host (those synchronise the stream
+ *     before returning because they write host memory).
+ *   - Return 0 on success, a negative TKR_ERR_* otherwise; the message is in
+ *     thread-local storage, `tkr_last_error()`.  No C++ exception crosses.
+ *   - Re-entrant across streams/devices; no global mutable state but the TLS
+ *     error string.
+ */
+#ifndef TOPKREC_H
+#define TOPKREC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TKR_VERSION 10100 /* 1.1.0 */
+
+#define TKR_OK 0
+#define TKR_ERR_INVALID (-1)     /* bad argument */
+#define TKR_ERR_WORKSPACE (-2)   /* workspace too small / misaligned */
+#define TKR_ERR_CUDA (-3)        /* CUDA runtime error */
+#define TKR_ERR_UNSUPPORTED (-4) /* shape outside what the kernels are built for */
+
+int tkr_version(void);
+const char* tkr_last_error(void);
+/* number of kernels launched by this library on the calling thread since the
+ * last tkr_reset_launch_count() -- bench.py reports it as gpu_launches */
+int64_t tkr_launch_count(void);
+void tkr_reset_launch_count(void);
+
+/* ------------------------------------------------------------------ path 1 */
+
+#define TKR_OPT_RMSPROP 0 /* tf.train.RMSPropOptimizer defaults, single/bpr.py:100 */
+#define TKR_OPT_SGD 1     /* old/methods/bpr.py:57-61 */
+
+typedef struct tkr_bpr_cfg {
+    int32_t n_users, n_items, d;                  /* d = embedding width k of the reference */
+    float lambda_u, lambda_i, lambda_j, lambda_b; /* single/bpr.py:20 */
+    float lr;
+    float rms_decay; /* 0.9  */
+    float rms_eps;   /* 1e-10, inside the sqrt */
+    int32_t l1;      /* 0: mode=='l2' (bpr.py:92-95); 1: L1 (bpr.py:96-99) */
+    int32_t optimizer;
+} tkr_bpr_cfg;
+
+/* Device-side sampler tables (CSR of positives; users with >= 1 positive). */
+typedef struct tkr_sampler {
+    const int32_t* tr_users;   /* [n_tr_users] user rows that have positives (bpr.py:67) */
+    int32_t n_tr_users;
+    const int64_t* pos_indptr; /* [n_users + 1] */
+    const int32_t* pos_idx;    /* positives of each user, ascending within a user */
+    int32_t n_items;
+    uint64_t seed;
+} tkr_sampler;
+
+/* Scratch for a step of `batch` triples.  Must be zero-filled once before the
+ * first step (tkr_bpr_workspace_init); every step leaves it zeroed again. */
+size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t batch);
+int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes, void* stream);
+
+/* n_steps consecutive synchronous mini-batch steps.  Step t uses triples
+ * [t*batch, (t+1)*batch) of u/i/j and writes the batch objective evaluated
+ * before the update to loss_out[t] (what sess.run returns for `obj`).
+ * All B gradients are taken at the pre-step snapshot, duplicate rows are
+ * summed, then one optimiser update per touched row.
+ * State: U[n_users,d], V[n_items,d], b[n_items] and the RMSProp `rms` slots
+ * msU/msV/msb of the same shapes (ignored for SGD; may be NULL then).
+ * If u == NULL the triples are drawn on the device from `smp` with the
+ * counter-based generator of tkr_bpr_sample (draw index = first_draw + t*batch + n)
+ * fused into the gradient kernel; i/j may then be NULL too. */
+int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                 const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, int64_t n_steps,
+                 const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* Same, with the triples and the losses in HOST memory (the feed_dict /
+ * fetch of sess.run): copies u/i/j host->device into `staging` (device,
+ * >= 3*batch*n_steps*4 bytes), runs the steps, copies loss back, synchronises. */
+int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                      const int32_t* u_host, const int32_t* i_host, const int32_t* j_host, int64_t batch,
+                      int64_t n_steps, float* loss_host, void* staging, size_t staging_bytes, void* ws,
+                      size_t ws_bytes, void* stream);
+
+/* Draw `n` triples (draw indices first_draw .. first_draw+n-1) with the
+ * semantics of single/bpr.py:155-165: user uniform over tr_users with
+ * replacement, positive uniform over the user's positives, negative uniform
+ * over [0, n_items) redrawn while it is a positive of the user.  Counter-based
+ * (Philox4x32-10 keyed by seed): reproducible and order-independent. */
+int tkr_bpr_sample(const tkr_sampler* smp, uint64_t first_draw, int64_t n, int32_t* u_out, int32_t* i_out,
+                   int32_t* j_out, void* stream);
+
+/* ------------------------------------------------------------------ path 2 */
+
+/* For every user row r of U[nu,d] the first k columns c of V[ni,d], in the
+ * order (score desc, column desc), that are not in the user's rated list:
+ *   score(r,c) = fp32 fma chain over the d products in ascending index order,
+ *                + bias[c] (if bias != NULL), + 0.0f
+ * Columns are reported as c + col_offset (item-sharded callers pass the shard's
+ * first global column; rated_idx holds global columns, ascending per user,
+ * rated_indptr[nu+1] indexes it).  Unused slots: idx -1, score -inf.
+ * k <= 64.  Output [nu,k] each.  The score matrix is never written to memory. */
+size_t tkr_score_topk_workspace_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k);
+int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
+                   const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
+                   int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, void* stream);
+
+/* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
+ * U_host/V_host/bias_host/rated_* in host memory, results to host memory.
+ * `dev` is device scratch of >= tkr_score_topk_host_device_bytes(). */
+size_t tkr_score_topk_host_device_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k, int64_t n_rated);
+int tkr_score_topk_host(const float* U_host, int64_t nu, const float* V_host, int64_t ni, int32_t d,
+                        const float* bias_host, const int64_t* rated_indptr_host, const int32_t* rated_idx_host,
+                        int32_t k, int32_t* out_idx_host, float* out_score_host, void* dev, size_t dev_bytes,
+                        void* stream);
+
+/* Merge n_lists candidate lists idx/score[n_lists][nu][k] (each in the order
+ * above, padded with idx -1) into out[nu][k] in the same order. */
+int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,
+                   int32_t* out_idx, float* out_score, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOPKREC_H */

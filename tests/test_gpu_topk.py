@@ -1,0 +1,178 @@
+"""GPU parity tests of hot path 2 (tkr_score_topk / tkr_topk_merge through the C ABI):
+index lists and scores must be BIT-EXACT against the C oracle (oracle/topk_ref.c), which is
+itself pinned to the reference's evaluate.py by the committed goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import topkrec
+from oracle import topk_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(nu, ni, d, k, seed, bias=False, rated=0, ties=False, scale=0.1):
+    rng = np.random.default_rng(seed)
+    U = (scale * rng.standard_normal((nu, d))).astype(np.float32)
+    V = (scale * rng.standard_normal((ni, d))).astype(np.float32)
+    if ties:
+        V[rng.integers(0, ni, ni // 10)] = V[0]
+        V[rng.integers(0, ni, ni // 20)] = 0
+        U[nu // 2] = 0
+    b = (0.05 * rng.standard_normal(ni)).astype(np.float32) if bias else None
+    indptr = idx = None
+    if rated:
+        cnt = rng.integers(0, rated + 1, nu)
+        cnt[0] = 0
+        if nu > 3:
+            cnt[3] = min(ni, 4 * rated)
+        indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum(cnt)
+        idx = np.concatenate([np.sort(rng.choice(ni, c, replace=False)) for c in cnt] + [np.zeros(0, np.int64)]).astype(np.int32)
+    return U, V, b, indptr, idx
+
+
+def _check(U, V, k, b, indptr, idx, col_offset=0):
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
+    gi, gs = topkrec.score_topk(t(U), t(V), k, t(b), t(indptr), t(idx), col_offset=col_offset)
+    if indptr is not None and col_offset:
+        pass
+    ri, rs = topk_ref.score_topk(U, V, k, b, indptr, idx, col_offset=col_offset)
+    gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+    assert np.array_equal(gi, ri), "index lists differ at rows %s" % np.nonzero((gi != ri).any(1))[0][:5]
+    assert np.array_equal(gs.view(np.uint32), rs.view(np.uint32)), "scores are not bit-identical"
+
+
+@pytest.mark.parametrize("nu,ni,d,k", [(300, 1000, 128, 30), (129, 65, 50, 30), (1, 1, 1, 1), (77, 200, 16, 5),
+                                       (64, 333, 256, 30), (40, 500, 300, 30), (33, 700, 512, 10), (10, 90, 7, 64),
+                                       (500, 4099, 64, 30), (260, 2048, 128, 15)])
+def test_score_topk_bit_exact_shapes(nu, ni, d, k):
+    _check(*_case(nu, ni, d, k, seed=nu + ni)[:2], k, None, None, None)
+
+
+@pytest.mark.parametrize("k", [5, 10, 15, 20, 25, 30])
+def test_score_topk_reference_cutoffs(k):
+    """the reference's k in {5,...,30} (evaluate.py -s 5 -t 30)"""
+    U, V, b, p, i = _case(200, 1500, 128, k, seed=k, bias=True, rated=40, ties=True)
+    _check(U, V, k, b, p, i)
+
+
+def test_score_topk_ties_and_zero_rows():
+    U, V, b, p, i = _case(150, 900, 50, 30, seed=11, ties=True)
+    _check(U, V, 30, None, None, None)
+    V[:] = 0                                   # every score ties at +0: order = column descending
+    t = lambda a: torch.from_numpy(a).cuda()   # noqa: E731
+    gi, gs = topkrec.score_topk(t(U), t(V), 30)
+    assert np.array_equal(gi.cpu().numpy(), np.tile(np.arange(899, 869, -1, dtype=np.int32), (150, 1)))
+    assert (gs.cpu().numpy().view(np.uint32) == 0).all()       # +0.0, never -0.0
+
+
+def test_score_topk_rated_mask_and_short_lists():
+    U, V, b, p, i = _case(120, 60, 32, 30, seed=12, bias=True, rated=45)   # some users have < 30 unrated columns
+    _check(U, V, 30, b, p, i)
+    full = np.arange(60, dtype=np.int32)                                    # a user who rated everything
+    p2 = np.array([0, 60], np.int64)
+    t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    gi, gs = topkrec.score_topk(t(U[:1]), t(V), 30, None, t(p2), t(full))
+    assert (gi.cpu().numpy() == -1).all() and np.isneginf(gs.cpu().numpy()).all()
+
+
+def test_score_topk_split_path_and_col_offset():
+    """few users x many items takes the item-split + merge path; shards report global columns"""
+    U, V, b, p, i = _case(40, 20000, 128, 30, seed=13, bias=True, rated=64)
+    _check(U, V, 30, b, p, i)
+    half = 9984
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
+    parts = [topkrec.score_topk(t(U), t(V[a:z].copy()), 30, t(b[a:z].copy()), t(p), t(i), col_offset=a) for a, z in ((0, half), (half, 20000))]
+    mi, ms = topkrec.topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]))
+    ri, rs = topk_ref.score_topk(U, V, 30, b, p, i)
+    assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+
+
+def test_topk_merge_matches_oracle():
+    rng = np.random.default_rng(14)
+    G, nu, k = 8, 257, 30
+    score = -np.sort(-rng.standard_normal((G, nu, k)).astype(np.float32), axis=2)
+    score[:, :, 20:][rng.random((G, nu, 10)) < 0.3] = 0.25            # ties across lists
+    score = -np.sort(-score, axis=2)
+    idx = np.empty((G, nu, k), np.int32)
+    for g in range(G):
+        for r in range(nu):
+            c = rng.choice(1000, k, replace=False) + 1000 * g
+            o = np.lexsort((-c, -score[g, r]))                           # (score desc, col desc) inside a list
+            idx[g, r] = c[o]; score[g, r] = score[g, r][o]
+    idx[1, :, 25:] = -1; score[1, :, 25:] = -np.inf                      # a short list
+    idx[2, 5, :] = -1; score[2, 5, :] = -np.inf                          # an empty list
+    mi, ms = topkrec.topk_merge(torch.from_numpy(idx).cuda(), torch.from_numpy(score).cuda())
+    ri, rs = topk_ref.topk_merge(idx, score)
+    assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy(), rs)
+
+
+def test_host_entry_equals_device_entry():
+    U, V, b, p, i = _case(300, 3000, 128, 30, seed=15, bias=True, rated=30)
+    hi, hs = topkrec.score_topk_host(U, V, 30, b, p, i)
+    ri, rs = topk_ref.score_topk(U, V, 30, b, p, i)
+    assert np.array_equal(hi, ri) and np.array_equal(hs.view(np.uint32), rs.view(np.uint32))
+    hi, hs = topkrec.score_topk_host(U, V, 30)
+    ri, rs = topk_ref.score_topk(U, V, 30)
+    assert np.array_equal(hi, ri)
+
+
+def test_evaluate_cli_matches_reference_goldens(golden, mini, capsys):
+    """our evaluate.py (reference CLI) on the reference-written .dat models == the numbers the
+    unmodified reference script printed (tests/golden/evaluate_mini.json)"""
+    import importlib.util
+    from conftest import PKG
+    spec = importlib.util.spec_from_file_location("tkr_evaluate", os.path.join(PKG, "evaluate.py"))
+    ev = importlib.util.module_from_spec(spec); spec.loader.exec_module(ev)
+    g = json.load(open(os.path.join(golden, "evaluate_mini.json")))
+    assert ev.main(["-d", mini, "-m", os.path.join(golden, "mini_model"), "-sl", "im", "om", "all"]) == g["no_bias"]
+    assert ev.main(["-d", mini, "-m", os.path.join(golden, "mini_model_bias"), "-sl", "all"]) == g["bias_all"]
+    assert ev.main(["-d", mini, "-m", os.path.join(golden, "mini_model_ties"), "-sl", "im", "om", "all"]) == g["ties_oracle_stable"]
+    out = capsys.readouterr().out.strip().splitlines()
+    assert out[:3] == g["no_bias"]
+
+
+def test_evaluate_lists_match_golden_lists(golden, mini):
+    import utils
+    lists = np.load(os.path.join(golden, "evaluate_mini_lists.npz"))
+    uids = utils.get_id_dict_from_file(os.path.join(mini, "uid")); vids = utils.get_id_dict_from_file(os.path.join(mini, "vid"))
+    browsed, _ = utils.get_history_from_file(os.path.join(mini, "f0tr.txt"))
+    for model, key_prefix in (("mini_model", ""), ("mini_model_ties", "ties_")):
+        U = utils.get_embed_from_file(os.path.join(golden, model, "final-U.dat"), uids)
+        V = utils.get_embed_from_file(os.path.join(golden, model, "final-V.dat"), vids)
+        for sc in ("im", "om", "all"):
+            teids = utils.get_id_dict_from_file(os.path.join(mini, "f0te.%s.idl" % sc))
+            cols = np.array([vids[v] for v in teids])
+            p, i = utils.rated_csr(uids, browsed, teids)
+            hi, _ = topkrec.score_topk_host(U, V[cols], 30, None, p, i)
+            assert np.array_equal(hi, lists[key_prefix + sc]), (model, sc)
+
+
+def test_full_size_property_sharded_equals_whole():
+    """C5-like width (1M items, d=128, k=30) on a small user batch: splitting the items into 8 shards and
+    merging gives the same bits as the single call; the returned scores are the exact FMA-chain scores;
+    lists are sorted by (score desc, col desc)."""
+    rng = np.random.default_rng(16)
+    nu, ni, d, k = 256, 1 << 20, 128, 30
+    U = torch.from_numpy((0.1 * rng.standard_normal((nu, d))).astype(np.float32)).cuda()
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    V = torch.randn(ni, d, device="cuda", generator=g) * 0.1
+    wi, ws_ = topkrec.score_topk(U, V, k)
+    bounds = np.linspace(0, ni, 9).astype(np.int64)
+    parts = [topkrec.score_topk(U, V[a:z], k, col_offset=int(a)) for a, z in zip(bounds[:-1], bounds[1:])]
+    mi, ms = topkrec.topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]))
+    assert torch.equal(mi, wi) and torch.equal(ms, ws_)
+    wi_h, ws_h = wi.cpu().numpy(), ws_.cpu().numpy()
+    assert (np.diff(ws_h, axis=1) <= 0).all()
+    Vh = V[torch.from_numpy(wi_h[:8].ravel().astype(np.int64)).cuda()].cpu().numpy().reshape(8, k, d)
+    Uh = U[:8].cpu().numpy()
+    for r in range(8):
+        _, rs = topk_ref.score_topk(Uh[r:r + 1], Vh[r], k)
+        assert np.array_equal(np.sort(rs[0])[::-1].view(np.uint32), ws_h[r].view(np.uint32))
+    # nothing outside the list beats the k-th score (fp64 check with a margin >> fp32 dot error)
+    S = (U[:8].double() @ V.double().T)
+    kth = torch.from_numpy(ws_h[:8, -1]).cuda().double()
+    assert int((S > (kth[:, None] + 1e-4)).sum().item()) <= 8 * (k - 1)

@@ -1,0 +1,185 @@
+"""CPU tests of the host side: file formats and loaders against the reference-generated
+goldens, the class surface, the C ABI (symbols only -- no compute without a GPU), and the
+"no fallback" rule."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import utils
+import topkrec
+import single
+from conftest import ROOT
+
+
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "topkrec.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(tkr_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 12
+    lib = ctypes.CDLL(os.path.join(ROOT, "top-k-rec_b200", "topkrec", "libtopkrec.so"))
+    for name in declared:
+        assert hasattr(lib, name), "libtopkrec.so does not export %s" % name
+    assert topkrec.version() == int(re.search(r"#define TKR_VERSION (\d+)", header).group(1))
+
+
+def test_abi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable here."""
+    L = topkrec.lib()
+    assert L.tkr_bpr_workspace_bytes(None, 256) == 0
+    cfg = topkrec.BprCfg(10, 10, 8)
+    assert L.tkr_bpr_workspace_bytes(cfg.ptr, 256) > 0
+    rc = L.tkr_bpr_step(cfg.ptr, None, None, None, None, None, None, None, None, None, 256, 1, None, 0, None, None, 0, None)
+    assert rc == -1 and b"must not be NULL" in L.tkr_last_error()
+    rc = L.tkr_score_topk(1, 4, 1, 4, 8, None, None, None, 65, 0, 1, 1, None, 0, None)
+    assert rc == -1 and b"k must be in" in L.tkr_last_error()
+    rc = L.tkr_topk_merge(None, None, 2, 4, 5, None, None, None)
+    assert rc == -1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    U = torch.zeros(4, 8); V = torch.zeros(6, 8)
+    with pytest.raises(topkrec.TkrError):
+        topkrec.score_topk(U, V, 3)
+    cfg = topkrec.BprCfg(4, 6, 8)
+    with pytest.raises((topkrec.TkrError, RuntimeError, AssertionError)):
+        topkrec.bpr_workspace(cfg, 16, "cuda")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "top-k-rec_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f
+
+
+# ------------------------------------------------------------------ formats vs reference goldens
+def test_dat_writer_is_byte_identical(golden, tmp_path):
+    emb, back = np.load(os.path.join(golden, "codec.npy"))
+    p = tmp_path / "m" / "x.dat"
+    utils.export_embed_to_file(str(p), emb)
+    assert p.read_bytes() == open(os.path.join(golden, "codec.dat"), "rb").read()
+    assert np.array_equal(utils.get_embed_from_file(str(p)), back)
+    ids = {"a": 2, "b": 0, "c": 1}
+    sub = utils.get_embed_from_file(str(p), ids)
+    assert sub.shape == (3, emb.shape[1]) and np.array_equal(sub, back[:3])
+    assert utils.get_embed_from_file(str(tmp_path / "missing.dat")) is None
+
+
+def test_reference_written_model_reads_back(golden):
+    U = utils.get_embed_from_file(os.path.join(golden, "mini_model_bias", "final-U.dat"))
+    B = utils.get_embed_from_file(os.path.join(golden, "mini_model_bias", "final-B.dat"))
+    assert U.shape == (300, 16) and B.shape == (160, 1) and U.dtype == np.float32
+
+
+def test_loaders_match_reference(golden, mini):
+    g = json.load(open(os.path.join(golden, "loader.json")))
+    m = single.BPR(k=8)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"), data_copy=True)
+    assert (m.n_users, m.n_items, m.epoch_sample_limit) == (g["n_users"], g["n_items"], g["epoch_sample_limit"])
+    assert m.tr_users == g["tr_users"]
+    assert {str(k): v for k, v in m.tr_data.items()} == g["tr_data"]
+    assert len(m.data) == g["epoch_sample_limit"] and isinstance(m.data[0], tuple)
+    assert utils.get_id_dict_from_file("/nonexistent") == {} and utils.get_data_from_file("/nonexistent", {}, {}) == []
+    ivt = utils.get_iv_dict_from_file(os.path.join(mini, "vid"))
+    assert ivt[0] == "1000" and len(ivt) == 160
+
+
+def test_host_sampler_replays_reference_stream(golden, mini):
+    z = np.load(os.path.join(golden, "sampler.npz"))
+    m = single.BPR(k=8)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    np.random.seed(int(z["seed"]))
+    gen = m._uniform_user_sampling(int(z["batch"]))
+    for t in range(z["ub"].shape[0]):
+        ub, ib, jb = next(gen)
+        assert np.array_equal(ub, z["ub"][t]) and np.array_equal(ib, z["ib"][t]) and np.array_equal(jb, z["jb"][t])
+
+
+def test_history_and_csr(mini):
+    browsed, counter = utils.get_history_from_file(os.path.join(mini, "f0tr.txt"))
+    uids = utils.get_id_dict_from_file(os.path.join(mini, "uid"))
+    teids = utils.get_id_dict_from_file(os.path.join(mini, "f0te.im.idl"))
+    indptr, idx = utils.rated_csr(uids, browsed, teids)
+    assert indptr.shape == (301,) and indptr[-1] == idx.shape[0]
+    from oracle import evaluate_ref
+    rp, ri = evaluate_ref.rated_csr(uids, evaluate_ref.load_history(os.path.join(mini, "f0tr.txt")), teids)
+    assert np.array_equal(indptr, rp) and np.array_equal(idx, ri)
+    for r in range(300):
+        seg = idx[indptr[r]:indptr[r + 1]]
+        assert (np.diff(seg) > 0).all()
+    assert sum(counter.values()) > 0
+
+
+def test_positives_csr_sorted(mini):
+    m = single.BPR(k=8)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    indptr, idx = utils.positives_csr(m.tr_users, m.tr_data, m.n_users)
+    for u in m.tr_users:
+        assert sorted(m.tr_data[u]) == idx[indptr[u]:indptr[u + 1]].tolist()
+    assert indptr[-1] == m.epoch_sample_limit
+
+
+def test_class_surface_matches_reference():
+    import inspect
+    sig = inspect.signature(single.BPR.__init__)
+    names = list(sig.parameters)[1:8]
+    assert names == ["k", "lambda_u", "lambda_i", "lambda_j", "lambda_b", "lr", "mode"]
+    d = {n: sig.parameters[n].default for n in names[1:]}
+    assert d == {"lambda_u": 2.5e-3, "lambda_i": 2.5e-3, "lambda_j": 2.5e-4, "lambda_b": 0, "lr": 1.0e-4, "mode": "l2"}
+    t = inspect.signature(single.BPR.train)
+    assert list(t.parameters)[1:] == ["sampling", "epochs", "batch_size", "epoch_sample_limit", "model_path"]
+    assert [t.parameters[n].default for n in list(t.parameters)[1:]] == ["user uniform", 5, 256, None, None]
+    v = inspect.signature(single.VBPR.__init__)
+    assert list(v.parameters)[1:10] == ["k", "d", "lambda_u", "lambda_i", "lambda_j", "lambda_b", "lambda_e", "lr", "mode"]
+    for meth in ("load_training_data", "load_content_data", "build_graph", "train", "export_model", "export_embeddings",
+                 "import_model", "import_embeddings"):
+        assert hasattr(single.REC, meth)
+    m = single.BPR(k=50)
+    for attr in ("fue", "fie", "fib", "uids", "iids", "n_users", "n_items", "tr_data", "tr_users", "epoch_sample_limit",
+                 "k", "lu", "li", "lj", "lb", "lr", "mode"):
+        assert hasattr(m, attr)
+
+
+def test_export_import_embeddings_roundtrip(tmp_path, mini):
+    m = single.BPR(k=4)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    rng = np.random.default_rng(0)
+    m.fue = rng.standard_normal((m.n_users, 4)).astype(np.float32)
+    m.fie = rng.standard_normal((m.n_items, 4)).astype(np.float32)
+    m.fib = rng.standard_normal((m.n_items, 1)).astype(np.float32)
+    out = str(tmp_path / "embed" / "bpr")          # parent missing: we makedirs (superset of D-6)
+    m.export_embeddings(out)
+    assert sorted(os.listdir(out)) == ["final-B.dat", "final-U.dat", "final-V.dat"]
+    m2 = single.BPR(k=4); m2.uids, m2.iids = m.uids, m.iids
+    m2.import_embeddings(out)
+    for a in ("fue", "fie", "fib"):
+        assert np.abs(getattr(m2, a) - getattr(m, a)).max() <= 1e-6
+        assert getattr(m2, a).shape == getattr(m, a).shape
+
+
+def test_load_content_data(tmp_path, mini):
+    import pickle
+    import scipy.sparse as ss
+    m = single.VBPR(k=8, d=6)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    F = ss.random(160, 6, density=0.3, format="lil", dtype=np.float32, random_state=1)
+    p = tmp_path / "meta.pkl"
+    pickle.dump(F, open(p, "wb"))
+    sub = tmp_path / "ids"                           # content rows follow a different id order
+    order = list(reversed(list(m.iids)))[:100]
+    sub.write_text("".join(i + "\n" for i in order))
+    m.load_content_data(str(p), str(sub))
+    dense = F.toarray()
+    for pos, iid in enumerate(order):
+        assert np.array_equal(m.feat[m.iids[iid]], dense[pos])
+    missing = [i for i in m.iids if i not in set(order)]
+    assert all((m.feat[m.iids[i]] == 0).all() for i in missing)

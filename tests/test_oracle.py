@@ -1,0 +1,252 @@
+"""CPU tests: the oracle against the committed golden vectors (tests/golden,
+generated from the reference by tests/golden/make_golden.py) and against
+first-principles checks where the reference offers no pin (the TF step)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bpr_ref, codec_ref, evaluate_ref, philox_ref, sampler_ref, topk_ref
+
+
+# ------------------------------------------------------------------ loader / sampler / codec
+def test_loader_matches_reference(golden, mini):
+    g = json.load(open(os.path.join(golden, "loader.json")))
+    uids = sampler_ref.load_ids(os.path.join(mini, "uid")); iids = sampler_ref.load_ids(os.path.join(mini, "vid"))
+    tr_users, tr_data, n_pos = sampler_ref.load_positives(os.path.join(mini, "f0tr.txt"), uids, iids)
+    assert (len(uids), len(iids), n_pos) == (g["n_users"], g["n_items"], g["epoch_sample_limit"])
+    assert tr_users == g["tr_users"]
+    assert {str(k): v for k, v in tr_data.items()} == g["tr_data"]
+
+
+def test_sampler_replays_reference_stream(golden, mini):
+    z = np.load(os.path.join(golden, "sampler.npz"))
+    uids = sampler_ref.load_ids(os.path.join(mini, "uid")); iids = sampler_ref.load_ids(os.path.join(mini, "vid"))
+    tr_users, tr_data, _ = sampler_ref.load_positives(os.path.join(mini, "f0tr.txt"), uids, iids)
+    rs = np.random.RandomState(int(z["seed"]))
+    ub, ib, jb = sampler_ref.replay_sampler(tr_users, tr_data, len(iids), int(z["batch"]), z["ub"].shape[0], rs)
+    assert np.array_equal(ub, z["ub"]) and np.array_equal(ib, z["ib"]) and np.array_equal(jb, z["jb"])
+
+
+def test_codec_matches_reference_bytes(golden):
+    emb, back = np.load(os.path.join(golden, "codec.npy"))
+    data = open(os.path.join(golden, "codec.dat"), "rb").read()
+    assert codec_ref.dat_bytes(emb) == data
+    assert np.array_equal(codec_ref.dat_parse(data), back)
+    assert np.abs(back - emb)[:5].max() <= 5e-7          # 6-decimal text is lossy
+
+
+# ------------------------------------------------------------------ path 2
+def test_evaluate_matches_reference_script(golden, mini):
+    g = json.load(open(os.path.join(golden, "evaluate_mini.json")))
+    scs = ("im", "om", "all")
+    r = evaluate_ref.evaluate(mini, os.path.join(golden, "mini_model"), scenarios=scs)
+    assert [evaluate_ref.format_line(s, r[s][0]) for s in scs] == g["no_bias"]
+    rb = evaluate_ref.evaluate(mini, os.path.join(golden, "mini_model_bias"), scenarios=("all",))
+    assert [evaluate_ref.format_line("all", rb["all"][0])] == g["bias_all"]
+    lists = np.load(os.path.join(golden, "evaluate_mini_lists.npz"))
+    for s in scs:
+        assert np.array_equal(r[s][1], lists[s])
+
+
+def test_evaluate_tie_rule_is_the_stable_one(golden, mini):
+    """Under exact ties the reference's unstable argsort is implementation-defined (D-12);
+    the oracle is the stable rule and must agree with np.dot + stable argsort."""
+    g = json.load(open(os.path.join(golden, "evaluate_mini.json")))
+    scs = ("im", "om", "all")
+    a = evaluate_ref.evaluate(mini, os.path.join(golden, "mini_model_ties"), scenarios=scs)
+    b = evaluate_ref.evaluate(mini, os.path.join(golden, "mini_model_ties"), scenarios=scs, scorer="blas")
+    assert [evaluate_ref.format_line(s, a[s][0]) for s in scs] == g["ties_oracle_stable"]
+    for s in scs:
+        assert np.array_equal(a[s][1], b[s][1])
+
+
+def test_fold0_numbers_recorded(golden):
+    g = json.load(open(os.path.join(golden, "evaluate_fold0.json")))
+    assert g["oracle_fma"] == g["oracle_blas_stable"]
+    assert g["users_with_different_top30_set_fma_vs_blas"] == {"im": 0, "om": 0}
+    # vs the live script only tie-order effects remain: every printed number within 1 hit of 307053/316588 likes
+    for ours, ref in zip(g["oracle_fma"], g["reference_stdout"]):
+        a = np.array(ours.split(",")[1:], float); b = np.array(ref.split(",")[1:], float)
+        assert np.abs(a - b).max() <= 5e-6
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/data"), reason="shipped fold 0 only exists in the build container")
+def test_fold0_oracle_live(golden):
+    """Re-run the FMA oracle on the real fold 0 (d=50) model of the golden file."""
+    import tempfile
+    g = json.load(open(os.path.join(golden, "evaluate_fold0.json")))
+    data = "/root/reference/data"
+    rng = np.random.default_rng(50)
+    nu = len(sampler_ref.load_ids(os.path.join(data, "uid"))); ni = len(sampler_ref.load_ids(os.path.join(data, "vid")))
+    U0 = (0.1 * rng.standard_normal((nu, 50))).astype(np.float32)
+    V0 = (0.1 * rng.standard_normal((ni, 50))).astype(np.float32)
+    V0[100:110] = V0[99]; V0[500:520] = 0
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "final-U.dat"), "wb").write(codec_ref.dat_bytes(U0))
+        open(os.path.join(td, "final-V.dat"), "wb").write(codec_ref.dat_bytes(V0))
+        r = evaluate_ref.evaluate(data, td, scenarios=("im",))
+    assert evaluate_ref.format_line("im", r["im"][0]) == g["oracle_fma"][0]
+
+
+def test_topk_oracle_semantics():
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal((9, 12)).astype(np.float32); V = rng.standard_normal((40, 12)).astype(np.float32)
+    V[7] = V[3]; V[20] = V[3]; V[11] = 0; V[12] = 0
+    bias = rng.standard_normal(40).astype(np.float32)
+    indptr = np.array([0, 2, 2, 5, 5, 5, 45, 45, 45, 45], np.int64)
+    idx = np.concatenate([[3, 9], [0, 1, 2], np.arange(40)]).astype(np.int32)
+    gi, gs = topk_ref.score_topk(U, V, 10, bias, indptr, idx)
+    ni, ns = topk_ref.score_topk_numpy(U, V, 10, bias, indptr, idx)
+    # fp64 check of the ordering on this small case: same lists as the BLAS+stable-argsort route
+    assert np.array_equal(gi, ni)
+    assert np.allclose(gs[gi >= 0], ns[ni >= 0], atol=1e-5)
+    assert (gi[5] == -1).all() and np.isinf(gs[5]).all()           # every column rated -> empty list
+    assert 3 not in gi[0] and 9 not in gi[0]
+    # ties: equal scores are ordered by column descending
+    for r in range(9):
+        row = gi[r][gi[r] >= 0]
+        sc = gs[r][: len(row)]
+        assert all(sc[p] > sc[p + 1] or (sc[p] == sc[p + 1] and row[p] > row[p + 1]) for p in range(len(row) - 1))
+
+
+def test_topk_merge_equals_unsharded():
+    rng = np.random.default_rng(2)
+    U = rng.standard_normal((17, 8)).astype(np.float32); V = rng.standard_normal((101, 8)).astype(np.float32)
+    V[50] = V[49]; V[100] = V[0]
+    whole = topk_ref.score_topk(U, V, 7)
+    bounds = [0, 30, 64, 101]
+    parts = [topk_ref.score_topk(U, V[a:b], 7, col_offset=a) for a, b in zip(bounds[:-1], bounds[1:])]
+    mi, ms = topk_ref.topk_merge(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
+    assert np.array_equal(mi, whole[0]) and np.array_equal(ms, whole[1])
+
+
+# ------------------------------------------------------------------ path 1 (unpinned: first-principles checks)
+def _objective64(st, u, i, j, cfg):
+    return bpr_ref.bpr_forward(st["U"], st["V"], st["b"], u, i, j, cfg)[1]
+
+
+@pytest.mark.parametrize("mode", ["l2", "l1"])
+def test_bpr_gradients_match_finite_differences(mode):
+    rng = np.random.default_rng(3)
+    nu, ni, k, B = 6, 5, 4, 16
+    st = bpr_ref.new_state(nu, ni, k, rng, np.float64)
+    for n in ("U", "V"):
+        st[n] *= 30.0
+    st["b"] = rng.standard_normal(ni)
+    cfg = bpr_ref.BprCfg(lambda_u=0.03, lambda_i=0.02, lambda_j=0.01, lambda_b=0.05, mode=mode)
+    u = rng.integers(0, nu, B); i = rng.integers(0, ni, B); j = rng.integers(0, ni, B)   # many duplicate rows
+    _, _, gU, gVi, gVj, gbi, gbj = bpr_ref.bpr_occurrence_grads(st["U"], st["V"], st["b"], u, i, j, cfg)
+    rU, GU = bpr_ref.segment_sum(u, gU)
+    ij = np.concatenate([i, j])
+    rV, GV = bpr_ref.segment_sum(ij, np.concatenate([gVi, gVj]))
+    rB, GB = bpr_ref.segment_sum(ij, np.concatenate([gbi, gbj]))
+    eps = 1e-6
+    for name, rows, G in (("U", rU, GU), ("V", rV, GV), ("b", rB, GB)):
+        dense = np.zeros_like(st[name]); dense[rows] = G
+        num = np.zeros_like(st[name])
+        it = np.nditer(st[name], flags=["multi_index"])
+        for _ in it:
+            ix = it.multi_index
+            old = st[name][ix]
+            st[name][ix] = old + eps; fp = _objective64(st, u, i, j, cfg)
+            st[name][ix] = old - eps; fm = _objective64(st, u, i, j, cfg)
+            st[name][ix] = old
+            num[ix] = (fp - fm) / (2 * eps)
+        assert np.abs(num - dense).max() < 1e-6, name
+
+
+def test_bpr_step_hand_computed_duplicates():
+    """Two triples sharing user 0 and item 1: gradients are summed BEFORE the single RMSProp update."""
+    cfg = bpr_ref.BprCfg(lambda_u=0.5, lambda_i=0.25, lambda_j=0.125, lambda_b=0.0, lr=0.1)
+    st = {"U": np.array([[1.0, 2.0]], np.float64), "V": np.array([[0.5, -1.0], [2.0, 0.0], [0.0, 1.0]], np.float64),
+          "b": np.zeros(3)}
+    for n in ("U", "V", "b"):
+        st["ms" + n] = np.ones_like(st[n])
+    u = np.array([0, 0]); i = np.array([1, 1]); j = np.array([0, 2])
+    x0 = (1 * 2 + 2 * 0) - (1 * 0.5 + 2 * -1.0); x1 = 2.0 - 2.0
+    s0, s1 = 1 / (1 + np.exp(x0)), 1 / (1 + np.exp(x1))
+    gU = (-s0 * (st["V"][1] - st["V"][0]) + 0.5 * st["U"][0]) + (-s1 * (st["V"][1] - st["V"][2]) + 0.5 * st["U"][0])
+    gV1 = (-s0 * st["U"][0] + 0.25 * st["V"][1]) + (-s1 * st["U"][0] + 0.25 * st["V"][1])
+    gV0 = s0 * st["U"][0] + 0.125 * st["V"][0]
+    exp_loss = np.log1p(np.exp(-x0)) + np.log1p(np.exp(-x1)) + 0.5 * (2 * 0.5 * 5 + 2 * 0.25 * 4 + 0.125 * 1.25 + 0.125 * 1)
+    U0, V0 = st["U"].copy(), st["V"].copy()
+    loss = bpr_ref.bpr_step(st, u, i, j, cfg)
+    assert abs(loss - exp_loss) < 1e-12
+
+    def upd(v, g):
+        ms = 0.9 + 0.1 * g * g
+        return v - 0.1 * g / np.sqrt(ms + 1e-10), ms
+    assert np.allclose(st["U"][0], upd(U0[0], gU)[0], atol=1e-14) and np.allclose(st["msU"][0], upd(U0[0], gU)[1])
+    assert np.allclose(st["V"][1], upd(V0[1], gV1)[0], atol=1e-14)
+    assert np.allclose(st["V"][0], upd(V0[0], gV0)[0], atol=1e-14)
+    # bias rows: item 1 gets -s0 - s1, items 0 / 2 get +s0 / +s1
+    for r, g in ((0, s0), (1, -(s0 + s1)), (2, s1)):
+        assert abs(st["b"][r] - upd(0.0, g)[0]) < 1e-14
+
+
+def test_bpr_fp32_tracks_fp64_shadow():
+    rng = np.random.default_rng(4)
+    st32 = bpr_ref.new_state(50, 30, 16, rng)
+    st64 = {k: v.astype(np.float64) for k, v in st32.items()}
+    cfg = bpr_ref.BprCfg()
+    u = rng.integers(0, 50, 64 * 20); i = rng.integers(0, 30, 64 * 20); j = rng.integers(0, 30, 64 * 20)
+    l32 = bpr_ref.bpr_train(st32, u, i, j, 64, cfg); l64 = bpr_ref.bpr_train(st64, u, i, j, 64, cfg)
+    assert np.allclose(l32, l64, rtol=1e-5)
+    for n in st32:
+        assert np.abs(st32[n] - st64[n]).max() / np.abs(st64[n]).max() < 1e-5, n
+
+
+@pytest.mark.parametrize("opt,mode", [("rmsprop", "l2"), ("sgd", "l2"), ("rmsprop", "l1")])
+def test_c_oracle_matches_numpy_oracle(opt, mode):
+    import ctypes
+    from oracle import clib
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("n_users", ctypes.c_int32), ("n_items", ctypes.c_int32), ("d", ctypes.c_int32),
+                    ("lu", ctypes.c_float), ("li", ctypes.c_float), ("lj", ctypes.c_float), ("lb", ctypes.c_float),
+                    ("lr", ctypes.c_float), ("l1", ctypes.c_int32), ("sgd", ctypes.c_int32)]
+    rng = np.random.default_rng(5)
+    nu, ni, d, B = 40, 25, 20, 300
+    st = bpr_ref.new_state(nu, ni, d, rng); st["b"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    ref = {k: v.copy() for k, v in st.items()}
+    cfg = bpr_ref.BprCfg(lambda_b=0.01, mode=mode, optimizer=opt)
+    u = rng.integers(0, nu, B).astype(np.int32); i = rng.integers(0, ni, B).astype(np.int32); j = rng.integers(0, ni, B).astype(np.int32)
+    loss_ref = bpr_ref.bpr_step(ref, u, i, j, cfg)
+    c = Cfg(nu, ni, d, cfg.lambda_u, cfg.lambda_i, cfg.lambda_j, cfg.lambda_b, cfg.lr, int(mode != "l2"), int(opt == "sgd"))
+    loss = ctypes.c_double()
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    rc = clib.lib().tkr_ref_bpr_step(ctypes.byref(c), fp(st["U"]), fp(st["V"]), fp(st["b"]), fp(st["msU"]), fp(st["msV"]),
+                                     fp(st["msb"]), fp(u), fp(i), fp(j), ctypes.c_int64(B), ctypes.byref(loss))
+    assert rc == 0 and abs(loss.value - loss_ref) / loss_ref < 1e-5
+    for n in st:
+        assert np.abs(st[n] - ref[n]).max() / np.abs(ref[n]).max() < 2e-6, n
+
+
+# ------------------------------------------------------------------ device sampler oracle (integer work)
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [((0, 0, 0, 0), 0, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, 0xffffffffffffffff, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), 0xa4093822 | (0x299f31d0 << 32),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, out in kat:
+        assert tuple(int(x) for x in philox_ref.philox4x32(np.array([ctr], np.uint32), key)[0]) == out
+
+
+def test_philox_sampler_is_valid_and_uniform(mini):
+    uids = sampler_ref.load_ids(os.path.join(mini, "uid")); iids = sampler_ref.load_ids(os.path.join(mini, "vid"))
+    tr_users, tr_data, _ = sampler_ref.load_positives(os.path.join(mini, "f0tr.txt"), uids, iids)
+    indptr, idx = sampler_ref.to_csr(tr_users, tr_data, len(uids))
+    for uu in tr_users:
+        idx[indptr[uu]:indptr[uu + 1]].sort()
+    u, i, j = philox_ref.sample(tr_users, indptr, idx, len(iids), 99, 0, 4000)
+    assert set(u.tolist()) <= set(tr_users)
+    for a, b, c in zip(u, i, j):
+        assert b in tr_data[a] and c not in tr_data[a] and 0 <= c < len(iids)
+    cnt = np.bincount(u, minlength=len(uids))[tr_users]
+    assert cnt.min() > 0 and cnt.max() < 4 * 4000 / len(tr_users)
+    # order independence: a later window of draws is the same as slicing a longer one
+    u2, i2, j2 = philox_ref.sample(tr_users, indptr, idx, len(iids), 99, 1000, 50)
+    assert np.array_equal(u2, u[1000:1050]) and np.array_equal(i2, i[1000:1050]) and np.array_equal(j2, j[1000:1050])

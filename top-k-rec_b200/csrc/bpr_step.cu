@@ -1,0 +1,404 @@
+// Hot path 1: the synchronous BPR mini-batch step (single/bpr.py:71-101,141 of the
+// reference; TF-1.15 RMSProp semantics per SURVEY.md App. A; SGD per old/methods/bpr.py:57-61).
+//
+// Two kernels per step, both HBM/L2-bandwidth bound (AI ~ 0.33 FLOP/B):
+//   bpr_grad_kernel   one warp per triple: [sample (u,i,j)] -> 128-bit coalesced gather of
+//                     U[u], V[i], V[j] into registers -> warp-shuffle dots -> s = sigma(-x) ->
+//                     per-occurrence regularised gradients, summed into the per-row
+//                     accumulators with vector red.global.add (duplicates summed = the
+//                     unique+segment_sum of TF) -> first toucher appends the row to a list.
+//   bpr_apply_kernel  one warp per touched row: RMSProp/SGD update from the summed gradient,
+//                     re-zeroes the accumulator (the workspace is left clean for the next step).
+// All B gradients are therefore taken at the pre-step snapshot and every touched row gets
+// exactly ONE optimiser update per step.
+#include "common.cuh"
+
+namespace tkr {
+
+struct SamplerDev {
+    const int32_t* tr_users;
+    const int64_t* pos_indptr;
+    const int32_t* pos_idx;
+    uint32_t n_tr_users, n_items, seed_lo, seed_hi;
+};
+
+__device__ __forceinline__ bool is_positive(const int32_t* __restrict__ pos, int n, int item) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(pos + mid) < item) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && __ldg(pos + lo) == item;
+}
+
+// One draw of single/bpr.py:159-164.  Philox counter = (draw_lo, draw_hi, round, 0).
+__device__ __forceinline__ void sample_triple(const SamplerDev& s, uint64_t draw, int& u, int& i, int& j) {
+    uint32_t c[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), 0u, 0u};
+    Philox::run(c, s.seed_lo, s.seed_hi);
+    u = __ldg(s.tr_users + bounded(c[0], s.n_tr_users));
+    const int64_t beg = __ldg(s.pos_indptr + u);
+    const int n = (int)(__ldg(s.pos_indptr + u + 1) - beg);
+    const int32_t* pos = s.pos_idx + beg;
+    i = __ldg(pos + bounded(c[1], (uint32_t)n));
+    j = (int)bounded(c[2], s.n_items);
+    if (!is_positive(pos, n, j)) return;
+    j = (int)bounded(c[3], s.n_items);
+    for (uint32_t round = 1; is_positive(pos, n, j) && round < 64; ++round) {
+        uint32_t r[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), round, 0u};
+        Philox::run(r, s.seed_lo, s.seed_hi);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            j = (int)bounded(r[t], s.n_items);
+            if (!is_positive(pos, n, j)) return;
+        }
+    }
+}
+
+__global__ void sample_kernel(SamplerDev s, uint64_t first_draw, int64_t n, int32_t* __restrict__ u_out,
+                              int32_t* __restrict__ i_out, int32_t* __restrict__ j_out) {
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int u, i, j;
+        sample_triple(s, first_draw + (uint64_t)t, u, i, j);
+        u_out[t] = u; i_out[t] = i; j_out[t] = j;
+    }
+}
+
+// ---- vector helpers: VW floats per lane per chunk (4 = 128-bit, 2 = 64-bit, 1 = scalar) ----
+template <int VW> struct Vec;
+template <> struct Vec<4> {
+    float v[4];
+    __device__ __forceinline__ void load(const float* p) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    __device__ __forceinline__ void red_add(float* p) const {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    }
+};
+template <> struct Vec<2> {
+    float v[2];
+    __device__ __forceinline__ void load(const float* p) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+    __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+    __device__ __forceinline__ void red_add(float* p) const {
+        asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    }
+};
+template <> struct Vec<1> {
+    float v[1];
+    __device__ __forceinline__ void load(const float* p) { v[0] = *p; }
+    __device__ __forceinline__ void store(float* p) const { *p = v[0]; }
+    __device__ __forceinline__ void red_add(float* p) const { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory"); }
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+__device__ __forceinline__ float reg_grad(float x, float lam, bool l1) {
+    return l1 ? lam * (float)((x > 0.f) - (x < 0.f)) : lam * x;
+}
+__device__ __forceinline__ float reg_val(float x, float lam, bool l1) { return l1 ? lam * fabsf(x) : 0.5f * lam * x * x; }
+
+struct StepWs {            // views into the caller's workspace
+    float* GU; float* GV; float* Gb;
+    int32_t* cntU; int32_t* cntV;
+    int32_t* listU; int32_t* listV;
+    int32_t* n_touched;    // [4]: {U,V} x parity
+};
+
+// grid-stride over triples, one warp each.  NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
+template <int VW, int NCH>
+__global__ void __launch_bounds__(256) bpr_grad_kernel(
+    tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
+    const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
+    SamplerDev smp, uint64_t first_draw, StepWs ws, int parity, float* __restrict__ loss_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int d = cfg.d;
+    const bool l1 = cfg.l1 != 0;
+    float loss_acc = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x < 2) ws.n_touched[threadIdx.x * 2 + (parity ^ 1)] = 0;  // arm the next step's counters
+
+    for (int64_t n = warp0; n < B; n += nwarps) {
+        int u, i, j;
+        if (ub != nullptr) {
+            u = __ldg(ub + n); i = __ldg(ib + n); j = __ldg(jb + n);
+        } else {
+            if (lane == 0) sample_triple(smp, first_draw + (uint64_t)n, u, i, j);
+            u = __shfl_sync(0xffffffffu, u, 0); i = __shfl_sync(0xffffffffu, i, 0); j = __shfl_sync(0xffffffffu, j, 0);
+        }
+        const float* pu = U + (int64_t)u * d;
+        const float* pi = V + (int64_t)i * d;
+        const float* pj = V + (int64_t)j * d;
+        Vec<VW> ru[NCH], ri[NCH], rj[NCH];
+        float xi = 0.f, xj = 0.f, reg = 0.f;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int off = (c * 32 + lane) * VW;
+            if (off < d) { ru[c].load(pu + off); ri[c].load(pi + off); rj[c].load(pj + off); }
+            else {
+#pragma unroll
+                for (int t = 0; t < VW; ++t) { ru[c].v[t] = 0.f; ri[c].v[t] = 0.f; rj[c].v[t] = 0.f; }
+            }
+#pragma unroll
+            for (int t = 0; t < VW; ++t) {
+                xi = fmaf(ru[c].v[t], ri[c].v[t], xi);
+                xj = fmaf(ru[c].v[t], rj[c].v[t], xj);
+                reg += reg_val(ru[c].v[t], cfg.lambda_u, l1) + reg_val(ri[c].v[t], cfg.lambda_i, l1) + reg_val(rj[c].v[t], cfg.lambda_j, l1);
+            }
+        }
+        xi = warp_sum(xi); xj = warp_sum(xj); reg = warp_sum(reg);
+        const float bi = __ldg(b + i), bj = __ldg(b + j);
+        const float x = bi - bj + xi - xj;                       // bpr.py:89
+        const float s = 1.0f / (1.0f + expf(x));                 // sigma(-x) = d/dx of -log(1+e^-x)
+        if (lane == 0) {
+            // log(1+e^-x), stable for both signs
+            const float l = (x > 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
+            loss_acc += l + reg + reg_val(bi, cfg.lambda_b, l1) + reg_val(bj, cfg.lambda_b, l1);
+            // first toucher of a row appends it to the step's touched list
+            if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0 + parity, 1)] = u;
+            if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 2 + parity, 1)] = i;
+            if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 2 + parity, 1)] = j;
+            atomicAdd(ws.Gb + i, -s + reg_grad(bi, cfg.lambda_b, l1));
+            atomicAdd(ws.Gb + j, s + reg_grad(bj, cfg.lambda_b, l1));
+        }
+        float* gu = ws.GU + (int64_t)u * d;
+        float* gi = ws.GV + (int64_t)i * d;
+        float* gj = ws.GV + (int64_t)j * d;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int off = (c * 32 + lane) * VW;
+            if (off < d) {
+                Vec<VW> a, p, q;
+#pragma unroll
+                for (int t = 0; t < VW; ++t) {
+                    a.v[t] = -s * (ri[c].v[t] - rj[c].v[t]) + reg_grad(ru[c].v[t], cfg.lambda_u, l1);  // gU   (App. A.2)
+                    p.v[t] = -s * ru[c].v[t] + reg_grad(ri[c].v[t], cfg.lambda_i, l1);                 // gV_i
+                    q.v[t] = s * ru[c].v[t] + reg_grad(rj[c].v[t], cfg.lambda_j, l1);                  // gV_j
+                }
+                a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
+            }
+        }
+    }
+    // block reduction of the loss -> one atomic per block
+    __shared__ float sl[8];
+    if (lane == 0) sl[threadIdx.x >> 5] = loss_acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? sl[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0 && loss_out != nullptr) atomicAdd(loss_out, v);
+    }
+}
+
+template <int VW>
+__device__ __forceinline__ void apply_row(const tkr_bpr_cfg& cfg, float* __restrict__ var, float* __restrict__ ms,
+                                          float* __restrict__ G, int d, int lane) {
+    for (int off = lane * VW; off < d; off += 32 * VW) {
+        Vec<VW> g, v, m, z;
+        g.load(G + off); v.load(var + off);
+        if (cfg.optimizer == TKR_OPT_RMSPROP) {
+            m.load(ms + off);
+#pragma unroll
+            for (int t = 0; t < VW; ++t) {
+                m.v[t] = cfg.rms_decay * m.v[t] + (1.0f - cfg.rms_decay) * g.v[t] * g.v[t];   // App. A.4
+                v.v[t] = v.v[t] - cfg.lr * g.v[t] / sqrtf(m.v[t] + cfg.rms_eps);
+            }
+            m.store(ms + off);
+        } else {
+#pragma unroll
+            for (int t = 0; t < VW; ++t) v.v[t] = v.v[t] - cfg.lr * g.v[t];
+        }
+        v.store(var + off);
+#pragma unroll
+        for (int t = 0; t < VW; ++t) z.v[t] = 0.f;
+        z.store(G + off);
+    }
+}
+
+// warps [0, nU) update touched user rows, warps [nU, nU+nV) touched item rows (+ their bias).
+template <int VW>
+__global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V,
+                                                        float* __restrict__ b, float* __restrict__ msU,
+                                                        float* __restrict__ msV, float* __restrict__ msb, StepWs ws,
+                                                        int parity) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nU = ws.n_touched[0 + parity], nV = ws.n_touched[2 + parity];
+    const int d = cfg.d;
+    for (int64_t w = warp0; w < (int64_t)nU + nV; w += nwarps) {
+        if (w < nU) {
+            const int r = ws.listU[w];
+            apply_row<VW>(cfg, U + (int64_t)r * d, msU + (int64_t)r * d, ws.GU + (int64_t)r * d, d, lane);
+            if (lane == 0) ws.cntU[r] = 0;
+        } else {
+            const int r = ws.listV[w - nU];
+            apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
+            if (lane == 0) {
+                apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0);
+                ws.cntV[r] = 0;
+            }
+        }
+    }
+}
+
+static int carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out) {
+    const size_t need = tkr_bpr_workspace_bytes(cfg, B);
+    if (ws == nullptr || ws_bytes < need) { set_error("bpr workspace too small: have %zu, need %zu", ws_bytes, need); return TKR_ERR_WORKSPACE; }
+    if ((uintptr_t)ws % 256 != 0) { set_error("bpr workspace must be 256-byte aligned"); return TKR_ERR_WORKSPACE; }
+    char* p = (char*)ws;
+    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
+    const size_t d = cfg->d;
+    out->GU = (float*)take((size_t)cfg->n_users * d * 4);
+    out->GV = (float*)take((size_t)cfg->n_items * d * 4);
+    out->Gb = (float*)take((size_t)cfg->n_items * 4);
+    out->cntU = (int32_t*)take((size_t)cfg->n_users * 4);
+    out->cntV = (int32_t*)take((size_t)cfg->n_items * 4);
+    out->n_touched = (int32_t*)take(4 * 4);
+    out->listU = (int32_t*)take((size_t)(B < cfg->n_users ? B : cfg->n_users) * 4);
+    out->listV = (int32_t*)take((size_t)(2 * B < cfg->n_items ? 2 * B : cfg->n_items) * 4);
+    return TKR_OK;
+}
+
+static int check_cfg(const tkr_bpr_cfg* cfg, int64_t B) {
+    TKR_CHECK_ARG(cfg != nullptr, "cfg is NULL");
+    TKR_CHECK_ARG(cfg->n_users > 0 && cfg->n_items > 0 && cfg->d > 0, "n_users, n_items, d must be positive");
+    TKR_CHECK_ARG(B > 0 && B < (int64_t)1 << 31, "batch must be in [1, 2^31)");
+    TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_RMSPROP || cfg->optimizer == TKR_OPT_SGD, "unknown optimizer %d", cfg->optimizer);
+    return TKR_OK;
+}
+
+template <int VW, int NCH>
+static void launch_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                        const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp,
+                        uint64_t first_draw, const StepWs& ws, int parity, float* loss, cudaStream_t st) {
+    const int threads = 256, wpb = threads / 32;
+    // 8 CTAs of 256 threads per SM keep 64 warps resident; cap the grid at the work available
+    int64_t blocks = (B + wpb - 1) / wpb;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    bpr_grad_kernel<VW, NCH><<<(unsigned)blocks, threads, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, parity, loss);
+    int64_t rows = (B < cfg->n_users ? B : cfg->n_users) + (2 * B < cfg->n_items ? 2 * B : cfg->n_items);
+    blocks = (rows + wpb - 1) / wpb;
+    if (blocks > cap) blocks = cap;
+    bpr_apply_kernel<VW><<<(unsigned)blocks, threads, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, parity);
+}
+
+}  // namespace tkr
+
+using namespace tkr;
+
+extern "C" size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t B) {
+    if (cfg == nullptr || B <= 0) return 0;
+    const size_t d = cfg->d;
+    size_t n = 0;
+    n += align_up((size_t)cfg->n_users * d * 4, 256) + align_up((size_t)cfg->n_items * d * 4, 256);
+    n += align_up((size_t)cfg->n_items * 4, 256);
+    n += align_up((size_t)cfg->n_users * 4, 256) + align_up((size_t)cfg->n_items * 4, 256);
+    n += 256;
+    n += align_up((size_t)(B < cfg->n_users ? B : cfg->n_users) * 4, 256);
+    n += align_up((size_t)(2 * B < cfg->n_items ? 2 * B : cfg->n_items) * 4, 256);
+    return n;
+}
+
+extern "C" int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    StepWs v;
+    if (int rc = carve(cfg, B, ws, ws_bytes, &v)) return rc;
+    TKR_CUDA(cudaMemsetAsync(ws, 0, tkr_bpr_workspace_bytes(cfg, B), (cudaStream_t)stream));
+    return TKR_OK;
+}
+
+static int make_sampler(const tkr_sampler* smp, SamplerDev* out) {
+    TKR_CHECK_ARG(smp != nullptr, "sampler is NULL");
+    TKR_CHECK_ARG(smp->tr_users && smp->pos_indptr && smp->pos_idx, "sampler tables are NULL");
+    TKR_CHECK_ARG(smp->n_tr_users > 0 && smp->n_items > 0, "sampler needs n_tr_users > 0 and n_items > 0");
+    out->tr_users = smp->tr_users; out->pos_indptr = smp->pos_indptr; out->pos_idx = smp->pos_idx;
+    out->n_tr_users = (uint32_t)smp->n_tr_users; out->n_items = (uint32_t)smp->n_items;
+    out->seed_lo = (uint32_t)smp->seed; out->seed_hi = (uint32_t)(smp->seed >> 32);
+    return TKR_OK;
+}
+
+extern "C" int tkr_bpr_sample(const tkr_sampler* smp, uint64_t first_draw, int64_t n, int32_t* u_out, int32_t* i_out,
+                              int32_t* j_out, void* stream) {
+    SamplerDev s;
+    if (int rc = make_sampler(smp, &s)) return rc;
+    TKR_CHECK_ARG(n >= 0 && u_out && i_out && j_out, "bad output arguments");
+    if (n == 0) return TKR_OK;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    sample_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(s, first_draw, n, u_out, i_out, j_out);
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
+}
+
+extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                            const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps,
+                            const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes,
+                            void* stream) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    TKR_CHECK_ARG(U && V && b, "U, V, b must not be NULL");
+    TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
+    TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
+    SamplerDev sd = {};
+    if (u == nullptr) {
+        if (int rc = make_sampler(smp, &sd)) return rc;
+        TKR_CHECK_ARG(smp->n_items == cfg->n_items, "sampler n_items != cfg n_items");
+    } else {
+        TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
+    }
+    StepWs w;
+    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    const int d = cfg->d;
+    // widest vector the row pitch allows (rows start at multiples of d floats)
+    const int vw = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;
+    const int nch = (d + 32 * vw - 1) / (32 * vw);
+    if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
+    for (int64_t t = 0; t < n_steps; ++t) {
+        const int32_t* ut = u ? u + t * B : nullptr;
+        const int32_t* it = u ? i + t * B : nullptr;
+        const int32_t* jt = u ? j + t * B : nullptr;
+        float* lt = loss_out ? loss_out + t : nullptr;
+        const uint64_t fd = first_draw + (uint64_t)t * (uint64_t)B;
+        const int par = (int)(t & 1);
+#define TKR_STEP(VW, NCH) launch_step<VW, NCH>(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, sd, fd, w, par, lt, st)
+        const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
+        if (vw == 4) { if (nchp == 1) TKR_STEP(4, 1); else if (nchp == 2) TKR_STEP(4, 2); else if (nchp == 4) TKR_STEP(4, 4); else TKR_STEP(4, 8); }
+        else if (vw == 2) { if (nchp == 1) TKR_STEP(2, 1); else if (nchp == 2) TKR_STEP(2, 2); else if (nchp == 4) TKR_STEP(2, 4); else TKR_STEP(2, 8); }
+        else { if (nchp == 1) TKR_STEP(1, 1); else if (nchp == 2) TKR_STEP(1, 2); else if (nchp == 4) TKR_STEP(1, 4); else TKR_STEP(1, 8); }
+#undef TKR_STEP
+        TKR_LAUNCH_CHECK();
+        count_launch();  // two kernels per step
+    }
+    // an odd number of steps leaves the "next" parity armed as 1; re-arm parity 0 for the next call
+    if (n_steps & 1) TKR_CUDA(cudaMemsetAsync(w.n_touched, 0, 16, st));
+    return TKR_OK;
+}
+
+extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV,
+                                 float* msb, const int32_t* u_host, const int32_t* i_host, const int32_t* j_host,
+                                 int64_t B, int64_t n_steps, float* loss_host, void* staging, size_t staging_bytes,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    TKR_CHECK_ARG(u_host && i_host && j_host && n_steps > 0, "host triples are NULL or n_steps <= 0");
+    const size_t n = (size_t)B * (size_t)n_steps;
+    const size_t need = align_up(n * 4, 256) * 3 + align_up((size_t)n_steps * 4, 256);
+    if (staging == nullptr || staging_bytes < need) { set_error("staging too small: have %zu, need %zu", staging_bytes, need); return TKR_ERR_WORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* p = (char*)staging;
+    int32_t* du = (int32_t*)p; p += align_up(n * 4, 256);
+    int32_t* di = (int32_t*)p; p += align_up(n * 4, 256);
+    int32_t* dj = (int32_t*)p; p += align_up(n * 4, 256);
+    float* dl = (float*)p;
+    TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
+    TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
+    TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
+    if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du, di, dj, B, n_steps, nullptr, 0, dl, ws, ws_bytes, stream)) return rc;
+    if (loss_host != nullptr) TKR_CUDA(cudaMemcpyAsync(loss_host, dl, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, st));
+    TKR_CUDA(cudaStreamSynchronize(st));
+    return TKR_OK;
+}

@@ -1,0 +1,7 @@
+"""Drop-in ``single`` package: the reference's model classes (``single/__init__.py:1-9``)
+on the B200 engine.  ``from single import *`` + ``train.py:3-16`` run unchanged."""
+from .rec import REC
+from .bpr import BPR
+from .vbpr import VBPR
+
+__all__ = ['REC', 'BPR', 'VBPR']

@@ -1,0 +1,229 @@
+"""BPR matrix factorisation on the B200 engine, behind the reference's ``BPR``
+class surface (``single/bpr.py`` of domainxz/top-k-rec).
+
+What the reference does per step (``bpr.py:141``: one ``sess.run`` of the graph
+built in ``bpr.py:71-101``) is one call of ``tkr_bpr_step`` here: gather ->
+sigma(x_ui - x_uj) -> per-occurrence regularised gradients -> duplicates summed ->
+one RMSProp update per touched row, all on the device.  The Python sampler
+(``bpr.py:155-165``) is replaced by a counter-based device sampler fused into
+the same kernel; ``sampler='numpy'`` replays the reference's RNG stream instead
+(slow, for parity runs).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+import topkrec
+from utils import tprint, get_id_dict_from_file, get_data_from_file, positives_csr
+
+from .rec import REC
+
+
+class BPR(REC):
+    def __init__(self, k: int, lambda_u: float = 2.5e-3, lambda_i: float = 2.5e-3, lambda_j: float = 2.5e-4,
+                 lambda_b: float = 0, lr: float = 1.0e-4, mode: str = 'l2', optimizer: str = 'rmsprop',
+                 sampler: str = 'device', seed: int = None, device: str = 'cuda') -> None:
+        self.k = k
+        self.lu, self.li, self.lj, self.lb = lambda_u, lambda_i, lambda_j, lambda_b
+        self.lr = lr
+        self.mode = mode
+        self.optimizer = optimizer            # 'rmsprop' (reference) | 'sgd' (old/methods/bpr.py)
+        self.sampler_backend = sampler        # 'device' (Philox, fused) | 'numpy' (reference RNG replay)
+        self.seed = seed
+        self.device = device
+        self.uids = self.iids = self.data = None
+        self.epoch_sample_limit = None
+        self.n_users = self.n_items = None
+        self.tr_data = self.tr_users = None
+        self.fue = self.fie = self.fib = None
+        self.losses = []                      # per-step batch objective of the last train()
+        self._state = None                    # device tensors U,V,b,msU,msV,msb
+        self._cfg = self._ws = self._ws_batch = self._smp = None
+        self._draws = 0                       # Philox draws consumed so far (checkpointed)
+
+    # ------------------------------------------------------------------ data
+    def load_training_data(self, uid_file: str, iid_file: str, tr_file: str, data_copy: bool = False) -> None:
+        """``bpr.py:51-69``: id maps, positive pairs, user -> positives adjacency."""
+        tprint('Load training data from %s' % tr_file)
+        self.uids = get_id_dict_from_file(uid_file)
+        self.iids = get_id_dict_from_file(iid_file)
+        assert isinstance(self.uids, dict) and isinstance(self.iids, dict)
+        self.n_users, self.n_items = len(self.uids), len(self.iids)
+        assert self.n_users > 0
+        assert self.n_items > 0
+        data = get_data_from_file(tr_file, self.uids, self.iids)
+        self.epoch_sample_limit = len(data)
+        self.tr_data = self._data_to_training_dict(data, self.uids, self.iids)
+        self.tr_users = list(self.tr_data.keys())
+        if data_copy:
+            self.data = data
+        self._smp = None
+        tprint('Loading finished!')
+
+    def _data_to_training_dict(self, data: list, users: dict, items: dict):
+        """user row -> positives in file order (``bpr.py:167-171``)."""
+        adj = defaultdict(list)
+        for uid, iid in data:
+            adj[users[uid]].append(items[iid])
+        return adj
+
+    # ----------------------------------------------------------------- state
+    def _engine_cfg(self):
+        return topkrec.BprCfg(self.n_users, self.n_items, self.k, self.lu, self.li, self.lj, self.lb, self.lr,
+                              self.mode, self.optimizer)
+
+    def build_graph(self):
+        """Allocate and initialise the device state: the counterpart of the
+        variable block of ``bpr.py:71-79`` (U,V ~ N(0, 0.01), b = 0) plus the
+        RMSProp ``rms`` slots (ones)."""
+        dev = torch.device(self.device)
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(int(self.seed) if self.seed is not None else int.from_bytes(os.urandom(7), 'little'))
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = {'U': torch.randn(self.n_users, self.k, generator=gen, **f32) * 0.01,
+              'V': torch.randn(self.n_items, self.k, generator=gen, **f32) * 0.01,
+              'b': torch.zeros(self.n_items, **f32)}
+        for name in ('U', 'V', 'b'):
+            st['ms' + name] = torch.ones_like(st[name])
+        self._state = st
+        self._cfg = self._engine_cfg()
+        self._ws = self._ws_batch = None
+        return st
+
+    def _assign(self, name, value):
+        t = torch.from_numpy(np.ascontiguousarray(value, np.float32)).to(self._state[name].device)
+        assert t.shape == self._state[name].shape, '%s: shape %s != %s' % (name, tuple(t.shape), tuple(self._state[name].shape))
+        self._state[name].copy_(t)
+
+    def _device_sampler(self):
+        if self._smp is None:
+            indptr, idx = positives_csr(self.tr_users, self.tr_data, self.n_users)
+            seed = self.seed if self.seed is not None else int.from_bytes(os.urandom(7), 'little')
+            self._smp = topkrec.Sampler(np.asarray(self.tr_users, np.int32), indptr, idx, self.n_items, seed, self.device)
+        return self._smp
+
+    def _uniform_user_sampling(self, batch_size: int):
+        """The reference's generator (``bpr.py:155-165``), same RNG call order on
+        the global ``np.random`` stream; yields fresh arrays."""
+        users = np.asarray(self.tr_users)
+        member = {u: set(v) for u, v in self.tr_data.items()}
+        while True:
+            ub = users[np.random.randint(0, len(users), batch_size)]
+            ib = np.empty(batch_size, np.int32)
+            jb = np.empty(batch_size, np.int32)
+            for n, u in enumerate(ub.tolist()):
+                pos = self.tr_data[u]
+                ib[n] = pos[np.random.randint(0, len(pos))]
+                neg = np.random.randint(0, self.n_items)
+                while neg in member[u]:
+                    neg = np.random.randint(0, self.n_items)
+                jb[n] = neg
+            yield ub.astype(np.int32), ib, jb
+
+    # ----------------------------------------------------------------- train
+    def train(self, sampling: str = 'user uniform', epochs: int = 5, batch_size: int = 256,
+              epoch_sample_limit: int = None, model_path: str = None):
+        assert isinstance(sampling, str)
+        assert isinstance(epochs, int)
+        assert isinstance(batch_size, int)
+        assert sampling == 'user uniform', "only 'user uniform' sampling exists (bpr.py:115-117)"
+        if epoch_sample_limit is not None:
+            # the shipped train.py passes 10e5 (a float); accept integral floats (SURVEY D-1)
+            assert float(epoch_sample_limit) == int(epoch_sample_limit), 'epoch_sample_limit must be integral'
+            self.epoch_sample_limit = int(epoch_sample_limit)
+        batch_limit = self.epoch_sample_limit // batch_size + 1
+        steps_per_epoch = batch_limit - 1
+        self.build_graph()
+        if model_path is not None:
+            assert isinstance(model_path, str)
+            tprint('Initialize weights with the previous trained model')
+            self.import_embeddings(model_path)
+        tprint('Training parameters: lu=%.6f, li=%.6f, lj=%.6f, lb=%.6f' % (self.lu, self.li, self.lj, self.lb))
+        tprint('Learning rate is %.6f, regularization mode is %s' % (self.lr, self.mode))
+        tprint('Training for %d epochs of %d batches using %s sampler' % (epochs, batch_limit, sampling))
+        if self.fue is not None:
+            tprint('Initialize user embeddings')
+            self._assign('U', self.fue)
+        if self.fie is not None:
+            tprint('Initialize item embeddings')
+            self._assign('V', self.fie)
+        if self.fib is not None:
+            tprint('Initialize item biases')
+            self._assign('b', np.asarray(self.fib).ravel())
+        self.losses = []
+        for eid in range(epochs):
+            t0 = time.time()
+            self._run_steps(steps_per_epoch, batch_size, eid)
+            sys.stderr.write(' ... total time collapse %8.4fs' % (time.time() - t0))
+            sys.stderr.flush()
+            print()
+        st = self._state
+        self.fue = st['U'].cpu().numpy()
+        self.fie = st['V'].cpu().numpy()
+        self.fib = st['b'].cpu().numpy().reshape(-1, 1)
+
+    def _workspace(self, batch_size):
+        if self._ws is None or self._ws_batch != batch_size:
+            self._ws = topkrec.bpr_workspace(self._cfg, batch_size, self.device)
+            self._ws_batch = batch_size
+        return self._ws
+
+    def _run_steps(self, n_steps, batch_size, eid=0):
+        """n_steps engine steps, in chunks so that a loss line can be shown."""
+        st = self._state
+        ws = self._workspace(batch_size)
+        chunk = max(1, min(n_steps, (1 << 20) // batch_size, 4096))
+        host_gen = self._uniform_user_sampling(batch_size) if self.sampler_backend == 'numpy' else None
+        done = 0
+        while done < n_steps:
+            n = min(chunk, n_steps - done)
+            t1 = time.time()
+            if host_gen is None:
+                loss = torch.empty(n, dtype=torch.float32, device=st['U'].device)
+                topkrec.bpr_step(self._cfg, st['U'], st['V'], st['b'], st['msU'], st['msV'], st['msb'], None, None, None,
+                                 batch_size, n, ws, loss, sampler=self._device_sampler(), first_draw=self._draws)
+                self._draws += n * batch_size
+                loss = loss.cpu().numpy()
+            else:
+                trip = [next(host_gen) for _ in range(n)]
+                u, i, j = (torch.from_numpy(np.concatenate([t[c] for t in trip])).pin_memory() for c in range(3))
+                loss_h = torch.empty(n, dtype=torch.float32).pin_memory()
+                staging = torch.empty(3 * (n * batch_size * 4 + 256) + n * 4 + 256, dtype=torch.uint8, device=st['U'].device)
+                topkrec.bpr_step_host(self._cfg, st['U'], st['V'], st['b'], st['msU'], st['msV'], st['msb'], u, i, j,
+                                      batch_size, n, loss_h, staging, ws)
+                loss = loss_h.numpy().copy()
+            dt = time.time() - t1
+            done += n
+            self.losses.extend(loss.tolist())
+            sys.stderr.write('\rEpoch=%3d, batch=%6d, loss=%8.4f, time=%4.4fs' % (eid + 1, done, loss[-1], dt / n))
+        return done
+
+    # ------------------------------------------------------------ checkpoint
+    def _ckpt_path(self, model_path):
+        return os.path.join(model_path, 'weights.npz')
+
+    def import_model(self, model_path: str) -> None:
+        """Restore parameters *and* RMSProp slots (the role of ``Saver.restore``,
+        ``bpr.py:173-177``).  train() then overwrites the parameters with the
+        ``final-*.dat`` values exactly like the reference (``bpr.py:127-135``)."""
+        path = self._ckpt_path(model_path)
+        if os.path.exists(path) and self._state is not None:
+            tprint('Restoring engine state from path %s' % path)
+            with np.load(path) as z:
+                for name in self._state:
+                    if name in z.files and tuple(z[name].shape) == tuple(self._state[name].shape):
+                        self._assign(name, z[name])
+                self._draws = int(z['draws']) if 'draws' in z.files else 0
+
+    def export_model(self, model_path: str) -> None:
+        """Save the engine state (``Saver.save``'s role, ``bpr.py:179-183``)."""
+        if os.path.exists(model_path) and self._state is not None:
+            path = self._ckpt_path(model_path)
+            tprint('Saving engine state to path %s' % path)
+            np.savez(path, draws=np.int64(self._draws), **{n: t.cpu().numpy() for n, t in self._state.items()})

@@ -1,0 +1,9 @@
+"""ctypes binding of libtopkrec.so (the sm_100a engine; ``include/topkrec.h``).
+
+PyTorch is only the carrier of device buffers and the current stream: every
+entry point receives raw ``data_ptr()`` values.  There is no CPU or eager
+fallback -- importing this module without the built library, or calling it
+without a CUDA device, raises.
+"""
+from ._lib import (TkrError, BprCfg, Sampler, lib, version, launch_count, reset_launch_count,  # noqa: F401
+                   bpr_workspace, bpr_step, bpr_step_host, bpr_sample, score_topk, score_topk_host, topk_merge)

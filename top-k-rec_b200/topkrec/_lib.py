@@ -1,0 +1,239 @@
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libtopkrec.so")
+
+
+class TkrError(RuntimeError):
+    pass
+
+
+class tkr_bpr_cfg(C.Structure):
+    _fields_ = [("n_users", C.c_int32), ("n_items", C.c_int32), ("d", C.c_int32),
+                ("lambda_u", C.c_float), ("lambda_i", C.c_float), ("lambda_j", C.c_float), ("lambda_b", C.c_float),
+                ("lr", C.c_float), ("rms_decay", C.c_float), ("rms_eps", C.c_float),
+                ("l1", C.c_int32), ("optimizer", C.c_int32)]
+
+
+class tkr_sampler(C.Structure):
+    _fields_ = [("tr_users", C.c_void_p), ("n_tr_users", C.c_int32), ("pos_indptr", C.c_void_p),
+                ("pos_idx", C.c_void_p), ("n_items", C.c_int32), ("seed", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the library (once).  No fallback: a missing .so is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise TkrError("libtopkrec.so is not built (%s); run `python top-k-rec_b200/build.py` "
+                       "or `python -c 'import __graft_entry__ as g; g.build()'`" % _SO)
+    L = C.CDLL(_SO)
+    vp, i64, i32, u64, sz = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_size_t
+    cfgp, smpp = C.POINTER(tkr_bpr_cfg), C.POINTER(tkr_sampler)
+    L.tkr_version.restype = C.c_int
+    L.tkr_last_error.restype = C.c_char_p
+    L.tkr_launch_count.restype = i64
+    L.tkr_reset_launch_count.restype = None
+    L.tkr_bpr_workspace_bytes.restype = sz; L.tkr_bpr_workspace_bytes.argtypes = [cfgp, i64]
+    L.tkr_bpr_workspace_init.argtypes = [cfgp, i64, vp, sz, vp]
+    L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
+    L.tkr_bpr_step_host.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, vp, vp, sz, vp, sz, vp]
+    L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
+    L.tkr_score_topk_workspace_bytes.restype = sz; L.tkr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32]
+    L.tkr_score_topk.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
+    L.tkr_score_topk_host_device_bytes.restype = sz
+    L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
+    L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
+    L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    for name in ("tkr_bpr_workspace_init", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_score_topk",
+                 "tkr_score_topk_host", "tkr_topk_merge"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise TkrError("libtopkrec error %d: %s" % (rc, lib().tkr_last_error().decode()))
+
+
+def version():
+    return lib().tkr_version()
+
+
+def launch_count():
+    return int(lib().tkr_launch_count())
+
+
+def reset_launch_count():
+    lib().tkr_reset_launch_count()
+
+
+def _dev(t, dtype, name):
+    """Device pointer of a contiguous CUDA tensor of the expected dtype."""
+    if t is None:
+        return None
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise TkrError("%s must be a CUDA tensor (no CPU path exists)" % name)
+    if t.dtype != dtype or not t.is_contiguous():
+        raise TkrError("%s must be contiguous %s, got %s contiguous=%s" % (name, dtype, t.dtype, t.is_contiguous()))
+    return t.data_ptr()
+
+
+def _stream():
+    if not torch.cuda.is_available():
+        raise TkrError("no CUDA device: libtopkrec has no CPU fallback")
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise TkrError("no CUDA device: libtopkrec has no CPU fallback")
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and not t.is_cuda:
+            raise TkrError("got a CPU tensor: libtopkrec has no CPU fallback (move it to the device)")
+
+
+class BprCfg:
+    """Host mirror of tkr_bpr_cfg; defaults are the reference's (single/bpr.py:20)."""
+
+    def __init__(self, n_users, n_items, d, lambda_u=2.5e-3, lambda_i=2.5e-3, lambda_j=2.5e-4, lambda_b=0.0,
+                 lr=1.0e-4, mode="l2", optimizer="rmsprop", rms_decay=0.9, rms_eps=1e-10):
+        if optimizer not in ("rmsprop", "sgd"):
+            raise ValueError("optimizer must be 'rmsprop' or 'sgd'")
+        self.c = tkr_bpr_cfg(int(n_users), int(n_items), int(d), lambda_u, lambda_i, lambda_j, lambda_b, lr,
+                             rms_decay, rms_eps, 0 if mode == "l2" else 1, 0 if optimizer == "rmsprop" else 1)
+
+    @property
+    def ptr(self):
+        return C.byref(self.c)
+
+
+class Sampler:
+    """Device-resident sampler tables (CSR of positives, ascending within a user)."""
+
+    def __init__(self, tr_users, pos_indptr, pos_idx, n_items, seed, device="cuda"):
+        self.tr_users = torch.as_tensor(np.ascontiguousarray(tr_users, np.int32)).to(device)
+        self.pos_indptr = torch.as_tensor(np.ascontiguousarray(pos_indptr, np.int64)).to(device)
+        self.pos_idx = torch.as_tensor(np.ascontiguousarray(pos_idx, np.int32)).to(device)
+        self.c = tkr_sampler(self.tr_users.data_ptr(), int(self.tr_users.numel()), self.pos_indptr.data_ptr(),
+                             self.pos_idx.data_ptr(), int(n_items), int(seed))
+
+    @property
+    def ptr(self):
+        return C.byref(self.c)
+
+
+def bpr_workspace(cfg: BprCfg, batch, device="cuda"):
+    """Allocate and zero the per-step scratch (a uint8 CUDA tensor)."""
+    _need_cuda()
+    n = lib().tkr_bpr_workspace_bytes(cfg.ptr, int(batch))
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(ws.device):
+        _check(lib().tkr_bpr_workspace_init(cfg.ptr, int(batch), ws.data_ptr(), n, _stream()))
+    return ws
+
+
+def bpr_step(cfg: BprCfg, U, V, b, msU, msV, msb, u, i, j, batch, n_steps, ws, loss=None, sampler=None, first_draw=0):
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(U, V, b, ws)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_step(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"),
+                                  _dev(msU, f32, "msU"), _dev(msV, f32, "msV"), _dev(msb, f32, "msb"),
+                                  _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"), int(batch), int(n_steps),
+                                  sampler.ptr if sampler is not None else None, int(first_draw),
+                                  _dev(loss, f32, "loss"), ws.data_ptr(), ws.numel(), _stream()))
+
+
+def bpr_step_host(cfg: BprCfg, U, V, b, msU, msV, msb, u_host, i_host, j_host, batch, n_steps, loss_host, staging, ws):
+    """u/i/j/loss are HOST tensors (pinned for async copies); the sess.run seam."""
+    f32 = torch.float32
+    _need_cuda(U, V, b, ws, staging)
+    for t, nm in ((u_host, "u_host"), (i_host, "i_host"), (j_host, "j_host")):
+        if t.is_cuda or t.dtype != torch.int32 or not t.is_contiguous():
+            raise TkrError("%s must be a contiguous int32 host tensor" % nm)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_step_host(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"),
+                                       _dev(msU, f32, "msU"), _dev(msV, f32, "msV"), _dev(msb, f32, "msb"),
+                                       u_host.data_ptr(), i_host.data_ptr(), j_host.data_ptr(), int(batch), int(n_steps),
+                                       loss_host.data_ptr() if loss_host is not None else None,
+                                       staging.data_ptr(), staging.numel(), ws.data_ptr(), ws.numel(), _stream()))
+
+
+def bpr_sample(sampler: Sampler, first_draw, n, device="cuda"):
+    _need_cuda()
+    u = torch.empty(n, dtype=torch.int32, device=device)
+    i = torch.empty_like(u); j = torch.empty_like(u)
+    with torch.cuda.device(u.device):
+        _check(lib().tkr_bpr_sample(sampler.ptr, int(first_draw), int(n), u.data_ptr(), i.data_ptr(), j.data_ptr(), _stream()))
+    return u, i, j
+
+
+def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset=0, out=None, ws=None):
+    """Device tensors in, device tensors out: (idx int32 [nu,k], score fp32 [nu,k])."""
+    f32 = torch.float32
+    _need_cuda(U, V)
+    nu, d = U.shape
+    ni = V.shape[0]
+    if V.shape[1] != d:
+        raise ValueError("U and V disagree on d")
+    if out is None:
+        out = (torch.empty((nu, k), dtype=torch.int32, device=U.device), torch.empty((nu, k), dtype=f32, device=U.device))
+    need = lib().tkr_score_topk_workspace_bytes(nu, ni, d, k)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=U.device)
+    if rated_indptr is not None and (rated_idx is None or rated_idx.numel() == 0):
+        rated_idx = torch.zeros(1, dtype=torch.int32, device=U.device)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_score_topk(_dev(U, f32, "U"), nu, _dev(V, f32, "V"), ni, d, _dev(bias, f32, "bias"),
+                                    _dev(rated_indptr, torch.int64, "rated_indptr"), _dev(rated_idx, torch.int32, "rated_idx"),
+                                    int(k), int(col_offset), out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel(),
+                                    _stream()))
+    return out
+
+
+def score_topk_host(U, V, k, bias=None, rated_indptr=None, rated_idx=None, dev=None, device="cuda"):
+    """numpy (host) arrays in and out; H2D/D2H copies happen inside the call
+    (the np.dot + np.argsort seam of evaluate.py:78-81)."""
+    _need_cuda()
+    U = np.ascontiguousarray(U, np.float32); V = np.ascontiguousarray(V, np.float32)
+    nu, d = U.shape; ni = V.shape[0]
+    if bias is not None:
+        bias = np.ascontiguousarray(bias, np.float32).ravel()
+    n_rated = 0
+    if rated_indptr is not None:
+        rated_indptr = np.ascontiguousarray(rated_indptr, np.int64)
+        rated_idx = np.ascontiguousarray(rated_idx if rated_idx is not None else np.zeros(0), np.int32)
+        n_rated = int(rated_indptr[-1])
+    need = lib().tkr_score_topk_host_device_bytes(nu, ni, d, k, n_rated)
+    if dev is None or dev.numel() < need:
+        dev = torch.empty(need, dtype=torch.uint8, device=device)
+    out_idx = np.empty((nu, k), np.int32); out_score = np.empty((nu, k), np.float32)
+    p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    with torch.cuda.device(dev.device):
+        _check(lib().tkr_score_topk_host(p(U), nu, p(V), ni, d, p(bias), p(rated_indptr),
+                                         p(rated_idx) if rated_indptr is not None else None,
+                                         int(k), p(out_idx), p(out_score), dev.data_ptr(), dev.numel(), _stream()))
+    return out_idx, out_score
+
+
+def topk_merge(idx, score, out=None):
+    """idx/score: device tensors [n_lists, nu, k] -> merged [nu, k]."""
+    _need_cuda(idx, score)
+    n_lists, nu, k = idx.shape
+    if out is None:
+        out = (torch.empty((nu, k), dtype=torch.int32, device=idx.device), torch.empty((nu, k), dtype=torch.float32, device=idx.device))
+    with torch.cuda.device(idx.device):
+        _check(lib().tkr_topk_merge(_dev(idx, torch.int32, "idx"), _dev(score, torch.float32, "score"), n_lists, nu, k,
+                                    out[0].data_ptr(), out[1].data_ptr(), _stream()))
+    return out
