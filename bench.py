@@ -1,0 +1,388 @@
+#!/usr/bin/env python3
+"""Benchmark of the two hot paths on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline (BASELINE.json configs[1]): BPR synthetic MovieLens-10M shape, 70k users x 10k
+items, d=128, reference optimiser (RMSProp), one "step" = one synchronous mini-batch of
+--batch triples (default 2^20) per GPU.  `value` = triples/s with the triples resident in
+HBM; `e2e` = the same through tkr_bpr_step_host (triples in pinned host memory, H2D + loss
+D2H inside the timed region).  The second path (score + top-30, BASELINE configs[4] slice:
+8192 users x 1M items, d=128) is reported in the same line under "score_topk".
+`--impl reference` times the CPU port of the reference step (oracle/bpr_ref.c, OpenMP, all
+host threads) on the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "top-k-rec_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_USERS, N_ITEMS, D = 70000, 10000, 128
+METRIC = "bpr_triples_per_sec"
+
+
+def algorithmic_bytes_per_triple(d, optimizer="rmsprop"):
+    """read+write 3 param rows and 3 rms rows, 2 biases + 2 bias-rms, 3 ids."""
+    return 48 * d + 44 if optimizer == "rmsprop" else 24 * d + 28
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def synth_interactions(n_users=N_USERS, n_items=N_ITEMS, n_pairs=10_000_000, seed=0):
+    """user ~ uniform, item ~ Zipf(1.0), like w.p. 0.15, dedup per user,
+    every user >= 1 positive.  Returns (tr_users, pos_indptr, pos_idx) with items ascending."""
+    rng = np.random.default_rng(seed)
+    pop = 1.0 / np.arange(1, n_items + 1); pop /= pop.sum()
+    users = rng.integers(0, n_users, n_pairs)
+    items = rng.choice(n_items, n_pairs, p=pop)
+    like = rng.random(n_pairs) < 0.15
+    keys = np.unique(users[like] * n_items + items[like])
+    have = np.zeros(n_users, bool); have[keys // n_items] = True
+    missing = np.nonzero(~have)[0]
+    keys = np.unique(np.concatenate([keys, missing * n_items + rng.choice(n_items, missing.size, p=pop)]))
+    u, it = keys // n_items, (keys % n_items).astype(np.int32)
+    indptr = np.zeros(n_users + 1, np.int64); np.cumsum(np.bincount(u, minlength=n_users), out=indptr[1:])
+    return np.arange(n_users, dtype=np.int32), indptr, it
+
+
+def init_state_np(n_users, n_items, d, seed=1):
+    rng = np.random.default_rng(seed)
+    st = {"U": (0.01 * rng.standard_normal((n_users, d))).astype(np.float32),
+          "V": (0.01 * rng.standard_normal((n_items, d))).astype(np.float32),
+          "b": np.zeros(n_items, np.float32)}
+    for k in ("U", "V", "b"):
+        st["ms" + k] = np.ones_like(st[k])
+    return st
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock + throttle reasons during a timed region (pynvml, 50 ms period)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._stop, self._th = [], set(), None, threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._th = threading.Thread(target=self._run, daemon=True); self._th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._th is not None:
+            self._th.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def profile_traffic(kernel):
+    """DRAM bytes per launch from the committed ncu capture (profiles/traffic.json), else None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(kernel)
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------- CPU port (reference arm / cpu_baseline)
+def cpu_bpr_steps(batch, n_steps, warmup, seed=123):
+    """Time the OpenMP C port of the reference step (oracle/bpr_ref.c) on the C2 workload.
+    Returns (triples_per_sec, ms_per_step, threads)."""
+    import ctypes
+    from oracle import clib
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("n_users", ctypes.c_int32), ("n_items", ctypes.c_int32), ("d", ctypes.c_int32),
+                    ("lu", ctypes.c_float), ("li", ctypes.c_float), ("lj", ctypes.c_float), ("lb", ctypes.c_float),
+                    ("lr", ctypes.c_float), ("l1", ctypes.c_int32), ("sgd", ctypes.c_int32)]
+    lib = clib.lib()
+    st = init_state_np(N_USERS, N_ITEMS, D)
+    rng = np.random.default_rng(seed)
+    pop = 1.0 / np.arange(1, N_ITEMS + 1); pop /= pop.sum()
+    u = rng.integers(0, N_USERS, batch).astype(np.int32)
+    i = rng.choice(N_ITEMS, batch, p=pop).astype(np.int32)
+    j = rng.integers(0, N_ITEMS, batch).astype(np.int32)
+    c = Cfg(N_USERS, N_ITEMS, D, 2.5e-3, 2.5e-3, 2.5e-4, 0.0, 1e-4, 0, 0)
+    loss = ctypes.c_double()
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+    def step():
+        rc = lib.tkr_ref_bpr_step(ctypes.byref(c), fp(st["U"]), fp(st["V"]), fp(st["b"]), fp(st["msU"]), fp(st["msV"]),
+                                  fp(st["msb"]), fp(u), fp(i), fp(j), ctypes.c_int64(batch), ctypes.byref(loss))
+        assert rc == 0
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * n_steps / dt, 1e3 * dt / n_steps, os.cpu_count()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    batch = min(args.batch, 1 << 20)
+    val, ms, threads = cpu_bpr_steps(batch, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "triples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BPR synthetic MovieLens-10M shape (70k users x 10k items), d=128, RMSProp, batch %d" % batch,
+                       "n_users": N_USERS, "n_items": N_ITEMS, "d": D, "batch_size": batch},
+            "cpu_baseline": {"value": val, "unit": "triples/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps of %d triples; OpenMP C port of single/bpr.py:71-101 + TF-1.15 RMSProp "
+                                       "(TensorFlow itself is not installable offline)" % (args.steps, batch)},
+            "e2e": {"value": val, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import topkrec
+    from topkrec import dist as tdist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, K, W = args.batch, args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload (identical on every rank; each rank samples only the users it owns)
+    tr_users, indptr, pos_idx = synth_interactions()
+    mine = tdist.user_partition(tr_users, rank, world)
+    smp = topkrec.Sampler(mine, indptr, pos_idx, N_ITEMS, seed=123, device=dev)
+    st = {k: torch.from_numpy(v).to(dev) for k, v in init_state_np(N_USERS, N_ITEMS, D).items()}
+    cfg = topkrec.BprCfg(N_USERS, N_ITEMS, D)
+    engine = tdist.DataParallelBpr(cfg, st, B)
+    POOL = 16                                   # distinct batches cycled through: 16 * 12 B * B = 201 MB > L2
+    pool = [topkrec.bpr_sample(smp, (rank * POOL + p) * B, B, dev) for p in range(POOL)]
+    loss = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def step(t):
+        u, i, j = pool[t % POOL]
+        engine.step(u, i, j, loss=loss)
+
+    for t in range(W):
+        step(t)
+    barrier()
+    topkrec.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for t in range(K):
+            step(W + t)
+        e1.record()
+        barrier()
+    launches = topkrec.launch_count()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    value = world * B * K / (ms * K / 1e3)
+
+    # ---- e2e: triples in pinned host memory, H2D + step + loss D2H every step
+    hpool = [tuple(x.cpu().pin_memory() for x in pool[p]) for p in range(min(POOL, 4))]
+    staging = torch.empty(4 * (B * 4 + 256), dtype=torch.uint8, device=dev)
+    loss_h = torch.zeros(1, dtype=torch.float32).pin_memory()
+    dstage = [torch.empty(B, dtype=torch.int32, device=dev) for _ in range(3)]
+
+    def e2e_step(t):
+        u, i, j = hpool[t % len(hpool)]
+        if world == 1:
+            topkrec.bpr_step_host(cfg, st["U"], st["V"], st["b"], st["msU"], st["msV"], st["msb"], u, i, j, B, 1, loss_h,
+                                  staging, engine.ws)
+        else:
+            for dst, src in zip(dstage, (u, i, j)):
+                dst.copy_(src, non_blocking=True)
+            loss.zero_()
+            engine.step(*dstage, loss=loss)
+            loss_h.copy_(loss, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for t in range(W):
+        e2e_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(K):
+        e2e_step(t)
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e = {"value": world * B * K / e2e_s, "unit": "triples/s", "h2d_bytes_per_step": 12 * B * world,
+           "d2h_bytes_per_step": 4 * world, "api": "tkr_bpr_step_host (the sess.run seam of single/bpr.py:141)"}
+
+    peaks, peak_src = measured_peaks()
+    abytes = algorithmic_bytes_per_triple(D) * B
+    achieved = abytes / (ms / 1e3) / 1e9
+    line = {"metric": METRIC, "value": value, "unit": "triples/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "BPR synthetic MovieLens-10M shape (70k users x 10k items), d=128, RMSProp, batch %d per GPU" % B,
+                       "n_users": N_USERS, "n_items": N_ITEMS, "d": D, "batch_size": B, "optimizer": "rmsprop",
+                       "parallelism": "dp%d: users partitioned, V/b replicated, all-reduce of item gradients" % world if world > 1 else "single GPU",
+                       "l2": "triple stream cycles through %d pre-sampled batches (%.0f MB) > L2; the %.0f MB of model state "
+                             "is reused every step and may stay L2-resident, as in real training" % (POOL, POOL * 12 * B / 1e6, 2 * 4 * D * (N_USERS + N_ITEMS) / 1e6)},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "bpr_grad_kernel + bpr_apply_kernel (one step)", "achieved": achieved,
+                         "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_launch": abytes, "traffic": profile_traffic("bpr_step")}}
+
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        # bounded CPU sample: ~10-30 s of the OpenMP port on the same workload
+        v1, ms1, threads = cpu_bpr_steps(min(B, 1 << 20), 1, 1)
+        n = int(max(2, min(40, 15e3 / ms1)))
+        v, _, threads = cpu_bpr_steps(min(B, 1 << 20), n, 0)
+        line["cpu_baseline"] = {"value": v, "unit": "triples/s", "cores": threads, "kind": "port",
+                                "sample": "%d steps of %d triples, OpenMP C port (oracle/bpr_ref.c) of single/bpr.py:71-101" % (n, min(B, 1 << 20))}
+    if not args.skip_score:
+        line["score_topk"] = bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src):
+    """score + top-30: 1M items (sharded over the ranks), d=128, user batches of --score-users."""
+    import torch
+    import topkrec
+    from topkrec import dist as tdist
+    NI, k, nb = args.score_items, 30, args.score_users
+    K, W = max(2, min(args.steps, args.score_steps)), 3
+    beg, end = tdist.shard_bounds(NI, world)[rank]
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    Vfull_rows = end - beg
+    V = torch.randn(Vfull_rows, D, device=dev, generator=g) * 0.1
+    gu = torch.Generator(device=dev); gu.manual_seed(3)
+    Ub = [torch.randn(nb, D, device=dev, generator=gu) * 0.1 for _ in range(4)]
+
+    def step(t):
+        return tdist.sharded_score_topk(Ub[t % 4], V, k, beg)
+    for t in range(W):
+        step(t)
+    barrier()
+    topkrec.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(dev.index) as clk:
+        e0.record()
+        for t in range(K):
+            step(t)
+        e1.record()
+        barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / K
+    launches = topkrec.launch_count()
+    flops = 2.0 * nb * NI * D
+    out = {"metric": "scored_users_per_sec_top30", "value": nb / (ms / 1e3), "unit": "users/s", "ms_per_step": ms, "steps": K,
+           "config": {"workload": "score + top-30, %d users/step x %d items, d=%d, item-sharded over %d GPU(s); V (%.0f MB/GPU) > L2 per step"
+                                  % (nb, NI, D, world, Vfull_rows * D * 4 / 1e6)},
+           "dtype": "f32 (exact fma-chain scores, CUDA cores)", "gpu_launches": launches, "clocks": clk.summary(),
+           "roofline": {"bound": "tensor", "kernel": "score_topk_kernel", "achieved": flops / (ms / 1e3) / 1e12,
+                        "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
+                        "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
+                        "note": "exact fp32 engine runs on the CUDA cores (fp32 FMA peak ~75 TFLOP/s), not tcgen05"}}
+    if world == 1:
+        # e2e: host U batch + host V (copied once per pass of K batches) -> device -> lists back on the host
+        Vh = V.cpu().pin_memory(); Uh = [u.cpu().pin_memory() for u in Ub]
+        oi = torch.empty((nb, k), dtype=torch.int32).pin_memory(); os_ = torch.empty((nb, k), dtype=torch.float32).pin_memory()
+        Vd = torch.empty_like(V); Ud = torch.empty_like(Ub[0])
+        barrier()
+        t0 = time.perf_counter()
+        Vd.copy_(Vh, non_blocking=True)
+        for t in range(K):
+            Ud.copy_(Uh[t % 4], non_blocking=True)
+            gi, gs = topkrec.score_topk(Ud, Vd, k)
+            oi.copy_(gi, non_blocking=True); os_.copy_(gs, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        dt = time.perf_counter() - t0
+        out["e2e"] = {"value": nb * K / dt, "unit": "users/s", "h2d_bytes_per_step": nb * D * 4 + Vfull_rows * D * 4 // K,
+                      "d2h_bytes_per_step": nb * k * 8, "api": "evaluate.py flow: V copied once per pass, U batch + lists per step"}
+        if rank == 0 and not args.skip_cpu:
+            from oracle import topk_ref
+            nsamp = 64
+            Un, Vn = Ub[0][:nsamp].cpu().numpy(), V.cpu().numpy()
+            t0 = time.perf_counter()
+            S = np.dot(Un, Vn.T); np.argsort(S, axis=1)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nsamp / dt, "unit": "users/s", "cores": os.cpu_count(), "kind": "reference",
+                                   "sample": "np.dot + np.argsort (evaluate.py:78,81 verbatim) on %d users x %d items" % (nsamp, NI)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1 << 20)
+    ap.add_argument("--score-users", type=int, default=8192)
+    ap.add_argument("--score-items", type=int, default=1 << 20)
+    ap.add_argument("--score-steps", type=int, default=5)
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-score", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        print("bench.py: --gpus %d needs torchrun (WORLD_SIZE=%d); running 1 GPU" % (args.gpus, world), file=sys.stderr)
+    args.warmup = max(args.warmup, 3)
+    run_ours(args, rank, local, world)
+
+
+if __name__ == "__main__":
+    main()

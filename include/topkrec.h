@@ -79,6 +79,38 @@ typedef struct tkr_sampler {
 size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t batch);
 int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes, void* stream);
 
+/* Byte offsets of the workspace regions, for callers that exchange gradients
+ * between devices (data-parallel training): offsets[TKR_WS_*]. The fp32 region
+ * [GV | Gb | TCHV] is contiguous ((n_items*d + 2*n_items) floats from offsets[TKR_WS_GV]). */
+#define TKR_WS_GU 0
+#define TKR_WS_CNTU 1
+#define TKR_WS_LISTU 2
+#define TKR_WS_NTOUCHED 3
+#define TKR_WS_GV 4
+#define TKR_WS_GB 5
+#define TKR_WS_TCHV 6
+#define TKR_WS_CNTV 7
+#define TKR_WS_LISTV 8
+#define TKR_WS_TOTAL 9
+#define TKR_WS_NFIELDS 10
+int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t batch, int64_t* offsets);
+
+/* The two halves of a step, for data-parallel training: users are
+ * partitioned across ranks (U rows never exchanged), V/b replicated.
+ *   tkr_bpr_grad   gathers + accumulates the summed per-row gradients of `batch` triples
+ *                  into the workspace (loss added to *loss_out, which the caller zeroes);
+ *   -- with data_parallel != 0 the caller now all-reduces (sum) the contiguous fp32
+ *      region [GV | Gb | TCHV] across ranks --
+ *   tkr_bpr_apply  one optimiser update per touched row; with data_parallel != 0 item
+ *                  rows are those whose summed occurrence count TCHV is non-zero, so
+ *                  every replica applies the identical update.
+ * tkr_bpr_step == tkr_bpr_grad + tkr_bpr_apply with data_parallel = 0. */
+int tkr_bpr_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                 const int32_t* i, const int32_t* j, int64_t batch, const tkr_sampler* smp, uint64_t first_draw,
+                 float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream);
+int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                  int64_t batch, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream);
+
 /* n_steps consecutive synchronous mini-batch steps.  Step t uses triples
  * [t*batch, (t+1)*batch) of u/i/j and writes the batch objective evaluated
  * before the update to loss_out[t] (what sess.run returns for `obj`).

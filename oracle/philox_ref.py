@@ -17,6 +17,7 @@ import numpy as np
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
 MASK = np.uint64(0xFFFFFFFF)
+MAX_ROUNDS = 1024      # kMaxSampleRounds of the CUDA sampler
 
 
 def philox4x32(counter, seed):
@@ -52,7 +53,7 @@ def sample(tr_users, pos_indptr, pos_idx, n_items, seed, first_draw, n):
         pick = next((c for c in cands if c not in pos), None)
         rnd = 1
         last = cands[-1]
-        while pick is None and rnd < 64:
+        while pick is None and rnd < MAX_ROUNDS:
             cc = ctr[t:t + 1].copy(); cc[0, 2] = rnd
             rr = philox4x32(cc, seed)[0]
             for w in rr:

@@ -31,6 +31,10 @@ __device__ __forceinline__ bool is_positive(const int32_t* __restrict__ pos, int
     return lo < n && __ldg(pos + lo) == item;
 }
 
+// The reference redraws the negative forever (bpr.py:163-164); we stop after 2 + 4*(kMaxSampleRounds-1)
+// candidates (only reachable when a user likes essentially every item) and keep the last one.
+constexpr uint32_t kMaxSampleRounds = 1024;
+
 // One draw of single/bpr.py:159-164.  Philox counter = (draw_lo, draw_hi, round, 0).
 __device__ __forceinline__ void sample_triple(const SamplerDev& s, uint64_t draw, int& u, int& i, int& j) {
     uint32_t c[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), 0u, 0u};
@@ -43,7 +47,7 @@ __device__ __forceinline__ void sample_triple(const SamplerDev& s, uint64_t draw
     j = (int)bounded(c[2], s.n_items);
     if (!is_positive(pos, n, j)) return;
     j = (int)bounded(c[3], s.n_items);
-    for (uint32_t round = 1; is_positive(pos, n, j) && round < 64; ++round) {
+    for (uint32_t round = 1; is_positive(pos, n, j) && round < kMaxSampleRounds; ++round) {
         uint32_t r[4] = {(uint32_t)draw, (uint32_t)(draw >> 32), round, 0u};
         Philox::run(r, s.seed_lo, s.seed_hi);
 #pragma unroll
@@ -101,9 +105,10 @@ __device__ __forceinline__ float reg_val(float x, float lam, bool l1) { return l
 
 struct StepWs {            // views into the caller's workspace
     float* GU; float* GV; float* Gb;
+    float* tchV;           // data-parallel mode: per-item occurrence count as fp32 (all-reduced with GV|Gb)
     int32_t* cntU; int32_t* cntV;
     int32_t* listU; int32_t* listV;
-    int32_t* n_touched;    // [4]: {U,V} x parity
+    int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
 };
 
 // grid-stride over triples, one warp each.  NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
@@ -111,14 +116,13 @@ template <int VW, int NCH>
 __global__ void __launch_bounds__(256) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
-    SamplerDev smp, uint64_t first_draw, StepWs ws, int parity, float* __restrict__ loss_out) {
+    SamplerDev smp, uint64_t first_draw, StepWs ws, int dp, float* __restrict__ loss_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d = cfg.d;
     const bool l1 = cfg.l1 != 0;
     float loss_acc = 0.f;
-    if (blockIdx.x == 0 && threadIdx.x < 2) ws.n_touched[threadIdx.x * 2 + (parity ^ 1)] = 0;  // arm the next step's counters
 
     for (int64_t n = warp0; n < B; n += nwarps) {
         int u, i, j;
@@ -157,9 +161,14 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
             const float l = (x > 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
             loss_acc += l + reg + reg_val(bi, cfg.lambda_b, l1) + reg_val(bj, cfg.lambda_b, l1);
             // first toucher of a row appends it to the step's touched list
-            if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0 + parity, 1)] = u;
-            if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 2 + parity, 1)] = i;
-            if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 2 + parity, 1)] = j;
+            if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0, 1)] = u;
+            if (dp) {   // item rows are found after the all-reduce from the summed occurrence counts
+                atomicAdd(ws.tchV + i, 1.0f);
+                atomicAdd(ws.tchV + j, 1.0f);
+            } else {
+                if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
+                if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
+            }
             atomicAdd(ws.Gb + i, -s + reg_grad(bi, cfg.lambda_b, l1));
             atomicAdd(ws.Gb + j, s + reg_grad(bj, cfg.lambda_b, l1));
         }
@@ -218,15 +227,17 @@ __device__ __forceinline__ void apply_row(const tkr_bpr_cfg& cfg, float* __restr
 }
 
 // warps [0, nU) update touched user rows, warps [nU, nU+nV) touched item rows (+ their bias).
+// dp != 0: item rows are all rows r with tchV[r] > 0 (dense scan over n_items).
+// The last block to finish re-arms the touched counters (no extra launch, no parity games).
 template <int VW>
 __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V,
                                                         float* __restrict__ b, float* __restrict__ msU,
                                                         float* __restrict__ msV, float* __restrict__ msb, StepWs ws,
-                                                        int parity) {
+                                                        int dp) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int nU = ws.n_touched[0 + parity], nV = ws.n_touched[2 + parity];
+    const int nU = ws.n_touched[0], nV = dp ? cfg.n_items : ws.n_touched[1];
     const int d = cfg.d;
     for (int64_t w = warp0; w < (int64_t)nU + nV; w += nwarps) {
         if (w < nU) {
@@ -234,31 +245,61 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
             apply_row<VW>(cfg, U + (int64_t)r * d, msU + (int64_t)r * d, ws.GU + (int64_t)r * d, d, lane);
             if (lane == 0) ws.cntU[r] = 0;
         } else {
-            const int r = ws.listV[w - nU];
+            int r;
+            if (dp) {
+                r = (int)(w - nU);
+                if (ws.tchV[r] == 0.0f) continue;
+            } else {
+                r = ws.listV[w - nU];
+            }
             apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
+            __syncwarp();
             if (lane == 0) {
                 apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0);
-                ws.cntV[r] = 0;
+                if (dp) ws.tchV[r] = 0.0f; else ws.cntV[r] = 0;
             }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ws.n_touched + 2, 1) == (int)gridDim.x - 1) {
+            ws.n_touched[0] = 0; ws.n_touched[1] = 0; ws.n_touched[2] = 0;
         }
     }
 }
 
+struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, total; };
+
+static WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
+    WsLayout L;
+    const size_t d = cfg->d, nu = cfg->n_users, ni = cfg->n_items;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+    L.GU = take(nu * d * 4);
+    L.cntU = take(nu * 4);
+    L.listU = take((size_t)(B < (int64_t)nu ? B : (int64_t)nu) * 4);
+    L.n_touched = take(16);
+    // [GV | Gb | tchV] is one contiguous fp32 region: a single all-reduce covers it in data-parallel mode
+    L.GV = o; o += ni * d * 4;
+    L.Gb = o; o += ni * 4;
+    L.tchV = o; o += ni * 4;
+    o = align_up(o, 256);
+    L.cntV = take(ni * 4);
+    L.listV = take((size_t)(2 * B < (int64_t)ni ? 2 * B : (int64_t)ni) * 4);
+    L.total = o;
+    return L;
+}
+
 static int carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out) {
-    const size_t need = tkr_bpr_workspace_bytes(cfg, B);
-    if (ws == nullptr || ws_bytes < need) { set_error("bpr workspace too small: have %zu, need %zu", ws_bytes, need); return TKR_ERR_WORKSPACE; }
+    const WsLayout L = ws_layout(cfg, B);
+    if (ws == nullptr || ws_bytes < L.total) { set_error("bpr workspace too small: have %zu, need %zu", ws_bytes, L.total); return TKR_ERR_WORKSPACE; }
     if ((uintptr_t)ws % 256 != 0) { set_error("bpr workspace must be 256-byte aligned"); return TKR_ERR_WORKSPACE; }
     char* p = (char*)ws;
-    auto take = [&](size_t bytes) { char* r = p; p += align_up(bytes, 256); return r; };
-    const size_t d = cfg->d;
-    out->GU = (float*)take((size_t)cfg->n_users * d * 4);
-    out->GV = (float*)take((size_t)cfg->n_items * d * 4);
-    out->Gb = (float*)take((size_t)cfg->n_items * 4);
-    out->cntU = (int32_t*)take((size_t)cfg->n_users * 4);
-    out->cntV = (int32_t*)take((size_t)cfg->n_items * 4);
-    out->n_touched = (int32_t*)take(4 * 4);
-    out->listU = (int32_t*)take((size_t)(B < cfg->n_users ? B : cfg->n_users) * 4);
-    out->listV = (int32_t*)take((size_t)(2 * B < cfg->n_items ? 2 * B : cfg->n_items) * 4);
+    out->GU = (float*)(p + L.GU); out->GV = (float*)(p + L.GV); out->Gb = (float*)(p + L.Gb); out->tchV = (float*)(p + L.tchV);
+    out->cntU = (int32_t*)(p + L.cntU); out->cntV = (int32_t*)(p + L.cntV);
+    out->n_touched = (int32_t*)(p + L.n_touched);
+    out->listU = (int32_t*)(p + L.listU); out->listV = (int32_t*)(p + L.listV);
     return TKR_OK;
 }
 
@@ -270,20 +311,43 @@ static int check_cfg(const tkr_bpr_cfg* cfg, int64_t B) {
     return TKR_OK;
 }
 
+static inline int64_t grid_cap() { return (int64_t)kNumSMs * 8; }   // 8 CTAs x 8 warps = 64 resident warps per SM
+
 template <int VW, int NCH>
-static void launch_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
-                        const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp,
-                        uint64_t first_draw, const StepWs& ws, int parity, float* loss, cudaStream_t st) {
-    const int threads = 256, wpb = threads / 32;
-    // 8 CTAs of 256 threads per SM keep 64 warps resident; cap the grid at the work available
-    int64_t blocks = (B + wpb - 1) / wpb;
-    const int64_t cap = (int64_t)kNumSMs * 8;
-    if (blocks > cap) blocks = cap;
-    bpr_grad_kernel<VW, NCH><<<(unsigned)blocks, threads, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, parity, loss);
-    int64_t rows = (B < cfg->n_users ? B : cfg->n_users) + (2 * B < cfg->n_items ? 2 * B : cfg->n_items);
-    blocks = (rows + wpb - 1) / wpb;
-    if (blocks > cap) blocks = cap;
-    bpr_apply_kernel<VW><<<(unsigned)blocks, threads, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, parity);
+static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                        const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
+                        const StepWs& ws, int dp, float* loss, cudaStream_t st) {
+    int64_t blocks = (B + 7) / 8;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    bpr_grad_kernel<VW, NCH><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, dp, loss);
+}
+
+static void launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                         int64_t B, const StepWs& ws, int dp, cudaStream_t st) {
+    const int d = cfg->d;
+    int64_t rows = (B < cfg->n_users ? B : cfg->n_users) + ((dp || 2 * B > cfg->n_items) ? cfg->n_items : 2 * B);
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > grid_cap()) blocks = grid_cap();
+    if (d % 4 == 0) bpr_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
+    else if (d % 2 == 0) bpr_apply_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
+    else bpr_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
+}
+
+static int dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                         const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
+                         const StepWs& ws, int dp, float* loss, cudaStream_t st) {
+    const int d = cfg->d;
+    const int vw = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;   // widest vector the row pitch allows
+    const int nch = (d + 32 * vw - 1) / (32 * vw);
+    if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
+    const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
+#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, dp, loss, st)
+    if (vw == 4) { if (nchp == 1) TKR_GRAD(4, 1); else if (nchp == 2) TKR_GRAD(4, 2); else if (nchp == 4) TKR_GRAD(4, 4); else TKR_GRAD(4, 8); }
+    else if (vw == 2) { if (nchp == 1) TKR_GRAD(2, 1); else if (nchp == 2) TKR_GRAD(2, 2); else if (nchp == 4) TKR_GRAD(2, 4); else TKR_GRAD(2, 8); }
+    else { if (nchp == 1) TKR_GRAD(1, 1); else if (nchp == 2) TKR_GRAD(1, 2); else if (nchp == 4) TKR_GRAD(1, 4); else TKR_GRAD(1, 8); }
+#undef TKR_GRAD
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
 }
 
 }  // namespace tkr
@@ -291,23 +355,24 @@ static void launch_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, fl
 using namespace tkr;
 
 extern "C" size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t B) {
-    if (cfg == nullptr || B <= 0) return 0;
-    const size_t d = cfg->d;
-    size_t n = 0;
-    n += align_up((size_t)cfg->n_users * d * 4, 256) + align_up((size_t)cfg->n_items * d * 4, 256);
-    n += align_up((size_t)cfg->n_items * 4, 256);
-    n += align_up((size_t)cfg->n_users * 4, 256) + align_up((size_t)cfg->n_items * 4, 256);
-    n += 256;
-    n += align_up((size_t)(B < cfg->n_users ? B : cfg->n_users) * 4, 256);
-    n += align_up((size_t)(2 * B < cfg->n_items ? 2 * B : cfg->n_items) * 4, 256);
-    return n;
+    if (cfg == nullptr || B <= 0 || cfg->n_users <= 0 || cfg->n_items <= 0 || cfg->d <= 0) return 0;
+    return ws_layout(cfg, B).total;
+}
+
+extern "C" int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t B, int64_t* offsets) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    TKR_CHECK_ARG(offsets != nullptr, "offsets is NULL");
+    const WsLayout L = ws_layout(cfg, B);
+    const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.total};
+    for (int t = 0; t < TKR_WS_NFIELDS; ++t) offsets[t] = (int64_t)v[t];
+    return TKR_OK;
 }
 
 extern "C" int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = check_cfg(cfg, B)) return rc;
     StepWs v;
     if (int rc = carve(cfg, B, ws, ws_bytes, &v)) return rc;
-    TKR_CUDA(cudaMemsetAsync(ws, 0, tkr_bpr_workspace_bytes(cfg, B), (cudaStream_t)stream));
+    TKR_CUDA(cudaMemsetAsync(ws, 0, ws_layout(cfg, B).total, (cudaStream_t)stream));
     return TKR_OK;
 }
 
@@ -334,12 +399,47 @@ extern "C" int tkr_bpr_sample(const tkr_sampler* smp, uint64_t first_draw, int64
     return TKR_OK;
 }
 
+static int check_state(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b) {
+    TKR_CHECK_ARG(U && V && b, "U, V, b must not be NULL");
+    (void)cfg;
+    return TKR_OK;
+}
+
+extern "C" int tkr_bpr_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                            const int32_t* i, const int32_t* j, int64_t B, const tkr_sampler* smp, uint64_t first_draw,
+                            float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = check_state(cfg, U, V, b)) return rc;
+    SamplerDev sd = {};
+    if (u == nullptr) {
+        if (int rc = make_sampler(smp, &sd)) return rc;
+        TKR_CHECK_ARG(smp->n_items == cfg->n_items, "sampler n_items != cfg n_items");
+    } else {
+        TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
+    }
+    StepWs w;
+    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    return dispatch_grad(cfg, U, V, b, u, i, j, B, sd, first_draw, w, data_parallel ? 1 : 0, loss_out, (cudaStream_t)stream);
+}
+
+extern "C" int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                             int64_t B, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
+    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = check_state(cfg, U, V, b)) return rc;
+    TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
+    StepWs w;
+    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    launch_apply(cfg, U, V, b, msU, msV, msb, B, w, data_parallel ? 1 : 0, (cudaStream_t)stream);
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
+}
+
 extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                             const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps,
                             const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes,
                             void* stream) {
     if (int rc = check_cfg(cfg, B)) return rc;
-    TKR_CHECK_ARG(U && V && b, "U, V, b must not be NULL");
+    if (int rc = check_state(cfg, U, V, b)) return rc;
     TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
     TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
     SamplerDev sd = {};
@@ -351,11 +451,6 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     }
     StepWs w;
     if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
-    const int d = cfg->d;
-    // widest vector the row pitch allows (rows start at multiples of d floats)
-    const int vw = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;
-    const int nch = (d + 32 * vw - 1) / (32 * vw);
-    if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
     cudaStream_t st = (cudaStream_t)stream;
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     for (int64_t t = 0; t < n_steps; ++t) {
@@ -363,19 +458,10 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
         const int32_t* it = u ? i + t * B : nullptr;
         const int32_t* jt = u ? j + t * B : nullptr;
         float* lt = loss_out ? loss_out + t : nullptr;
-        const uint64_t fd = first_draw + (uint64_t)t * (uint64_t)B;
-        const int par = (int)(t & 1);
-#define TKR_STEP(VW, NCH) launch_step<VW, NCH>(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, sd, fd, w, par, lt, st)
-        const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
-        if (vw == 4) { if (nchp == 1) TKR_STEP(4, 1); else if (nchp == 2) TKR_STEP(4, 2); else if (nchp == 4) TKR_STEP(4, 4); else TKR_STEP(4, 8); }
-        else if (vw == 2) { if (nchp == 1) TKR_STEP(2, 1); else if (nchp == 2) TKR_STEP(2, 2); else if (nchp == 4) TKR_STEP(2, 4); else TKR_STEP(2, 8); }
-        else { if (nchp == 1) TKR_STEP(1, 1); else if (nchp == 2) TKR_STEP(1, 2); else if (nchp == 4) TKR_STEP(1, 4); else TKR_STEP(1, 8); }
-#undef TKR_STEP
+        if (int rc = dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, 0, lt, st)) return rc;
+        launch_apply(cfg, U, V, b, msU, msV, msb, B, w, 0, st);
         TKR_LAUNCH_CHECK();
-        count_launch();  // two kernels per step
     }
-    // an odd number of steps leaves the "next" parity armed as 1; re-arm parity 0 for the next call
-    if (n_steps & 1) TKR_CUDA(cudaMemsetAsync(w.n_touched, 0, 16, st));
     return TKR_OK;
 }
 

@@ -46,6 +46,9 @@ def lib():
     L.tkr_reset_launch_count.restype = None
     L.tkr_bpr_workspace_bytes.restype = sz; L.tkr_bpr_workspace_bytes.argtypes = [cfgp, i64]
     L.tkr_bpr_workspace_init.argtypes = [cfgp, i64, vp, sz, vp]
+    L.tkr_bpr_workspace_layout.argtypes = [cfgp, i64, C.POINTER(C.c_int64)]
+    L.tkr_bpr_grad.argtypes = [cfgp] + [vp] * 3 + [vp] * 3 + [i64, smpp, u64, vp, vp, sz, i32, vp]
+    L.tkr_bpr_apply.argtypes = [cfgp] + [vp] * 6 + [i64, vp, sz, i32, vp]
     L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
     L.tkr_bpr_step_host.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, vp, vp, sz, vp, sz, vp]
     L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
@@ -55,7 +58,7 @@ def lib():
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
-    for name in ("tkr_bpr_workspace_init", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_score_topk",
+    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_score_topk",
                  "tkr_score_topk_host", "tkr_topk_merge"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -142,6 +145,42 @@ def bpr_workspace(cfg: BprCfg, batch, device="cuda"):
     with torch.cuda.device(ws.device):
         _check(lib().tkr_bpr_workspace_init(cfg.ptr, int(batch), ws.data_ptr(), n, _stream()))
     return ws
+
+
+WS_FIELDS = ("GU", "cntU", "listU", "n_touched", "GV", "Gb", "tchV", "cntV", "listV", "total")
+
+
+def bpr_workspace_layout(cfg: BprCfg, batch):
+    """Byte offsets of the workspace regions (include/topkrec.h, TKR_WS_*)."""
+    off = (C.c_int64 * len(WS_FIELDS))()
+    _check(lib().tkr_bpr_workspace_layout(cfg.ptr, int(batch), off))
+    return dict(zip(WS_FIELDS, (int(x) for x in off)))
+
+
+def bpr_item_grad_view(cfg: BprCfg, batch, ws):
+    """fp32 view of the contiguous [GV | Gb | tchV] region: what data-parallel training all-reduces."""
+    lay = bpr_workspace_layout(cfg, batch)
+    n = cfg.c.n_items * cfg.c.d + 2 * cfg.c.n_items
+    return ws[lay["GV"]:lay["GV"] + 4 * n].view(torch.float32)
+
+
+def bpr_grad(cfg: BprCfg, U, V, b, u, i, j, batch, ws, loss=None, sampler=None, first_draw=0, data_parallel=False):
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(U, V, b, ws)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_grad(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"),
+                                  _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"), int(batch),
+                                  sampler.ptr if sampler is not None else None, int(first_draw), _dev(loss, f32, "loss"),
+                                  ws.data_ptr(), ws.numel(), int(bool(data_parallel)), _stream()))
+
+
+def bpr_apply(cfg: BprCfg, U, V, b, msU, msV, msb, batch, ws, data_parallel=False):
+    f32 = torch.float32
+    _need_cuda(U, V, b, ws)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_apply(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"),
+                                   _dev(msU, f32, "msU"), _dev(msV, f32, "msV"), _dev(msb, f32, "msb"), int(batch),
+                                   ws.data_ptr(), ws.numel(), int(bool(data_parallel)), _stream()))
 
 
 def bpr_step(cfg: BprCfg, U, V, b, msU, msV, msb, u, i, j, batch, n_steps, ws, loss=None, sampler=None, first_draw=0):
