@@ -93,7 +93,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -279,6 +279,8 @@ def run_ours(args, rank, local_rank, world):
                          "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "algorithmic_bytes_per_launch": abytes, "traffic": profile_traffic("bpr_step")}}
 
+    if world == 1 and not args.skip_sweep:
+        line["sweep"] = bpr_sweep(cfg, st, smp, dev)
     if rank == 0 and world == 1 and not args.skip_cpu:
         # bounded CPU sample: ~10-30 s of the OpenMP port on the same workload
         v1, ms1, threads = cpu_bpr_steps(min(B, 1 << 20), 1, 1)
@@ -292,6 +294,34 @@ def run_ours(args, rank, local_rank, world):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bpr_sweep(cfg, st, smp, dev):
+    """Other operating points of the same kernels on C2 (device-timed, triples resident or fused sampler):
+    the reference's own batch size 256 (bpr.py:103), 2^16, and 2^20 with the sampler fused into the step."""
+    import torch
+    import topkrec
+    out = []
+    for B, fused, n_steps, reps in ((256, False, 512, 3), (256, True, 512, 3), (1 << 16, False, 16, 5), (1 << 20, True, 1, 10)):
+        ws = topkrec.bpr_workspace(cfg, B, dev)
+        loss = torch.zeros(n_steps, dtype=torch.float32, device=dev)
+        trip = (None, None, None) if fused else topkrec.bpr_sample(smp, 7 << 32, B * n_steps, dev)
+
+        def run(k):
+            topkrec.bpr_step(cfg, st["U"], st["V"], st["b"], st["msU"], st["msV"], st["msb"], trip[0], trip[1], trip[2], B, n_steps, ws,
+                             loss, sampler=smp if fused else None, first_draw=(9 << 32) + k * B * n_steps)
+        for k in range(3):
+            run(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(reps):
+            run(3 + k)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * n_steps)
+        out.append({"batch_size": B, "fused_sampler": fused, "us_per_step": 1e3 * ms, "triples_per_sec": B / (ms / 1e3),
+                    "roofline_frac": algorithmic_bytes_per_triple(D) * B / (ms / 1e3) / 1e9 / measured_peaks()[0]["hbm_gbs"]})
+    return out
 
 
 def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src):
@@ -372,6 +402,7 @@ def main():
     ap.add_argument("--score-steps", type=int, default=5)
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-score", action="store_true")
+    ap.add_argument("--skip-sweep", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

@@ -9,9 +9,9 @@ cat gpurun_out/pytest_$TAG.log
 timeout 600 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 cat gpurun_out/bench_$TAG.json; tail -3 gpurun_out/bench_$TAG.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv \
-    python bench.py --steps 4 --warmup 3 --skip-cpu > /dev/null 2> gpurun_out/ncu_launches_$TAG.err
+    python bench.py --steps 4 --warmup 3 --skip-cpu --skip-sweep > /dev/null 2> gpurun_out/ncu_launches_$TAG.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bpr_ -s 8 -c 4 -f -o gpurun_out/prof_bpr_$TAG \
-    python bench.py --steps 4 --warmup 3 --skip-cpu --skip-score > /dev/null 2> gpurun_out/ncu_bpr_$TAG.err
+    python bench.py --steps 4 --warmup 3 --skip-cpu --skip-score --skip-sweep > /dev/null 2> gpurun_out/ncu_bpr_$TAG.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_topk -s 2 -c 1 -f -o gpurun_out/prof_score_$TAG \
-    python bench.py --steps 4 --warmup 3 --skip-cpu > /dev/null 2> gpurun_out/ncu_score_$TAG.err
+    python bench.py --steps 4 --warmup 3 --skip-cpu --skip-sweep > /dev/null 2> gpurun_out/ncu_score_$TAG.err
 ls -la gpurun_out | tail -12

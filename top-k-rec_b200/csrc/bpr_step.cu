@@ -2,11 +2,13 @@
 // reference; TF-1.15 RMSProp semantics per SURVEY.md App. A; SGD per old/methods/bpr.py:57-61).
 //
 // Two kernels per step, both HBM/L2-bandwidth bound (AI ~ 0.33 FLOP/B):
-//   bpr_grad_kernel   one warp per triple: [sample (u,i,j)] -> 128-bit coalesced gather of
-//                     U[u], V[i], V[j] into registers -> warp-shuffle dots -> s = sigma(-x) ->
+//   bpr_grad_kernel   one warp per 32 triples (lane t owns the scalars of triple t: ids or the fused
+//                     sampler draw, biases, flags, loss term); per triple: 128-bit coalesced gather of
+//                     U[u], V[i], V[j] into registers (next triple prefetched) -> warp-shuffle dot -> s = sigma(-x) ->
 //                     per-occurrence regularised gradients, summed into the per-row
 //                     accumulators with vector red.global.add (duplicates summed = the
-//                     unique+segment_sum of TF) -> first toucher appends the row to a list.
+//                     unique+segment_sum of TF) -> the row is flagged (large batches) or appended
+//                     to the step's touched list by its first toucher (small batches).
 //   bpr_apply_kernel  one warp per touched row: RMSProp/SGD update from the summed gradient,
 //                     re-zeroes the accumulator (the workspace is left clean for the next step).
 // All B gradients are therefore taken at the pre-step snapshot and every touched row gets
@@ -98,106 +100,146 @@ __device__ __forceinline__ float warp_sum(float x) {
     return x;
 }
 
-__device__ __forceinline__ float reg_grad(float x, float lam, bool l1) {
-    return l1 ? lam * (float)((x > 0.f) - (x < 0.f)) : lam * x;
+template <bool L1> __device__ __forceinline__ float reg_grad(float x, float lam) {
+    if (L1) return lam * (float)((x > 0.f) - (x < 0.f));
+    return lam * x;
 }
-__device__ __forceinline__ float reg_val(float x, float lam, bool l1) { return l1 ? lam * fabsf(x) : 0.5f * lam * x * x; }
+template <bool L1> __device__ __forceinline__ float reg_val(float x, float lam) {
+    if (L1) return lam * fabsf(x);
+    return 0.5f * lam * x * x;
+}
 
 struct StepWs {            // views into the caller's workspace
     float* GU; float* GV; float* Gb;
-    float* tchV;           // data-parallel mode: per-item occurrence count as fp32 (all-reduced with GV|Gb)
+    float* tchV;           // dense / data-parallel mode: per-item "touched" flag as fp32 (all-reduced with GV|Gb)
     int32_t* cntU; int32_t* cntV;
     int32_t* listU; int32_t* listV;
     int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
 };
 
-// grid-stride over triples, one warp each.  NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
+// How touched rows are found by the apply kernel:
+//   MODE_LIST   first toucher (returning atomic on cnt) appends the row to a list  -> small batches
+//   MODE_DENSE  plain flag stores, the apply kernel scans every row                -> batches that touch most rows,
+//               and data-parallel training (item flags are summed by the all-reduce)
+constexpr int MODE_LIST = 0, MODE_DENSE = 1;
+
+// Rows of one triple held in registers: NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
 template <int VW, int NCH>
+struct TripleRows {
+    Vec<VW> u[NCH], i[NCH], j[NCH];
+    __device__ __forceinline__ void load(const float* __restrict__ U, const float* __restrict__ V, int ru, int ri, int rj, int d, int lane) {
+        const float* pu = U + (int64_t)ru * d;
+        const float* pi = V + (int64_t)ri * d;
+        const float* pj = V + (int64_t)rj * d;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            const int off = (c * 32 + lane) * VW;
+            if (off < d) { u[c].load(pu + off); i[c].load(pi + off); j[c].load(pj + off); }
+            else {
+#pragma unroll
+                for (int t = 0; t < VW; ++t) { u[c].v[t] = 0.f; i[c].v[t] = 0.f; j[c].v[t] = 0.f; }
+            }
+        }
+    }
+};
+
+// One warp per block of up to 32 consecutive triples.  Lane t owns the scalar side of triple t (ids --
+// loaded coalesced or drawn by the fused sampler --, biases, touched flags, bias gradient, loss term);
+// the 32 row gathers run through the whole warp one triple after the other, software-pipelined so the
+// 128-bit gathers of triple t+1 are in flight while triple t is reduced and scattered.
+template <int VW, int NCH, bool L1, bool SAMPLE>
 __global__ void __launch_bounds__(256) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
-    SamplerDev smp, uint64_t first_draw, StepWs ws, int dp, float* __restrict__ loss_out) {
+    SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, float* __restrict__ loss_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d = cfg.d;
-    const bool l1 = cfg.l1 != 0;
-    float loss_acc = 0.f;
+    const bool want_loss = loss_out != nullptr;
+    float loss_acc = 0.f;          // per-lane partial; summed over the block at the end
+    constexpr unsigned FULL = 0xffffffffu;
 
-    for (int64_t n = warp0; n < B; n += nwarps) {
-        int u, i, j;
-        if (ub != nullptr) {
-            u = __ldg(ub + n); i = __ldg(ib + n); j = __ldg(jb + n);
-        } else {
-            if (lane == 0) sample_triple(smp, first_draw + (uint64_t)n, u, i, j);
-            u = __shfl_sync(0xffffffffu, u, 0); i = __shfl_sync(0xffffffffu, i, 0); j = __shfl_sync(0xffffffffu, j, 0);
+    // tpw (<= 32) triples per warp per round: 32 for large batches, fewer when the batch is too small
+    // to give every resident warp a full block
+    for (int64_t base = warp0 * tpw; base < B; base += nwarps * tpw) {
+        const int64_t n = base + lane;
+        const bool valid = lane < tpw && n < B;
+        const int cnt = (B - base) < tpw ? (int)(B - base) : tpw;
+        int u = 0, i = 0, j = 0;
+        if (valid) {
+            if (SAMPLE) sample_triple(smp, first_draw + (uint64_t)n, u, i, j);
+            else { u = __ldg(ub + n); i = __ldg(ib + n); j = __ldg(jb + n); }
         }
-        const float* pu = U + (int64_t)u * d;
-        const float* pi = V + (int64_t)i * d;
-        const float* pj = V + (int64_t)j * d;
-        Vec<VW> ru[NCH], ri[NCH], rj[NCH];
-        float xi = 0.f, xj = 0.f, reg = 0.f;
+        const float bi = valid ? __ldg(b + i) : 0.f, bj = valid ? __ldg(b + j) : 0.f;
+        const float bdiff = bi - bj;
+        float x_mine = 0.f, s_mine = 0.f;
+
+        TripleRows<VW, NCH> cur, nxt;
+        cur.load(U, V, __shfl_sync(FULL, u, 0), __shfl_sync(FULL, i, 0), __shfl_sync(FULL, j, 0), d, lane);
+        for (int t = 0; t < cnt; ++t) {
+            const int ru = __shfl_sync(FULL, u, t), ri = __shfl_sync(FULL, i, t), rj = __shfl_sync(FULL, j, t);
+            if (t + 1 < cnt)   // next triple's gathers go out before this one's reduction
+                nxt.load(U, V, __shfl_sync(FULL, u, t + 1), __shfl_sync(FULL, i, t + 1), __shfl_sync(FULL, j, t + 1), d, lane);
+            float x = 0.f;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int off = (c * 32 + lane) * VW;
-            if (off < d) { ru[c].load(pu + off); ri[c].load(pi + off); rj[c].load(pj + off); }
-            else {
+            for (int c = 0; c < NCH; ++c)
 #pragma unroll
-                for (int t = 0; t < VW; ++t) { ru[c].v[t] = 0.f; ri[c].v[t] = 0.f; rj[c].v[t] = 0.f; }
+                for (int q = 0; q < VW; ++q) x = fmaf(cur.u[c].v[q], cur.i[c].v[q] - cur.j[c].v[q], x);   // <U_u, V_i - V_j>
+            x = warp_sum(x) + __shfl_sync(FULL, bdiff, t);           // x_uij, bpr.py:87-89
+            const float s = __fdividef(1.0f, 1.0f + __expf(x));      // sigma(-x) = -d/dx log(1+e^-x)
+            if (lane == t) { x_mine = x; s_mine = s; }
+            if (want_loss) {
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int q = 0; q < VW; ++q)
+                        loss_acc += reg_val<L1>(cur.u[c].v[q], cfg.lambda_u) + reg_val<L1>(cur.i[c].v[q], cfg.lambda_i) + reg_val<L1>(cur.j[c].v[q], cfg.lambda_j);
             }
+            float* gu = ws.GU + (int64_t)ru * d;
+            float* gi = ws.GV + (int64_t)ri * d;
+            float* gj = ws.GV + (int64_t)rj * d;
 #pragma unroll
-            for (int t = 0; t < VW; ++t) {
-                xi = fmaf(ru[c].v[t], ri[c].v[t], xi);
-                xj = fmaf(ru[c].v[t], rj[c].v[t], xj);
-                reg += reg_val(ru[c].v[t], cfg.lambda_u, l1) + reg_val(ri[c].v[t], cfg.lambda_i, l1) + reg_val(rj[c].v[t], cfg.lambda_j, l1);
+            for (int c = 0; c < NCH; ++c) {
+                const int off = (c * 32 + lane) * VW;
+                if (off < d) {
+                    Vec<VW> a, p, q;
+#pragma unroll
+                    for (int e = 0; e < VW; ++e) {
+                        a.v[e] = fmaf(-s, cur.i[c].v[e] - cur.j[c].v[e], reg_grad<L1>(cur.u[c].v[e], cfg.lambda_u));  // gU   (App. A.2)
+                        p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], cfg.lambda_i));                  // gV_i
+                        q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], cfg.lambda_j));                   // gV_j
+                    }
+                    a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
+                }
             }
+            cur = nxt;
         }
-        xi = warp_sum(xi); xj = warp_sum(xj); reg = warp_sum(reg);
-        const float bi = __ldg(b + i), bj = __ldg(b + j);
-        const float x = bi - bj + xi - xj;                       // bpr.py:89
-        const float s = 1.0f / (1.0f + expf(x));                 // sigma(-x) = d/dx of -log(1+e^-x)
-        if (lane == 0) {
-            // log(1+e^-x), stable for both signs
-            const float l = (x > 0.f) ? log1pf(expf(-x)) : (-x + log1pf(expf(x)));
-            loss_acc += l + reg + reg_val(bi, cfg.lambda_b, l1) + reg_val(bj, cfg.lambda_b, l1);
-            // first toucher of a row appends it to the step's touched list
-            if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0, 1)] = u;
-            if (dp) {   // item rows are found after the all-reduce from the summed occurrence counts
-                atomicAdd(ws.tchV + i, 1.0f);
-                atomicAdd(ws.tchV + j, 1.0f);
-            } else {
+        // lane-parallel scalar tail: lane t finishes triple t
+        if (valid) {
+            if (mode == MODE_DENSE) {
+                ws.cntU[u] = 1; ws.tchV[i] = 1.0f; ws.tchV[j] = 1.0f;
+            } else {   // first toucher of a row appends it to the step's touched list
+                if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0, 1)] = u;
                 if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
                 if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
             }
-            atomicAdd(ws.Gb + i, -s + reg_grad(bi, cfg.lambda_b, l1));
-            atomicAdd(ws.Gb + j, s + reg_grad(bj, cfg.lambda_b, l1));
-        }
-        float* gu = ws.GU + (int64_t)u * d;
-        float* gi = ws.GV + (int64_t)i * d;
-        float* gj = ws.GV + (int64_t)j * d;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            const int off = (c * 32 + lane) * VW;
-            if (off < d) {
-                Vec<VW> a, p, q;
-#pragma unroll
-                for (int t = 0; t < VW; ++t) {
-                    a.v[t] = -s * (ri[c].v[t] - rj[c].v[t]) + reg_grad(ru[c].v[t], cfg.lambda_u, l1);  // gU   (App. A.2)
-                    p.v[t] = -s * ru[c].v[t] + reg_grad(ri[c].v[t], cfg.lambda_i, l1);                 // gV_i
-                    q.v[t] = s * ru[c].v[t] + reg_grad(rj[c].v[t], cfg.lambda_j, l1);                  // gV_j
-                }
-                a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
-            }
+            atomicAdd(ws.Gb + i, -s_mine + reg_grad<L1>(bi, cfg.lambda_b));
+            atomicAdd(ws.Gb + j, s_mine + reg_grad<L1>(bj, cfg.lambda_b));
+            if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)
+                loss_acc += fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
         }
     }
-    // block reduction of the loss -> one atomic per block
+    if (!want_loss) return;
+    // block reduction of the per-lane partials -> one atomic per block
     __shared__ float sl[8];
+    loss_acc = warp_sum(loss_acc);
     if (lane == 0) sl[threadIdx.x >> 5] = loss_acc;
     __syncthreads();
     if (threadIdx.x < 32) {
         float v = (threadIdx.x < (blockDim.x >> 5)) ? sl[threadIdx.x] : 0.f;
         v = warp_sum(v);
-        if (threadIdx.x == 0 && loss_out != nullptr) atomicAdd(loss_out, v);
+        if (threadIdx.x == 0) atomicAdd(loss_out, v);
     }
 }
 
@@ -226,38 +268,48 @@ __device__ __forceinline__ void apply_row(const tkr_bpr_cfg& cfg, float* __restr
     }
 }
 
-// warps [0, nU) update touched user rows, warps [nU, nU+nV) touched item rows (+ their bias).
-// dp != 0: item rows are all rows r with tchV[r] > 0 (dense scan over n_items).
-// The last block to finish re-arms the touched counters (no extra launch, no parity games).
+// MODE_LIST : warps [0, nU) update the listed user rows, [nU, nU+nV) the listed item rows (+ their bias);
+//             the last block to finish re-arms the list counters (no extra launch).
+// MODE_DENSE: warp w looks at row w of [users | items] and updates it if its flag is set
+//             (items_dense_only: users still come from the list -- unused today).
 template <int VW>
 __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V,
                                                         float* __restrict__ b, float* __restrict__ msU,
                                                         float* __restrict__ msV, float* __restrict__ msb, StepWs ws,
-                                                        int dp) {
+                                                        int mode) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int nU = ws.n_touched[0], nV = dp ? cfg.n_items : ws.n_touched[1];
     const int d = cfg.d;
+    if (mode == MODE_DENSE) {
+        const int64_t total = (int64_t)cfg.n_users + cfg.n_items;
+        for (int64_t w = warp0; w < total; w += nwarps) {
+            if (w < cfg.n_users) {
+                const int r = (int)w;
+                if (ws.cntU[r] == 0) continue;
+                apply_row<VW>(cfg, U + (int64_t)r * d, msU + (int64_t)r * d, ws.GU + (int64_t)r * d, d, lane);
+                __syncwarp();
+                if (lane == 0) ws.cntU[r] = 0;
+            } else {
+                const int r = (int)(w - cfg.n_users);
+                if (ws.tchV[r] == 0.0f) continue;
+                apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
+                __syncwarp();
+                if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.tchV[r] = 0.0f; }
+            }
+        }
+        return;
+    }
+    const int nU = ws.n_touched[0], nV = ws.n_touched[1];
     for (int64_t w = warp0; w < (int64_t)nU + nV; w += nwarps) {
         if (w < nU) {
             const int r = ws.listU[w];
             apply_row<VW>(cfg, U + (int64_t)r * d, msU + (int64_t)r * d, ws.GU + (int64_t)r * d, d, lane);
             if (lane == 0) ws.cntU[r] = 0;
         } else {
-            int r;
-            if (dp) {
-                r = (int)(w - nU);
-                if (ws.tchV[r] == 0.0f) continue;
-            } else {
-                r = ws.listV[w - nU];
-            }
+            const int r = ws.listV[w - nU];
             apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
-            __syncwarp();
-            if (lane == 0) {
-                apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0);
-                if (dp) ws.tchV[r] = 0.0f; else ws.cntV[r] = 0;
-            }
+            if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.cntV[r] = 0; }
         }
     }
     __syncthreads();
@@ -313,35 +365,49 @@ static int check_cfg(const tkr_bpr_cfg* cfg, int64_t B) {
 
 static inline int64_t grid_cap() { return (int64_t)kNumSMs * 8; }   // 8 CTAs x 8 warps = 64 resident warps per SM
 
+// Dense flags pay a scan of every row in the apply kernel; worth it once a batch touches a good share of
+// the rows (and mandatory in data-parallel mode, where the item flags travel with the all-reduce).
+static inline int pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel) {
+    return (data_parallel || 3 * B >= ((int64_t)cfg->n_users + cfg->n_items) / 8) ? MODE_DENSE : MODE_LIST;
+}
+
 template <int VW, int NCH>
 static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                         const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                        const StepWs& ws, int dp, float* loss, cudaStream_t st) {
-    int64_t blocks = (B + 7) / 8;
+                        const StepWs& ws, int mode, float* loss, cudaStream_t st) {
+    // triples per warp: spread small batches over all resident warps, cap at one per lane
+    const int64_t max_warps = grid_cap() * 8;
+    int64_t tpw64 = (B + max_warps - 1) / max_warps;
+    const int tpw = tpw64 > 32 ? 32 : (int)tpw64;
+    int64_t blocks = ((B + tpw - 1) / tpw + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-    bpr_grad_kernel<VW, NCH><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, dp, loss);
+#define TKR_K(L1_, S_) bpr_grad_kernel<VW, NCH, L1_, S_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, loss)
+    if (cfg->l1) { if (u == nullptr) TKR_K(true, true); else TKR_K(true, false); }
+    else { if (u == nullptr) TKR_K(false, true); else TKR_K(false, false); }
+#undef TKR_K
 }
 
 static void launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
-                         int64_t B, const StepWs& ws, int dp, cudaStream_t st) {
+                         int64_t B, const StepWs& ws, int mode, cudaStream_t st) {
     const int d = cfg->d;
-    int64_t rows = (B < cfg->n_users ? B : cfg->n_users) + ((dp || 2 * B > cfg->n_items) ? cfg->n_items : 2 * B);
+    int64_t rows = mode == MODE_DENSE ? (int64_t)cfg->n_users + cfg->n_items
+                                      : (B < cfg->n_users ? B : cfg->n_users) + (2 * B < cfg->n_items ? 2 * B : cfg->n_items);
     int64_t blocks = (rows + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-    if (d % 4 == 0) bpr_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
-    else if (d % 2 == 0) bpr_apply_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
-    else bpr_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, dp);
+    if (d % 4 == 0) bpr_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
+    else if (d % 2 == 0) bpr_apply_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
+    else bpr_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
 }
 
 static int dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                          const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                         const StepWs& ws, int dp, float* loss, cudaStream_t st) {
+                         const StepWs& ws, int mode, float* loss, cudaStream_t st) {
     const int d = cfg->d;
     const int vw = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;   // widest vector the row pitch allows
     const int nch = (d + 32 * vw - 1) / (32 * vw);
     if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
     const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
-#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, dp, loss, st)
+#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, loss, st)
     if (vw == 4) { if (nchp == 1) TKR_GRAD(4, 1); else if (nchp == 2) TKR_GRAD(4, 2); else if (nchp == 4) TKR_GRAD(4, 4); else TKR_GRAD(4, 8); }
     else if (vw == 2) { if (nchp == 1) TKR_GRAD(2, 1); else if (nchp == 2) TKR_GRAD(2, 2); else if (nchp == 4) TKR_GRAD(2, 4); else TKR_GRAD(2, 8); }
     else { if (nchp == 1) TKR_GRAD(1, 1); else if (nchp == 2) TKR_GRAD(1, 2); else if (nchp == 4) TKR_GRAD(1, 4); else TKR_GRAD(1, 8); }
@@ -419,7 +485,7 @@ extern "C" int tkr_bpr_grad(const tkr_bpr_cfg* cfg, const float* U, const float*
     }
     StepWs w;
     if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
-    return dispatch_grad(cfg, U, V, b, u, i, j, B, sd, first_draw, w, data_parallel ? 1 : 0, loss_out, (cudaStream_t)stream);
+    return dispatch_grad(cfg, U, V, b, u, i, j, B, sd, first_draw, w, pick_mode(cfg, B, data_parallel), loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
@@ -429,7 +495,7 @@ extern "C" int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* 
     TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
     StepWs w;
     if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
-    launch_apply(cfg, U, V, b, msU, msV, msb, B, w, data_parallel ? 1 : 0, (cudaStream_t)stream);
+    launch_apply(cfg, U, V, b, msU, msV, msb, B, w, pick_mode(cfg, B, data_parallel), (cudaStream_t)stream);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
@@ -452,14 +518,15 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     StepWs w;
     if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    const int mode = pick_mode(cfg, B, 0);
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     for (int64_t t = 0; t < n_steps; ++t) {
         const int32_t* ut = u ? u + t * B : nullptr;
         const int32_t* it = u ? i + t * B : nullptr;
         const int32_t* jt = u ? j + t * B : nullptr;
         float* lt = loss_out ? loss_out + t : nullptr;
-        if (int rc = dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, 0, lt, st)) return rc;
-        launch_apply(cfg, U, V, b, msU, msV, msb, B, w, 0, st);
+        if (int rc = dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, mode, lt, st)) return rc;
+        launch_apply(cfg, U, V, b, msU, msV, msb, B, w, mode, st);
         TKR_LAUNCH_CHECK();
     }
     return TKR_OK;
