@@ -338,8 +338,12 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
     gu = torch.Generator(device=dev); gu.manual_seed(3)
     Ub = [torch.randn(nb, D, device=dev, generator=gu) * 0.1 for _ in range(4)]
 
+    eng = args.score_engine
+    need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(nb, Vfull_rows, D, k, 0) if eng == "tc" else topkrec.lib().tkr_score_topk_workspace_bytes(nb, Vfull_rows, D, k)
+    wsb = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+
     def step(t):
-        return tdist.sharded_score_topk(Ub[t % 4], V, k, beg)
+        return tdist.sharded_score_topk(Ub[t % 4], V, k, beg, engine=eng, ws=wsb)
     for t in range(W):
         step(t)
     barrier()
@@ -357,11 +361,13 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
     out = {"metric": "scored_users_per_sec_top30", "value": nb / (ms / 1e3), "unit": "users/s", "ms_per_step": ms, "steps": K,
            "config": {"workload": "score + top-30, %d users/step x %d items, d=%d, item-sharded over %d GPU(s); V (%.0f MB/GPU) > L2 per step"
                                   % (nb, NI, D, world, Vfull_rows * D * 4 / 1e6)},
-           "dtype": "f32 (exact fma-chain scores, CUDA cores)", "gpu_launches": launches, "clocks": clk.summary(),
-           "roofline": {"bound": "tensor", "kernel": "score_topk_kernel", "achieved": flops / (ms / 1e3) / 1e12,
-                        "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
+           "dtype": "bf16 tcgen05 filter (fp32 accumulate in TMEM) + exact fp32 fma-chain refine; results bit-identical to the fp32 oracle"
+                    if eng == "tc" else "f32 (exact fma-chain scores, CUDA cores)",
+           "gpu_launches": launches, "clocks": clk.summary(),
+           "roofline": {"bound": "tensor", "kernel": "score_filter_kernel" if eng == "tc" else "score_topk_kernel",
+                        "achieved": flops / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
                         "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
-                        "note": "exact fp32 engine runs on the CUDA cores (fp32 FMA peak ~75 TFLOP/s), not tcgen05"}}
+                        "note": "FLOP = 2*nu*ni*d over the whole step (convert + filter + refine + fallback), against the burst bf16 peak"}}
     if world == 1:
         # e2e: host U batch + host V (copied once per pass of K batches) -> device -> lists back on the host
         Vh = V.cpu().pin_memory(); Uh = [u.cpu().pin_memory() for u in Ub]
@@ -372,7 +378,7 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
         Vd.copy_(Vh, non_blocking=True)
         for t in range(K):
             Ud.copy_(Uh[t % 4], non_blocking=True)
-            gi, gs = topkrec.score_topk(Ud, Vd, k)
+            gi, gs = topkrec.score_topk(Ud, Vd, k, engine=eng, ws=wsb)
             oi.copy_(gi, non_blocking=True); os_.copy_(gs, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         dt = time.perf_counter() - t0
@@ -397,7 +403,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1 << 20)
-    ap.add_argument("--score-users", type=int, default=8192)
+    ap.add_argument("--score-users", type=int, default=18944)      # 148 tiles of 128 users: one CTA per SM
+    ap.add_argument("--score-engine", default="tc", choices=["tc", "exact"])
     ap.add_argument("--score-items", type=int, default=1 << 20)
     ap.add_argument("--score-steps", type=int, default=5)
     ap.add_argument("--skip-cpu", action="store_true")

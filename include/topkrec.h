@@ -157,6 +157,18 @@ int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_t ni, int32
                    const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
                    int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, void* stream);
 
+/* Same contract and bit-identical results, computed on the tensor cores: BF16 tcgen05 GEMM with a
+ * fused in-SM candidate filter (TMA-fed, accumulators in TMEM, scores never written), exact fp32
+ * re-scoring of the <= 64 survivors per row, a per-row error-bound certificate, and the exact kernel
+ * above for the rows that cannot be certified (their count is written to *n_fallback_rows, a DEVICE
+ * int32, if not NULL).  Shapes the filter does not cover (d + 3 > 256 after padding, k > 48) are
+ * routed to tkr_score_topk entirely. */
+size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k, int32_t has_bias);
+int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
+                      const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
+                      int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
+                      void* stream);
+
 /* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
  * U_host/V_host/bias_host/rated_* in host memory, results to host memory.
  * `dev` is device scratch of >= tkr_score_topk_host_device_bytes(). */

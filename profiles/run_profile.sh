@@ -12,6 +12,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --steps 4 --warmup 3 --skip-cpu --skip-sweep > /dev/null 2> gpurun_out/ncu_launches_$TAG.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bpr_ -s 8 -c 4 -f -o gpurun_out/prof_bpr_$TAG \
     python bench.py --steps 4 --warmup 3 --skip-cpu --skip-score --skip-sweep > /dev/null 2> gpurun_out/ncu_bpr_$TAG.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_topk -s 2 -c 1 -f -o gpurun_out/prof_score_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_filter -s 2 -c 1 -f -o gpurun_out/prof_score_$TAG \
     python bench.py --steps 4 --warmup 3 --skip-cpu --skip-sweep > /dev/null 2> gpurun_out/ncu_score_$TAG.err
 ls -la gpurun_out | tail -12

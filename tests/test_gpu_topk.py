@@ -34,22 +34,30 @@ def _case(nu, ni, d, k, seed, bias=False, rated=0, ties=False, scale=0.1):
     return U, V, b, indptr, idx
 
 
-def _check(U, V, k, b, indptr, idx, col_offset=0):
+ENGINES = ("exact", "tc")     # CUDA-core fp32 kernel / tcgen05 BF16 filter + exact refine: same bits required of both
+
+
+def _check(U, V, k, b, indptr, idx, col_offset=0, engines=ENGINES):
     t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
-    gi, gs = topkrec.score_topk(t(U), t(V), k, t(b), t(indptr), t(idx), col_offset=col_offset)
-    if indptr is not None and col_offset:
-        pass
     ri, rs = topk_ref.score_topk(U, V, k, b, indptr, idx, col_offset=col_offset)
-    gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
-    assert np.array_equal(gi, ri), "index lists differ at rows %s" % np.nonzero((gi != ri).any(1))[0][:5]
-    assert np.array_equal(gs.view(np.uint32), rs.view(np.uint32)), "scores are not bit-identical"
+    fallback = {}
+    for eng in engines:
+        nf = torch.zeros(1, dtype=torch.int32, device="cuda")
+        gi, gs = topkrec.score_topk(t(U), t(V), k, t(b), t(indptr), t(idx), col_offset=col_offset, engine=eng, n_fallback=nf)
+        gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+        assert np.array_equal(gi, ri), "[%s] index lists differ at rows %s" % (eng, np.nonzero((gi != ri).any(1))[0][:5])
+        assert np.array_equal(gs.view(np.uint32), rs.view(np.uint32)), "[%s] scores are not bit-identical" % eng
+        fallback[eng] = int(nf.item())
+    return fallback
 
 
 @pytest.mark.parametrize("nu,ni,d,k", [(300, 1000, 128, 30), (129, 65, 50, 30), (1, 1, 1, 1), (77, 200, 16, 5),
                                        (64, 333, 256, 30), (40, 500, 300, 30), (33, 700, 512, 10), (10, 90, 7, 64),
                                        (500, 4099, 64, 30), (260, 2048, 128, 15)])
 def test_score_topk_bit_exact_shapes(nu, ni, d, k):
-    _check(*_case(nu, ni, d, k, seed=nu + ni)[:2], k, None, None, None)
+    fb = _check(*_case(nu, ni, d, k, seed=nu + ni)[:2], k, None, None, None)
+    if ni >= 1000 and d <= 256:
+        assert fb["tc"] <= nu // 50, "tensor-core filter should certify nearly every row on generic data (%d fell back)" % fb["tc"]
 
 
 @pytest.mark.parametrize("k", [5, 10, 15, 20, 25, 30])
@@ -64,9 +72,10 @@ def test_score_topk_ties_and_zero_rows():
     _check(U, V, 30, None, None, None)
     V[:] = 0                                   # every score ties at +0: order = column descending
     t = lambda a: torch.from_numpy(a).cuda()   # noqa: E731
-    gi, gs = topkrec.score_topk(t(U), t(V), 30)
-    assert np.array_equal(gi.cpu().numpy(), np.tile(np.arange(899, 869, -1, dtype=np.int32), (150, 1)))
-    assert (gs.cpu().numpy().view(np.uint32) == 0).all()       # +0.0, never -0.0
+    for eng in ENGINES:                        # (the tc engine cannot certify an all-tie row: exact fallback)
+        gi, gs = topkrec.score_topk(t(U), t(V), 30, engine=eng)
+        assert np.array_equal(gi.cpu().numpy(), np.tile(np.arange(899, 869, -1, dtype=np.int32), (150, 1)))
+        assert (gs.cpu().numpy().view(np.uint32) == 0).all()       # +0.0, never -0.0
 
 
 def test_score_topk_rated_mask_and_short_lists():
@@ -75,8 +84,9 @@ def test_score_topk_rated_mask_and_short_lists():
     full = np.arange(60, dtype=np.int32)                                    # a user who rated everything
     p2 = np.array([0, 60], np.int64)
     t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
-    gi, gs = topkrec.score_topk(t(U[:1]), t(V), 30, None, t(p2), t(full))
-    assert (gi.cpu().numpy() == -1).all() and np.isneginf(gs.cpu().numpy()).all()
+    for eng in ENGINES:
+        gi, gs = topkrec.score_topk(t(U[:1]), t(V), 30, None, t(p2), t(full), engine=eng)
+        assert (gi.cpu().numpy() == -1).all() and np.isneginf(gs.cpu().numpy()).all()
 
 
 def test_score_topk_split_path_and_col_offset():
@@ -85,10 +95,12 @@ def test_score_topk_split_path_and_col_offset():
     _check(U, V, 30, b, p, i)
     half = 9984
     t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
-    parts = [topkrec.score_topk(t(U), t(V[a:z].copy()), 30, t(b[a:z].copy()), t(p), t(i), col_offset=a) for a, z in ((0, half), (half, 20000))]
-    mi, ms = topkrec.topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]))
     ri, rs = topk_ref.score_topk(U, V, 30, b, p, i)
-    assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+    for eng in ENGINES:
+        parts = [topkrec.score_topk(t(U), t(V[a:z].copy()), 30, t(b[a:z].copy()), t(p), t(i), col_offset=a, engine=eng)
+                 for a, z in ((0, half), (half, 20000))]
+        mi, ms = topkrec.topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]))
+        assert np.array_equal(mi.cpu().numpy(), ri) and np.array_equal(ms.cpu().numpy().view(np.uint32), rs.view(np.uint32))
 
 
 def test_topk_merge_matches_oracle():
@@ -160,9 +172,11 @@ def test_full_size_property_sharded_equals_whole():
     U = torch.from_numpy((0.1 * rng.standard_normal((nu, d))).astype(np.float32)).cuda()
     g = torch.Generator(device="cuda"); g.manual_seed(4)
     V = torch.randn(ni, d, device="cuda", generator=g) * 0.1
-    wi, ws_ = topkrec.score_topk(U, V, k)
+    wi, ws_ = topkrec.score_topk(U, V, k, engine="tc")
+    ei, es = topkrec.score_topk(U, V, k, engine="exact")
+    assert torch.equal(ei, wi) and torch.equal(es, ws_), "tensor-core path and exact engine disagree at full width"
     bounds = np.linspace(0, ni, 9).astype(np.int64)
-    parts = [topkrec.score_topk(U, V[a:z], k, col_offset=int(a)) for a, z in zip(bounds[:-1], bounds[1:])]
+    parts = [topkrec.score_topk(U, V[a:z], k, col_offset=int(a), engine="tc") for a, z in zip(bounds[:-1], bounds[1:])]
     mi, ms = topkrec.topk_merge(torch.stack([x[0] for x in parts]), torch.stack([x[1] for x in parts]))
     assert torch.equal(mi, wi) and torch.equal(ms, ws_)
     wi_h, ws_h = wi.cpu().numpy(), ws_.cpu().numpy()
@@ -176,3 +190,25 @@ def test_full_size_property_sharded_equals_whole():
     S = (U[:8].double() @ V.double().T)
     kth = torch.from_numpy(ws_h[:8, -1]).cuda().double()
     assert int((S > (kth[:, None] + 1e-4)).sum().item()) <= 8 * (k - 1)
+
+
+def test_tc_adversarial_rows_fall_back_and_stay_exact():
+    """near-ties at the k-th place (gap << bf16 error) cannot be certified: those rows must take the exact
+    fallback and still come out bit-identical; a wide user batch takes the single-split path."""
+    rng = np.random.default_rng(21)
+    nu, ni, d, k = 700, 6000, 128, 30
+    U = (0.1 * rng.standard_normal((nu, d))).astype(np.float32)
+    V = (0.1 * rng.standard_normal((ni, d))).astype(np.float32)
+    V[1000:1100] = V[999] * (1 + 1e-6 * rng.standard_normal((100, 1))).astype(np.float32)   # 100 near-duplicates
+    fb = _check(U, V, k, None, None, None, engines=("tc",))
+    assert fb["tc"] > 0
+    big = _case(19000, 3000, 64, 30, seed=22, bias=True, rated=20)
+    _check(big[0], big[1], 30, big[2], big[3], big[4], engines=("tc",))
+
+
+def test_tc_large_norm_spread():
+    """rows with very different norms: the per-row error bound scales with |u| * max|v|"""
+    rng = np.random.default_rng(23)
+    U = (rng.standard_normal((400, 96)) * np.exp(rng.uniform(-6, 3, (400, 1)))).astype(np.float32)
+    V = (rng.standard_normal((9000, 96)) * np.exp(rng.uniform(-6, 3, (9000, 1)))).astype(np.float32)
+    _check(U, V, 30, None, None, None)

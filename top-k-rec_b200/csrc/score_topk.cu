@@ -26,7 +26,7 @@ template <int BM, int KCAP>
 struct ScoreSmem {
     // dynamic smem layout (bytes): As[dpad][BM] | Bs[2][BK][BS] | T[BM][KCAP] | C[BM][BN] | cnt | nvalid | tau
     static size_t bytes(int dpad) {
-        return (size_t)dpad * BM * 4 + 2 * BK * BS * 4 + (size_t)BM * KCAP * 8 + (size_t)BM * BN * 8 + BM * 4 * 3;
+        return (size_t)dpad * BM * 4 + 2 * BK * BS * 4 + (size_t)BM * KCAP * 8 + (size_t)BM * BN * 8 + BM * 4 * 4;
     }
 };
 
@@ -74,8 +74,13 @@ template <int BM, int KCAP, bool VEC4>
 __global__ void __launch_bounds__(256) score_topk_kernel(
     const float* __restrict__ U, int64_t nu, const float* __restrict__ V, int64_t ni, int d, int dpad,
     const float* __restrict__ bias, const int64_t* __restrict__ rated_indptr, const int32_t* __restrict__ rated_idx,
-    int k, int64_t col_offset, int tiles_per_split, int32_t* __restrict__ out_idx, float* __restrict__ out_score) {
+    int k, int64_t col_offset, int tiles_per_split, const int32_t* __restrict__ row_map, const int32_t* __restrict__ n_rows_dev,
+    int32_t* __restrict__ out_idx, float* __restrict__ out_score) {
     constexpr int RM = BM / 16;  // rows per thread
+    // optional indirection: logical row r of this launch is row row_map[r] of U / rated / out, and only
+    // the first *n_rows_dev logical rows exist (the tensor-core path hands its uncertified rows over this way)
+    const int64_t n_rows = n_rows_dev ? (int64_t)*n_rows_dev : nu;
+    if ((int64_t)blockIdx.x * BM >= n_rows) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);
     float* Bs = As + (size_t)dpad * BM;
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
     int* cnt = reinterpret_cast<int*>(C + (size_t)BM * BN);
     int* nvalid = cnt + BM;
     float* tau = reinterpret_cast<float*>(nvalid + BM);
+    int* arow = reinterpret_cast<int*>(tau + BM);   // actual row per logical row, -1 = none
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
@@ -94,12 +100,17 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
     int64_t tile_end = tile_beg + tiles_per_split;
     if (tile_end > ntiles) tile_end = ntiles;
 
+    for (int idx = tid; idx < BM; idx += 256) {
+        const int64_t lr = row0 + idx;
+        arow[idx] = lr < n_rows ? (row_map ? row_map[lr] : (int)lr) : -1;
+    }
+    __syncthreads();
     // ---- stage the U tile, k-major: As[kk][r]; lanes walk rows so the stores are conflict-free
     for (int idx = tid; idx < BM * (dpad / 4); idx += 256) {
         const int r = idx % BM, kq = (idx / BM) * 4;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (row0 + r < nu) {
-            const float* p = U + (row0 + r) * d + kq;
+        if (arow[r] >= 0) {
+            const float* p = U + (int64_t)arow[r] * d + kq;
             if (VEC4) { if (kq < d) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; } }
             else {
 #pragma unroll
@@ -199,14 +210,14 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
                 s = s + 0.0f;
                 if (s >= t) {
                     const int64_t lc = n0 + tx * 4 + c;
-                    if (lc < ni && row0 + row < nu) {
+                    if (lc < ni && arow[row] >= 0) {
                         const int32_t gc = (int32_t)(lc + col_offset);
                         const uint64_t key = make_key(s, gc);
                         const bool full = nvalid[row] == k;
                         if (!full || key > T[(size_t)row * KCAP + k - 1]) {
                             bool rated = false;
                             if (rated_indptr != nullptr)
-                                rated = rated_contains(rated_idx, __ldg(rated_indptr + row0 + row), __ldg(rated_indptr + row0 + row + 1), gc);
+                                rated = rated_contains(rated_idx, __ldg(rated_indptr + arow[row]), __ldg(rated_indptr + arow[row] + 1), gc);
                             if (!rated) C[(size_t)row * BN + atomicAdd(cnt + row, 1)] = key;
                         }
                     }
@@ -227,9 +238,9 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
     // ---- write the lists (split s of row r at [(s*nu + r)*k])
     for (int idx = tid; idx < BM * k; idx += 256) {
         const int row = idx / k, p = idx % k;
-        if (row0 + row < nu) {
+        if (arow[row] >= 0) {
             const uint64_t key = T[(size_t)row * KCAP + p];
-            const int64_t o = ((int64_t)split * nu + row0 + row) * k + p;
+            const int64_t o = ((int64_t)split * nu + arow[row]) * k + p;
             out_idx[o] = key ? (int32_t)(uint32_t)key : -1;
             out_score[o] = key ? ord_to_f32((uint32_t)(key >> 32)) : -INFINITY;
         }
@@ -319,17 +330,48 @@ extern "C" int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_
 template <int BM, int KCAP, bool VEC4>
 static int launch_score(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
                         const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, int ns, int tps,
-                        int32_t* oi, float* os, cudaStream_t st) {
+                        const int32_t* row_map, const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
     const int dpad = (d + BK - 1) / BK * BK;
     const size_t smem = ScoreSmem<BM, KCAP>::bytes(dpad);
     if (smem > 227 * 1024) { set_error("score_topk: d=%d k=%d needs %zu B of shared memory (> 227 KB)", d, k, smem); return TKR_ERR_UNSUPPORTED; }
     auto kern = score_topk_kernel<BM, KCAP, VEC4>;
     TKR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((nu + BM - 1) / BM), (unsigned)ns);
-    kern<<<grid, 256, smem, st>>>(U, nu, V, ni, d, dpad, bias, rp, ri, k, col_offset, tps, oi, os);
+    kern<<<grid, 256, smem, st>>>(U, nu, V, ni, d, dpad, bias, rp, ri, k, col_offset, tps, row_map, n_rows_dev, oi, os);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
+
+static int dispatch_score(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
+                          const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, int ns, int tps,
+                          const int32_t* row_map, const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
+    if (d > 512) { set_error("score_topk: d=%d > 512 is not supported by the exact kernel", d); return TKR_ERR_UNSUPPORTED; }
+    const int BM = pick_bm(d);
+    const bool vec4 = (d % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)V % 16 == 0);
+    const int kcap = k <= 32 ? 32 : 64;
+    int rc;
+#define TKR_SCORE(BM_, KC_, V4_) rc = launch_score<BM_, KC_, V4_>(U, nu, V, ni, d, bias, rp, ri, k, col_offset, ns, tps, row_map, n_rows_dev, oi, os, st)
+#define TKR_SCORE_BM(BM_)                                                   \
+    do {                                                                    \
+        if (kcap == 32) { if (vec4) TKR_SCORE(BM_, 32, true); else TKR_SCORE(BM_, 32, false); } \
+        else { if (vec4) TKR_SCORE(BM_, 64, true); else TKR_SCORE(BM_, 64, false); }            \
+    } while (0)
+    if (BM == 128) TKR_SCORE_BM(128); else if (BM == 64) TKR_SCORE_BM(64); else TKR_SCORE_BM(32);
+#undef TKR_SCORE_BM
+#undef TKR_SCORE
+    return rc;
+}
+
+namespace tkr {
+// Exact engine over a device-side list of rows (row_map[0 .. *n_rows_dev)), results written in place into
+// out[row_map[r]].  One item split; CTAs beyond the list exit immediately.
+int launch_exact_rows(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
+                      const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, const int32_t* row_map,
+                      const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
+    const int64_t ntiles = (ni + BN - 1) / BN;
+    return dispatch_score(U, nu, V, ni, d, bias, rp, ri, k, col_offset, 1, (int)ntiles, row_map, n_rows_dev, oi, os, st);
+}
+}  // namespace tkr
 
 extern "C" int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
                               const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
@@ -351,19 +393,7 @@ extern "C" int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_
         if (ws == nullptr || ws_bytes < 2 * half) { set_error("score_topk workspace too small: have %zu, need %zu", ws_bytes, 2 * half); return TKR_ERR_WORKSPACE; }
         oi = (int32_t*)ws; os = (float*)((char*)ws + half);
     }
-    const bool vec4 = (d % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)V % 16 == 0);
-    const int kcap = k <= 32 ? 32 : 64;
-    int rc;
-#define TKR_SCORE(BM_, KC_, V4_) rc = launch_score<BM_, KC_, V4_>(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, ns, tps, oi, os, st)
-#define TKR_SCORE_BM(BM_)                                                   \
-    do {                                                                    \
-        if (kcap == 32) { if (vec4) TKR_SCORE(BM_, 32, true); else TKR_SCORE(BM_, 32, false); } \
-        else { if (vec4) TKR_SCORE(BM_, 64, true); else TKR_SCORE(BM_, 64, false); }            \
-    } while (0)
-    if (BM == 128) TKR_SCORE_BM(128); else if (BM == 64) TKR_SCORE_BM(64); else TKR_SCORE_BM(32);
-#undef TKR_SCORE_BM
-#undef TKR_SCORE
-    if (rc) return rc;
+    if (int rc = dispatch_score(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, ns, tps, nullptr, nullptr, oi, os, st)) return rc;
     if (ns > 1) return tkr_topk_merge(oi, os, ns, nu, k, out_idx, out_score, stream);
     return TKR_OK;
 }

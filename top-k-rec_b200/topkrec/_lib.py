@@ -54,12 +54,14 @@ def lib():
     L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
     L.tkr_score_topk_workspace_bytes.restype = sz; L.tkr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.tkr_score_topk.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
+    L.tkr_score_topk_tc_workspace_bytes.restype = sz; L.tkr_score_topk_tc_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
+    L.tkr_score_topk_tc.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp, vp]
     L.tkr_score_topk_host_device_bytes.restype = sz
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
     for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_score_topk",
-                 "tkr_score_topk_host", "tkr_topk_merge"):
+                 "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -218,26 +220,37 @@ def bpr_sample(sampler: Sampler, first_draw, n, device="cuda"):
     return u, i, j
 
 
-def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset=0, out=None, ws=None):
-    """Device tensors in, device tensors out: (idx int32 [nu,k], score fp32 [nu,k])."""
+def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset=0, out=None, ws=None, engine="exact",
+               n_fallback=None):
+    """Device tensors in, device tensors out: (idx int32 [nu,k], score fp32 [nu,k]).
+    engine='exact': fp32 CUDA-core kernel; engine='tc': tcgen05 BF16 filter + exact refine (same bits).
+    n_fallback (tc only): optional int32 CUDA tensor [1] receiving the number of rows the exact kernel re-did."""
     f32 = torch.float32
     _need_cuda(U, V)
     nu, d = U.shape
     ni = V.shape[0]
     if V.shape[1] != d:
         raise ValueError("U and V disagree on d")
+    if engine not in ("exact", "tc"):
+        raise ValueError("engine must be 'exact' or 'tc'")
     if out is None:
         out = (torch.empty((nu, k), dtype=torch.int32, device=U.device), torch.empty((nu, k), dtype=f32, device=U.device))
-    need = lib().tkr_score_topk_workspace_bytes(nu, ni, d, k)
+    if engine == "tc":
+        need = lib().tkr_score_topk_tc_workspace_bytes(nu, ni, d, k, int(bias is not None))
+    else:
+        need = lib().tkr_score_topk_workspace_bytes(nu, ni, d, k)
     if ws is None or ws.numel() < need:
         ws = torch.empty(max(need, 256), dtype=torch.uint8, device=U.device)
     if rated_indptr is not None and (rated_idx is None or rated_idx.numel() == 0):
         rated_idx = torch.zeros(1, dtype=torch.int32, device=U.device)
+    args = (_dev(U, f32, "U"), nu, _dev(V, f32, "V"), ni, d, _dev(bias, f32, "bias"),
+            _dev(rated_indptr, torch.int64, "rated_indptr"), _dev(rated_idx, torch.int32, "rated_idx"),
+            int(k), int(col_offset), out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel())
     with torch.cuda.device(U.device):
-        _check(lib().tkr_score_topk(_dev(U, f32, "U"), nu, _dev(V, f32, "V"), ni, d, _dev(bias, f32, "bias"),
-                                    _dev(rated_indptr, torch.int64, "rated_indptr"), _dev(rated_idx, torch.int32, "rated_idx"),
-                                    int(k), int(col_offset), out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel(),
-                                    _stream()))
+        if engine == "tc":
+            _check(lib().tkr_score_topk_tc(*args, _dev(n_fallback, torch.int32, "n_fallback"), _stream()))
+        else:
+            _check(lib().tkr_score_topk(*args, _stream()))
     return out
 
 
