@@ -7,7 +7,7 @@
  *   tkr_bpr_step / _host   <- sess.run([solver, obj], feed_dict={u,i,j})   single/bpr.py:141
  *                             (graph = single/bpr.py:71-101, RMSProp :100; SGD = old/methods/bpr.py:57-61)
  *   tkr_bpr_sample         <- BPR._uniform_user_sampling                    single/bpr.py:155-165
- *   tkr_vbpr_step          <- sess.run(..., feed_dict={u,i,j,ic,jc})        single/vbpr.py:114 (graph :29-74)
+ *   tkr_vbpr_step/_project <- sess.run(..., feed_dict={u,i,j,ic,jc})        single/vbpr.py:114 (graph :29-74, export :124-126)
  *   tkr_score_topk / _host <- np.dot + np.argsort + rated-filter walk       evaluate.py:78,81,96-105
  *   tkr_topk_merge         <- (no reference equivalent: merges item-sharded candidates so the
  *                              sharded result equals the single-process one)
@@ -133,6 +133,27 @@ int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
                       const int32_t* u_host, const int32_t* i_host, const int32_t* j_host, int64_t batch,
                       int64_t n_steps, float* loss_host, void* staging, size_t staging_bytes, void* ws,
                       size_t ws_bytes, void* stream);
+
+/* VBPR (single/vbpr.py): content-aware BPR with item features F[n_items, d_feat] resident on the device.
+ * State in the layout the reference exports (vbpr.py:124-126):
+ *   U[n_users, k] = [ur | uc],  V[n_items, k] = [ir | F.E],  rb[n_items] (trainable rating bias),
+ *   bsum[n_items] = rb + F.c,  E[d_feat, k/2],  c[d_feat];  rms slots msU, msV (ir columns used), msrb, msE, msc.
+ * cfg.base.d = k (even).  tkr_vbpr_project refreshes V[:, k/2:] and bsum from E, c (call it once after
+ * initialising / importing E, c, rb); tkr_vbpr_step runs n_steps synchronous steps exactly like
+ * tkr_bpr_step (same triple / sampler / loss conventions) and leaves V, bsum projected with the final E, c. */
+typedef struct tkr_vbpr_cfg {
+    tkr_bpr_cfg base;
+    int32_t d_feat;
+    float lambda_e; /* single/vbpr.py:18 */
+} tkr_vbpr_cfg;
+size_t tkr_vbpr_workspace_bytes(const tkr_vbpr_cfg* cfg, int64_t batch);
+int tkr_vbpr_workspace_init(const tkr_vbpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes, void* stream);
+int tkr_vbpr_project(const tkr_vbpr_cfg* cfg, const float* F, const float* E, const float* c, const float* rb,
+                     float* V, float* bsum, void* stream);
+int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c,
+                  const float* F, float* msU, float* msV, float* msrb, float* msE, float* msc, const int32_t* u,
+                  const int32_t* i, const int32_t* j, int64_t batch, int64_t n_steps, const tkr_sampler* smp,
+                  uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes, void* stream);
 
 /* Draw `n` triples (draw indices first_draw .. first_draw+n-1) with the
  * semantics of single/bpr.py:155-165: user uniform over tr_users with

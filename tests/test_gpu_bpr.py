@@ -256,3 +256,37 @@ def test_full_size_properties_c2():
     for n in a:
         assert _rel(a[n].cpu().numpy(), b[n].cpu().numpy()) <= 1e-5, n
     _assert_ws_clean(cfg, B, ws)
+
+
+def test_bpr_class_train_export_resume(tmp_path, mini):
+    """train.py:3-9 on the mini fixture through the public class: device sampler, export, warm start."""
+    import single
+    m = single.BPR(k=16, seed=3)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    m.train(epochs=3, batch_size=64, epoch_sample_limit=20e2)          # float limit as in train.py:6 (D-1)
+    steps = 3 * (2000 // 64)
+    assert len(m.losses) == steps and m.losses[-1] < m.losses[0] * 1.05
+    assert m.fue.shape == (300, 16) and m.fie.shape == (160, 16) and m.fib.shape == (160, 1) and m.fue.dtype == np.float32
+    out = str(tmp_path / "embed" / "bpr")
+    m.export_embeddings(out)
+    assert sorted(os.listdir(out)) == ["final-B.dat", "final-U.dat", "final-V.dat", "weights.npz"]
+    fue = m.fue.copy()
+    m.train(epochs=1, batch_size=64, epoch_sample_limit=64, model_path=out)   # one step from the exported model
+    assert np.abs(m.fue - fue).max() < 1e-3                                    # started from the export, moved a little
+
+
+def test_bpr_class_numpy_sampler_matches_oracle_replay(mini):
+    """sampler='numpy' replays the reference RNG stream: same triples as oracle.sampler_ref -> state within 1e-4."""
+    import single
+    rng = np.random.default_rng(11)
+    m = single.BPR(k=32, sampler="numpy", seed=1)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    st = bpr_ref.new_state(m.n_users, m.n_items, 32, rng)
+    m.fue, m.fie, m.fib = st["U"].copy(), st["V"].copy(), st["b"].reshape(-1, 1).copy()   # inject initial weights (bpr.py:127-135)
+    np.random.seed(123)
+    m.train(epochs=1, batch_size=64, epoch_sample_limit=64 * 20)
+    rs = np.random.RandomState(123)
+    ub, ib, jb = sampler_ref.replay_sampler(m.tr_users, m.tr_data, m.n_items, 64, 20, rs)
+    ref_loss = bpr_ref.bpr_train(st, ub.ravel(), ib.ravel(), jb.ravel(), 64, bpr_ref.BprCfg())
+    assert _rel(m.fue, st["U"]) <= REL_TOL and _rel(m.fie, st["V"]) <= REL_TOL and _rel(m.fib.ravel(), st["b"]) <= REL_TOL
+    assert np.allclose(m.losses, ref_loss, rtol=1e-4)

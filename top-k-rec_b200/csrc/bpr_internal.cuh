@@ -1,0 +1,46 @@
+// Internal interface between bpr_step.cu and vbpr_step.cu (not part of the C ABI).
+#pragma once
+#include "common.cuh"
+
+namespace tkr {
+
+struct SamplerDev {
+    const int32_t* tr_users;
+    const int64_t* pos_indptr;
+    const int32_t* pos_idx;
+    uint32_t n_tr_users, n_items, seed_lo, seed_hi;
+};
+
+struct StepWs {            // views into the caller's workspace
+    float* GU; float* GV; float* Gb;
+    float* tchV;           // dense / data-parallel mode: per-item "touched" flag as fp32 (all-reduced with GV|Gb)
+    int32_t* cntU; int32_t* cntV;
+    int32_t* listU; int32_t* listV;
+    int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
+};
+
+// VBPR rides on the same kernels with concatenated rows U' = [ur|uc], V' = [ir | F.E]:
+//   item_cols  leading columns of an item row that are parameters (regularised, updated); the rest is the
+//              content projection, whose accumulated gradient W feeds the dense dE GEMM instead;
+//   b_reg      the trainable bias (rb) used for regularisation / update, while x reads b = rb + F.c;
+//   wq         per-item sum of -/+ s (the bias gradient without regularisation), the dc GEMV input.
+struct StepExtra {
+    int item_cols;
+    const float* b_reg;
+    float* wq;
+};
+
+constexpr int MODE_LIST = 0, MODE_DENSE = 1;
+
+size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B);
+int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out);
+int bpr_check_cfg(const tkr_bpr_cfg* cfg, int64_t B);
+int bpr_pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel);
+int bpr_make_sampler(const tkr_sampler* smp, SamplerDev* out);
+int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                      const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
+                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st);
+void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                      int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st);
+
+}  // namespace tkr

@@ -13,16 +13,9 @@
 //                     re-zeroes the accumulator (the workspace is left clean for the next step).
 // All B gradients are therefore taken at the pre-step snapshot and every touched row gets
 // exactly ONE optimiser update per step.
-#include "common.cuh"
+#include "bpr_internal.cuh"
 
 namespace tkr {
-
-struct SamplerDev {
-    const int32_t* tr_users;
-    const int64_t* pos_indptr;
-    const int32_t* pos_idx;
-    uint32_t n_tr_users, n_items, seed_lo, seed_hi;
-};
 
 __device__ __forceinline__ bool is_positive(const int32_t* __restrict__ pos, int n, int item) {
     int lo = 0, hi = n;
@@ -109,20 +102,6 @@ template <bool L1> __device__ __forceinline__ float reg_val(float x, float lam) 
     return 0.5f * lam * x * x;
 }
 
-struct StepWs {            // views into the caller's workspace
-    float* GU; float* GV; float* Gb;
-    float* tchV;           // dense / data-parallel mode: per-item "touched" flag as fp32 (all-reduced with GV|Gb)
-    int32_t* cntU; int32_t* cntV;
-    int32_t* listU; int32_t* listV;
-    int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
-};
-
-// How touched rows are found by the apply kernel:
-//   MODE_LIST   first toucher (returning atomic on cnt) appends the row to a list  -> small batches
-//   MODE_DENSE  plain flag stores, the apply kernel scans every row                -> batches that touch most rows,
-//               and data-parallel training (item flags are summed by the all-reduce)
-constexpr int MODE_LIST = 0, MODE_DENSE = 1;
-
 // Rows of one triple held in registers: NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
 template <int VW, int NCH>
 struct TripleRows {
@@ -151,12 +130,20 @@ template <int VW, int NCH, bool L1, bool SAMPLE>
 __global__ void __launch_bounds__(256) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
-    SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, float* __restrict__ loss_out) {
+    SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, StepExtra ex, float* __restrict__ loss_out) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d = cfg.d;
     const bool want_loss = loss_out != nullptr;
+    // item-row regularisation applies to the parameter columns only (all of them for plain BPR)
+    float lam_i[NCH], lam_j[NCH];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const bool par = (c * 32 + lane) * VW < ex.item_cols;
+        lam_i[c] = par ? cfg.lambda_i : 0.f;
+        lam_j[c] = par ? cfg.lambda_j : 0.f;
+    }
     float loss_acc = 0.f;          // per-lane partial; summed over the block at the end
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -171,8 +158,8 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
             if (SAMPLE) sample_triple(smp, first_draw + (uint64_t)n, u, i, j);
             else { u = __ldg(ub + n); i = __ldg(ib + n); j = __ldg(jb + n); }
         }
-        const float bi = valid ? __ldg(b + i) : 0.f, bj = valid ? __ldg(b + j) : 0.f;
-        const float bdiff = bi - bj;
+        const float bdiff = valid ? __ldg(b + i) - __ldg(b + j) : 0.f;
+        const float bi = valid ? __ldg(ex.b_reg + i) : 0.f, bj = valid ? __ldg(ex.b_reg + j) : 0.f;   // regularised bias
         float x_mine = 0.f, s_mine = 0.f;
 
         TripleRows<VW, NCH> cur, nxt;
@@ -194,7 +181,7 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
                 for (int c = 0; c < NCH; ++c)
 #pragma unroll
                     for (int q = 0; q < VW; ++q)
-                        loss_acc += reg_val<L1>(cur.u[c].v[q], cfg.lambda_u) + reg_val<L1>(cur.i[c].v[q], cfg.lambda_i) + reg_val<L1>(cur.j[c].v[q], cfg.lambda_j);
+                        loss_acc += reg_val<L1>(cur.u[c].v[q], cfg.lambda_u) + reg_val<L1>(cur.i[c].v[q], lam_i[c]) + reg_val<L1>(cur.j[c].v[q], lam_j[c]);
             }
             float* gu = ws.GU + (int64_t)ru * d;
             float* gi = ws.GV + (int64_t)ri * d;
@@ -207,8 +194,8 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
 #pragma unroll
                     for (int e = 0; e < VW; ++e) {
                         a.v[e] = fmaf(-s, cur.i[c].v[e] - cur.j[c].v[e], reg_grad<L1>(cur.u[c].v[e], cfg.lambda_u));  // gU   (App. A.2)
-                        p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], cfg.lambda_i));                  // gV_i
-                        q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], cfg.lambda_j));                   // gV_j
+                        p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], lam_i[c]));                      // gV_i
+                        q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], lam_j[c]));                       // gV_j
                     }
                     a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
                 }
@@ -226,6 +213,7 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
             }
             atomicAdd(ws.Gb + i, -s_mine + reg_grad<L1>(bi, cfg.lambda_b));
             atomicAdd(ws.Gb + j, s_mine + reg_grad<L1>(bj, cfg.lambda_b));
+            if (ex.wq != nullptr) { atomicAdd(ex.wq + i, -s_mine); atomicAdd(ex.wq + j, s_mine); }
             if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)
                 loss_acc += fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
         }
@@ -243,9 +231,16 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
     }
 }
 
+// `d` leading columns are parameters; columns [d, dz) of the accumulator row are only re-zeroed
 template <int VW>
 __device__ __forceinline__ void apply_row(const tkr_bpr_cfg& cfg, float* __restrict__ var, float* __restrict__ ms,
-                                          float* __restrict__ G, int d, int lane) {
+                                          float* __restrict__ G, int d, int lane, int dz = 0) {
+    for (int off = d + lane * VW; off < dz; off += 32 * VW) {
+        Vec<VW> z;
+#pragma unroll
+        for (int t = 0; t < VW; ++t) z.v[t] = 0.f;
+        z.store(G + off);
+    }
     for (int off = lane * VW; off < d; off += 32 * VW) {
         Vec<VW> g, v, m, z;
         g.load(G + off); v.load(var + off);
@@ -276,7 +271,7 @@ template <int VW>
 __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V,
                                                         float* __restrict__ b, float* __restrict__ msU,
                                                         float* __restrict__ msV, float* __restrict__ msb, StepWs ws,
-                                                        int mode) {
+                                                        int mode, StepExtra ex) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -293,9 +288,9 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
             } else {
                 const int r = (int)(w - cfg.n_users);
                 if (ws.tchV[r] == 0.0f) continue;
-                apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
+                apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, ex.item_cols, lane, d);
                 __syncwarp();
-                if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.tchV[r] = 0.0f; }
+                if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.tchV[r] = 0.0f; if (ex.wq) ex.wq[r] = 0.0f; }
             }
         }
         return;
@@ -308,8 +303,8 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
             if (lane == 0) ws.cntU[r] = 0;
         } else {
             const int r = ws.listV[w - nU];
-            apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, d, lane);
-            if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.cntV[r] = 0; }
+            apply_row<VW>(cfg, V + (int64_t)r * d, msV + (int64_t)r * d, ws.GV + (int64_t)r * d, ex.item_cols, lane, d);
+            if (lane == 0) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); ws.cntV[r] = 0; if (ex.wq) ex.wq[r] = 0.0f; }
         }
     }
     __syncthreads();
@@ -323,7 +318,7 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
 
 struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, total; };
 
-static WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
+WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     WsLayout L;
     const size_t d = cfg->d, nu = cfg->n_users, ni = cfg->n_items;
     size_t o = 0;
@@ -343,7 +338,7 @@ static WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     return L;
 }
 
-static int carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out) {
+int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out) {
     const WsLayout L = ws_layout(cfg, B);
     if (ws == nullptr || ws_bytes < L.total) { set_error("bpr workspace too small: have %zu, need %zu", ws_bytes, L.total); return TKR_ERR_WORKSPACE; }
     if ((uintptr_t)ws % 256 != 0) { set_error("bpr workspace must be 256-byte aligned"); return TKR_ERR_WORKSPACE; }
@@ -355,7 +350,7 @@ static int carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, S
     return TKR_OK;
 }
 
-static int check_cfg(const tkr_bpr_cfg* cfg, int64_t B) {
+int bpr_check_cfg(const tkr_bpr_cfg* cfg, int64_t B) {
     TKR_CHECK_ARG(cfg != nullptr, "cfg is NULL");
     TKR_CHECK_ARG(cfg->n_users > 0 && cfg->n_items > 0 && cfg->d > 0, "n_users, n_items, d must be positive");
     TKR_CHECK_ARG(B > 0 && B < (int64_t)1 << 31, "batch must be in [1, 2^31)");
@@ -367,47 +362,49 @@ static inline int64_t grid_cap() { return (int64_t)kNumSMs * 8; }   // 8 CTAs x 
 
 // Dense flags pay a scan of every row in the apply kernel; worth it once a batch touches a good share of
 // the rows (and mandatory in data-parallel mode, where the item flags travel with the all-reduce).
-static inline int pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel) {
+int bpr_pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel) {
     return (data_parallel || 3 * B >= ((int64_t)cfg->n_users + cfg->n_items) / 8) ? MODE_DENSE : MODE_LIST;
 }
 
 template <int VW, int NCH>
 static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                         const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                        const StepWs& ws, int mode, float* loss, cudaStream_t st) {
+                        const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st) {
     // triples per warp: spread small batches over all resident warps, cap at one per lane
     const int64_t max_warps = grid_cap() * 8;
     int64_t tpw64 = (B + max_warps - 1) / max_warps;
     const int tpw = tpw64 > 32 ? 32 : (int)tpw64;
     int64_t blocks = ((B + tpw - 1) / tpw + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-#define TKR_K(L1_, S_) bpr_grad_kernel<VW, NCH, L1_, S_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, loss)
+#define TKR_K(L1_, S_) bpr_grad_kernel<VW, NCH, L1_, S_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss)
     if (cfg->l1) { if (u == nullptr) TKR_K(true, true); else TKR_K(true, false); }
     else { if (u == nullptr) TKR_K(false, true); else TKR_K(false, false); }
 #undef TKR_K
 }
 
-static void launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
-                         int64_t B, const StepWs& ws, int mode, cudaStream_t st) {
+void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
+                      int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st) {
     const int d = cfg->d;
     int64_t rows = mode == MODE_DENSE ? (int64_t)cfg->n_users + cfg->n_items
                                       : (B < cfg->n_users ? B : cfg->n_users) + (2 * B < cfg->n_items ? 2 * B : cfg->n_items);
     int64_t blocks = (rows + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-    if (d % 4 == 0) bpr_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
-    else if (d % 2 == 0) bpr_apply_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
-    else bpr_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode);
+    const int a = ex.item_cols;   // vector width must divide both the row pitch and the parameter-column count
+    if (d % 4 == 0 && a % 4 == 0) bpr_apply_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode, ex);
+    else if (d % 2 == 0 && a % 2 == 0) bpr_apply_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode, ex);
+    else bpr_apply_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, ws, mode, ex);
 }
 
-static int dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
-                         const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                         const StepWs& ws, int mode, float* loss, cudaStream_t st) {
+int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
+                      const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
+                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st) {
     const int d = cfg->d;
-    const int vw = (d % 4 == 0) ? 4 : (d % 2 == 0) ? 2 : 1;   // widest vector the row pitch allows
+    const int a = ex.item_cols;
+    const int vw = (d % 4 == 0 && a % 4 == 0) ? 4 : (d % 2 == 0 && a % 2 == 0) ? 2 : 1;   // widest vector the row pitch allows
     const int nch = (d + 32 * vw - 1) / (32 * vw);
     if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
     const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
-#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, loss, st)
+#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, ex, loss, st)
     if (vw == 4) { if (nchp == 1) TKR_GRAD(4, 1); else if (nchp == 2) TKR_GRAD(4, 2); else if (nchp == 4) TKR_GRAD(4, 4); else TKR_GRAD(4, 8); }
     else if (vw == 2) { if (nchp == 1) TKR_GRAD(2, 1); else if (nchp == 2) TKR_GRAD(2, 2); else if (nchp == 4) TKR_GRAD(2, 4); else TKR_GRAD(2, 8); }
     else { if (nchp == 1) TKR_GRAD(1, 1); else if (nchp == 2) TKR_GRAD(1, 2); else if (nchp == 4) TKR_GRAD(1, 4); else TKR_GRAD(1, 8); }
@@ -416,9 +413,13 @@ static int dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V,
     return TKR_OK;
 }
 
+size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B) { return ws_layout(cfg, B).total; }
+
 }  // namespace tkr
 
 using namespace tkr;
+
+static inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) { return StepExtra{cfg->d, b, nullptr}; }
 
 extern "C" size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t B) {
     if (cfg == nullptr || B <= 0 || cfg->n_users <= 0 || cfg->n_items <= 0 || cfg->d <= 0) return 0;
@@ -426,7 +427,7 @@ extern "C" size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t B) {
 }
 
 extern "C" int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t B, int64_t* offsets) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     TKR_CHECK_ARG(offsets != nullptr, "offsets is NULL");
     const WsLayout L = ws_layout(cfg, B);
     const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.total};
@@ -435,14 +436,15 @@ extern "C" int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t B, int64
 }
 
 extern "C" int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, void* stream) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     StepWs v;
-    if (int rc = carve(cfg, B, ws, ws_bytes, &v)) return rc;
+    if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &v)) return rc;
     TKR_CUDA(cudaMemsetAsync(ws, 0, ws_layout(cfg, B).total, (cudaStream_t)stream));
     return TKR_OK;
 }
 
-static int make_sampler(const tkr_sampler* smp, SamplerDev* out) {
+namespace tkr {
+int bpr_make_sampler(const tkr_sampler* smp, SamplerDev* out) {
     TKR_CHECK_ARG(smp != nullptr, "sampler is NULL");
     TKR_CHECK_ARG(smp->tr_users && smp->pos_indptr && smp->pos_idx, "sampler tables are NULL");
     TKR_CHECK_ARG(smp->n_tr_users > 0 && smp->n_items > 0, "sampler needs n_tr_users > 0 and n_items > 0");
@@ -451,11 +453,12 @@ static int make_sampler(const tkr_sampler* smp, SamplerDev* out) {
     out->seed_lo = (uint32_t)smp->seed; out->seed_hi = (uint32_t)(smp->seed >> 32);
     return TKR_OK;
 }
+}  // namespace tkr
 
 extern "C" int tkr_bpr_sample(const tkr_sampler* smp, uint64_t first_draw, int64_t n, int32_t* u_out, int32_t* i_out,
                               int32_t* j_out, void* stream) {
     SamplerDev s;
-    if (int rc = make_sampler(smp, &s)) return rc;
+    if (int rc = bpr_make_sampler(smp, &s)) return rc;
     TKR_CHECK_ARG(n >= 0 && u_out && i_out && j_out, "bad output arguments");
     if (n == 0) return TKR_OK;
     int64_t blocks = (n + 255) / 256;
@@ -474,28 +477,28 @@ static int check_state(const tkr_bpr_cfg* cfg, const float* U, const float* V, c
 extern "C" int tkr_bpr_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                             const int32_t* i, const int32_t* j, int64_t B, const tkr_sampler* smp, uint64_t first_draw,
                             float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     if (int rc = check_state(cfg, U, V, b)) return rc;
     SamplerDev sd = {};
     if (u == nullptr) {
-        if (int rc = make_sampler(smp, &sd)) return rc;
+        if (int rc = bpr_make_sampler(smp, &sd)) return rc;
         TKR_CHECK_ARG(smp->n_items == cfg->n_items, "sampler n_items != cfg n_items");
     } else {
         TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
     }
     StepWs w;
-    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
-    return dispatch_grad(cfg, U, V, b, u, i, j, B, sd, first_draw, w, pick_mode(cfg, B, data_parallel), loss_out, (cudaStream_t)stream);
+    if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    return bpr_dispatch_grad(cfg, U, V, b, u, i, j, B, sd, first_draw, w, bpr_pick_mode(cfg, B, data_parallel), plain_extra(cfg, b), loss_out, (cudaStream_t)stream);
 }
 
 extern "C" int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                              int64_t B, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     if (int rc = check_state(cfg, U, V, b)) return rc;
     TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
     StepWs w;
-    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
-    launch_apply(cfg, U, V, b, msU, msV, msb, B, w, pick_mode(cfg, B, data_parallel), (cudaStream_t)stream);
+    if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    bpr_launch_apply(cfg, U, V, b, msU, msV, msb, B, w, bpr_pick_mode(cfg, B, data_parallel), plain_extra(cfg, b), (cudaStream_t)stream);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
@@ -504,29 +507,30 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
                             const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps,
                             const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes,
                             void* stream) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     if (int rc = check_state(cfg, U, V, b)) return rc;
     TKR_CHECK_ARG(cfg->optimizer == TKR_OPT_SGD || (msU && msV && msb), "RMSProp needs the msU/msV/msb slots");
     TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
     SamplerDev sd = {};
     if (u == nullptr) {
-        if (int rc = make_sampler(smp, &sd)) return rc;
+        if (int rc = bpr_make_sampler(smp, &sd)) return rc;
         TKR_CHECK_ARG(smp->n_items == cfg->n_items, "sampler n_items != cfg n_items");
     } else {
         TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
     }
     StepWs w;
-    if (int rc = carve(cfg, B, ws, ws_bytes, &w)) return rc;
+    if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &w)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int mode = pick_mode(cfg, B, 0);
+    const int mode = bpr_pick_mode(cfg, B, 0);
+    const StepExtra ex = plain_extra(cfg, b);
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     for (int64_t t = 0; t < n_steps; ++t) {
         const int32_t* ut = u ? u + t * B : nullptr;
         const int32_t* it = u ? i + t * B : nullptr;
         const int32_t* jt = u ? j + t * B : nullptr;
         float* lt = loss_out ? loss_out + t : nullptr;
-        if (int rc = dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, mode, lt, st)) return rc;
-        launch_apply(cfg, U, V, b, msU, msV, msb, B, w, mode, st);
+        if (int rc = bpr_dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, mode, ex, lt, st)) return rc;
+        bpr_launch_apply(cfg, U, V, b, msU, msV, msb, B, w, mode, ex, st);
         TKR_LAUNCH_CHECK();
     }
     return TKR_OK;
@@ -536,7 +540,7 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
                                  float* msb, const int32_t* u_host, const int32_t* i_host, const int32_t* j_host,
                                  int64_t B, int64_t n_steps, float* loss_host, void* staging, size_t staging_bytes,
                                  void* ws, size_t ws_bytes, void* stream) {
-    if (int rc = check_cfg(cfg, B)) return rc;
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
     TKR_CHECK_ARG(u_host && i_host && j_host && n_steps > 0, "host triples are NULL or n_steps <= 0");
     const size_t n = (size_t)B * (size_t)n_steps;
     const size_t need = align_up(n * 4, 256) * 3 + align_up((size_t)n_steps * 4, 256);

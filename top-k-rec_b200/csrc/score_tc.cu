@@ -30,7 +30,8 @@ constexpr int FM = 128, FN = 256, FK = 64;        // MMA tile; FK bf16 = one 128
 constexpr int A_CHUNK_BYTES = FM * FK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = FN * FK * 2;        // 32 KB
 constexpr int KPRIME = 64, CAP = 128;             // kept candidates / buffer capacity per row
-constexpr int F_THREADS = 192;                    // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int F_EPI_WARPS = 8;                    // two per TMEM lane quarter: each takes half the columns of a tile
+constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 constexpr int MAX_KB = 4;                         // d_pad <= 256
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -45,17 +46,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    uint32_t ok;   // the hardware parks the thread up to the hint (ticks) before reporting "not yet"
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (++spins > (1u << 22)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -139,8 +139,8 @@ struct FilterParams {
     int kb, stages, tiles_per_split;
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
-    uint64_t* cand;          // [n_splits][nu][CAP] scratch keys
-    int32_t* out_idx;        // [n_splits][nu][KPRIME] approximate lists, (score desc, col desc)
+    uint64_t* cand;          // [2 * n_splits][nu][CAP] scratch keys (list = split * 2 + column half)
+    int32_t* out_idx;        // [2 * n_splits][nu][KPRIME] approximate lists, (score desc, col desc)
     float* out_score;
 };
 
@@ -202,9 +202,19 @@ __device__ __noinline__ float warp_compact(uint64_t* buf, int n, int lane, uint6
     return last ? ord_to_f32((uint32_t)(last >> 32)) : -INFINITY;
 }
 
-// Fast path: one 3-input-max tree over the thread's 32 scores and a compare against its threshold.
-// Slow path (some score reaches the threshold; rare once the threshold has risen): spill the chunk to
-// local memory, walk the hit mask, drop rated columns, append keys to the row's candidate buffer.
+// returns 1 if the key was appended at buf[cnt]
+__device__ __noinline__ int push_candidate(float sv, int64_t col, const FilterParams& p, int64_t r_lo, int64_t r_hi,
+                                           uint64_t* __restrict__ buf, int cnt) {
+    if (col >= p.ni) return 0;
+    const int32_t gc = (int32_t)(col + p.col_offset);
+    if (p.rated_indptr != nullptr && rated_has(p.rated_idx, r_lo, r_hi, gc)) return 0;
+    buf[cnt] = make_key(sv + 0.0f, gc);
+    return 1;
+}
+
+// Fast path: a max tree over the thread's 32 scores (groups of 4) and one compare against its threshold.
+// Slow path (some score reaches the threshold; rare once the threshold has risen): only the groups whose
+// max passes are opened; survivors lose rated columns and are appended to the row's candidate buffer.
 __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, const FilterParams& p, int64_t r_lo, int64_t r_hi,
                                            uint64_t* __restrict__ buf, int& cnt, float tau) {
     float m[8];
@@ -213,21 +223,13 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, 
         m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
     const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
     if (mx >= tau) {
-        float loc[32];
-        unsigned mask = 0;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            loc[t] = __uint_as_float(v[t]);
-            mask |= (__uint_as_float(v[t]) >= tau ? 1u : 0u) << t;
-        }
-        while (mask) {
-            const int t = __ffs(mask) - 1;
-            mask &= mask - 1;
-            if (c0 + t < p.ni) {
-                const int32_t gc = (int32_t)(c0 + t + p.col_offset);
-                if (p.rated_indptr == nullptr || !rated_has(p.rated_idx, r_lo, r_hi, gc)) {
-                    buf[cnt] = make_key(loc[t] + 0.0f, gc);
-                    ++cnt;
+        for (int g = 0; g < 8; ++g) {
+            if (m[g] >= tau) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float sv = __uint_as_float(v[4 * g + e]);
+                    if (sv >= tau) cnt += push_candidate(sv, c0 + 4 * g + e, p, r_lo, r_hi, buf, cnt);
                 }
             }
         }
@@ -236,8 +238,7 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, 
 
 // Rows whose buffer could overflow on the next chunk are compacted to their best KPRIME (warp-wide sort),
 // which also raises their threshold.
-__device__ __forceinline__ void compact_if_needed(uint64_t* buf, int& cnt, float& tau, int lane, uint64_t (&skey)[4]) {
-    __syncwarp();
+__device__ __forceinline__ void compact_if_needed(uint64_t* buf, int& cnt, float& tau, int lane, uint64_t (&skey)[4], volatile float* tau_pub) {
     unsigned fullm = __ballot_sync(0xffffffffu, cnt > CAP - 32);
     while (fullm) {
         const int src = __ffs(fullm) - 1;
@@ -245,7 +246,7 @@ __device__ __forceinline__ void compact_if_needed(uint64_t* buf, int& cnt, float
         const int n_src = __shfl_sync(0xffffffffu, cnt, src);
         uint64_t* b_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
         const float nt = warp_compact(b_src, n_src, lane, skey);
-        if (lane == src) { cnt = KPRIME; tau = nt; }
+        if (lane == src) { cnt = KPRIME; tau = fmaxf(tau, nt); *tau_pub = tau; }
     }
 }
 
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     uint64_t* tempty = bars + 18;          // [2]       epilogue -> MMA
     uint64_t* afull = bars + 20;           //           U tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+    float* tau_sh = reinterpret_cast<float*>(bars + 22);   // [2][FM]: thresholds the two column halves publish to each other
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * FM;
@@ -272,10 +274,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_EPI_WARPS); }
         mbar_init(afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int t = threadIdx.x; t < 2 * FM; t += F_THREADS) tau_sh[t] = -INFINITY;
     if (warp == 1) {   // whole TMEM: two 256-column fp32 accumulators (1 CTA per SM, smem-limited)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -326,41 +329,49 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             }
         }
     } else {
-        // ===================== epilogue: thread == user row =====================
+        // ===================== epilogue: thread == (user row, column half) =====================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;                             // columns [half*128, half*128 + 128) of every tile
         const int row = q * 32 + lane;
         const bool row_ok = row0 + row < p.nu;
-        uint64_t* buf = p.cand + ((size_t)split * p.nu + (size_t)(row_ok ? row0 + row : 0)) * CAP;
+        const int list = split * 2 + half;                            // each (split, half) produces its own candidate list
+        uint64_t* buf = p.cand + ((size_t)list * p.nu + (size_t)(row_ok ? row0 + row : 0)) * CAP;
         const int64_t r_lo = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row) : 0;
         const int64_t r_hi = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row + 1) : 0;
         float tau = row_ok ? -INFINITY : INFINITY;                    // padded rows never collect
+        volatile float* tau_mine = tau_sh + half * FM + row;
+        volatile float* tau_other = tau_sh + (half ^ 1) * FM + row;
         int cnt = 0;
         uint64_t skey[4];
+        constexpr int NCHUNK = FN / 2 / 32;                           // 4 chunks of 32 columns per thread per tile
         int tl = 0;
         for (int64_t tile = t0; tile < t1; ++tile, ++tl) {
             const int acc = tl & 1;
             mbar_wait(tfull + acc, (tl >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * FN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * FN + (uint32_t)half * (FN / 2);
+            const int64_t cbase = tile * FN + half * (FN / 2);
+            // the 64-th best of EITHER half bounds the row's 64-th best from below: adopt the partner's threshold
+            tau = fmaxf(tau, *tau_other);
             // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is scanned
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
 #pragma unroll 1
-            for (int cc = 0; cc < FN / 32; cc += 2) {
+            for (int cc = 0; cc < NCHUNK; cc += 2) {
                 tmem_ld_wait();
                 tmem_ld32(taddr + (cc + 1) * 32, vb);
-                scan_chunk(va, tile * FN + cc * 32, p, r_lo, r_hi, buf, cnt, tau);
-                compact_if_needed(buf, cnt, tau, lane, skey);
+                scan_chunk(va, cbase + cc * 32, p, r_lo, r_hi, buf, cnt, tau);
+                compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
                 tmem_ld_wait();
-                if (cc + 2 < FN / 32) tmem_ld32(taddr + (cc + 2) * 32, va);
-                scan_chunk(vb, tile * FN + (cc + 1) * 32, p, r_lo, r_hi, buf, cnt, tau);
-                compact_if_needed(buf, cnt, tau, lane, skey);
+                if (cc + 2 < NCHUNK) tmem_ld32(taddr + (cc + 2) * 32, va);
+                scan_chunk(vb, cbase + (cc + 1) * 32, p, r_lo, r_hi, buf, cnt, tau);
+                compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
-        // final: sorted best-KPRIME list of every row of this warp
+        // final: sorted best-KPRIME list of every (row, half) of this warp
         __syncwarp();
         for (int src = 0; src < 32; ++src) {
             const int n_src = __shfl_sync(0xffffffffu, cnt, src);
@@ -368,7 +379,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             const int64_t grow = row0 + q * 32 + src;
             if (grow >= p.nu) continue;                               // warp-uniform
             warp_compact(b_src, n_src, lane, skey);
-            const int64_t o = ((int64_t)split * p.nu + grow) * KPRIME;
+            const int64_t o = ((int64_t)list * p.nu + grow) * KPRIME;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const uint64_t key = skey[r];
@@ -495,13 +506,13 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
     P->kb = P->dpad / FK;
     if (P->kb > MAX_KB || k > 48 || nu <= 0 || ni <= 0) return false;
     P->stages = P->kb >= 4 ? 4 : 5;
-    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * B_STAGE_BYTES + 256;
+    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * B_STAGE_BYTES + 256 + 2 * FM * 4;
     const int64_t row_tiles = (nu + FM - 1) / FM, ntiles = (ni + FN - 1) / FN;
     // one CTA per SM; split the items only when the user tiles alone cannot fill the chip
     int64_t ns = row_tiles >= kNumSMs ? 1 : (kNumSMs + row_tiles - 1) / row_tiles;
     const int64_t maxs = ntiles / 16 > 0 ? ntiles / 16 : 1;
     if (ns > maxs) ns = maxs;
-    if (ns > 32) ns = 32;
+    if (ns > 16) ns = 16;
     P->tps = (int)((ntiles + ns - 1) / ns);
     P->ns = (int)((ntiles + P->tps - 1) / P->tps);
     size_t o = 0;
@@ -510,9 +521,9 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
     P->o_vbf = take((size_t)ni * P->dpad * 2);
     P->o_unorm = take((size_t)nu * 4);
     P->o_scal = take(64);                                   // [0] vnorm_max  [1] bias_max  [2] n_fail
-    P->o_cand = take((size_t)P->ns * nu * CAP * 8);
-    P->o_sidx = take((size_t)P->ns * nu * KPRIME * 4);
-    P->o_sscore = take((size_t)P->ns * nu * KPRIME * 4);
+    P->o_cand = take((size_t)2 * P->ns * nu * CAP * 8);            // one list per (item split, column half)
+    P->o_sidx = take((size_t)2 * P->ns * nu * KPRIME * 4);
+    P->o_sscore = take((size_t)2 * P->ns * nu * KPRIME * 4);
     P->o_midx = take((size_t)nu * KPRIME * 4);
     P->o_mscore = take((size_t)nu * KPRIME * 4);
     P->o_fail = take((size_t)nu * 4);
@@ -567,13 +578,12 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     FilterParams fp;
     fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
-    fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
+    fp.out_idx = sidx; fp.out_score = sscore;
     TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
     dim3 grid((unsigned)((nu + FM - 1) / FM), (unsigned)P.ns);
     score_filter_kernel<<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
     TKR_LAUNCH_CHECK();
-    if (P.ns > 1)
-        if (int rc = tkr_topk_merge(sidx, sscore, P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
+    if (int rc = tkr_topk_merge(sidx, sscore, 2 * P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
 
     // |bf16 tensor-core score - exact fma-chain score| <= coef * |u| * |v|: two roundings to 8-bit significands
     // (2^-8 + 2^-18 on every product, Cauchy-Schwarz over the row) + fp32 accumulation slack on both sides.

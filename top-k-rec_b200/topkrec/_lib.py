@@ -21,6 +21,10 @@ class tkr_bpr_cfg(C.Structure):
                 ("l1", C.c_int32), ("optimizer", C.c_int32)]
 
 
+class tkr_vbpr_cfg(C.Structure):
+    _fields_ = [("base", tkr_bpr_cfg), ("d_feat", C.c_int32), ("lambda_e", C.c_float)]
+
+
 class tkr_sampler(C.Structure):
     _fields_ = [("tr_users", C.c_void_p), ("n_tr_users", C.c_int32), ("pos_indptr", C.c_void_p),
                 ("pos_idx", C.c_void_p), ("n_items", C.c_int32), ("seed", C.c_uint64)]
@@ -52,6 +56,11 @@ def lib():
     L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
     L.tkr_bpr_step_host.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, vp, vp, sz, vp, sz, vp]
     L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
+    vcfgp = C.POINTER(tkr_vbpr_cfg)
+    L.tkr_vbpr_workspace_bytes.restype = sz; L.tkr_vbpr_workspace_bytes.argtypes = [vcfgp, i64]
+    L.tkr_vbpr_workspace_init.argtypes = [vcfgp, i64, vp, sz, vp]
+    L.tkr_vbpr_project.argtypes = [vcfgp] + [vp] * 6 + [vp]
+    L.tkr_vbpr_step.argtypes = [vcfgp] + [vp] * 12 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
     L.tkr_score_topk_workspace_bytes.restype = sz; L.tkr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.tkr_score_topk.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
     L.tkr_score_topk_tc_workspace_bytes.restype = sz; L.tkr_score_topk_tc_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
@@ -60,7 +69,7 @@ def lib():
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
-    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_score_topk",
+    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge"):
         getattr(L, name).restype = C.c_int
     _lib = L
@@ -118,6 +127,19 @@ class BprCfg:
             raise ValueError("optimizer must be 'rmsprop' or 'sgd'")
         self.c = tkr_bpr_cfg(int(n_users), int(n_items), int(d), lambda_u, lambda_i, lambda_j, lambda_b, lr,
                              rms_decay, rms_eps, 0 if mode == "l2" else 1, 0 if optimizer == "rmsprop" else 1)
+
+    @property
+    def ptr(self):
+        return C.byref(self.c)
+
+
+class VbprCfg:
+    """Host mirror of tkr_vbpr_cfg (single/vbpr.py:18 defaults); k must be even."""
+
+    def __init__(self, n_users, n_items, k, d_feat, lambda_u=2.5e-3, lambda_i=2.5e-3, lambda_j=2.5e-4, lambda_b=0.0, lambda_e=0.0,
+                 lr=1.0e-4, mode="l2", optimizer="rmsprop"):
+        base = BprCfg(n_users, n_items, k, lambda_u, lambda_i, lambda_j, lambda_b, lr, mode, optimizer).c
+        self.c = tkr_vbpr_cfg(base, int(d_feat), float(lambda_e))
 
     @property
     def ptr(self):
@@ -209,6 +231,39 @@ def bpr_step_host(cfg: BprCfg, U, V, b, msU, msV, msb, u_host, i_host, j_host, b
                                        u_host.data_ptr(), i_host.data_ptr(), j_host.data_ptr(), int(batch), int(n_steps),
                                        loss_host.data_ptr() if loss_host is not None else None,
                                        staging.data_ptr(), staging.numel(), ws.data_ptr(), ws.numel(), _stream()))
+
+
+VBPR_STATE = ("U", "V", "rb", "bsum", "E", "c")
+VBPR_SLOTS = ("msU", "msV", "msrb", "msE", "msc")
+
+
+def vbpr_workspace(cfg: VbprCfg, batch, device="cuda"):
+    _need_cuda()
+    n = lib().tkr_vbpr_workspace_bytes(cfg.ptr, int(batch))
+    ws = torch.empty(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(ws.device):
+        _check(lib().tkr_vbpr_workspace_init(cfg.ptr, int(batch), ws.data_ptr(), n, _stream()))
+    return ws
+
+
+def vbpr_project(cfg: VbprCfg, st, F):
+    """Refresh st['V'][:, k/2:] = F.E and st['bsum'] = rb + F.c."""
+    f32 = torch.float32
+    _need_cuda(F, st["V"])
+    with torch.cuda.device(F.device):
+        _check(lib().tkr_vbpr_project(cfg.ptr, _dev(F, f32, "F"), _dev(st["E"], f32, "E"), _dev(st["c"], f32, "c"), _dev(st["rb"], f32, "rb"),
+                                      _dev(st["V"], f32, "V"), _dev(st["bsum"], f32, "bsum"), _stream()))
+
+
+def vbpr_step(cfg: VbprCfg, st, F, u, i, j, batch, n_steps, ws, loss=None, sampler=None, first_draw=0):
+    """st: dict of CUDA tensors U, V, rb, bsum, E, c and the slots msU, msV, msrb, msE, msc."""
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(F, st["U"], ws)
+    with torch.cuda.device(F.device):
+        _check(lib().tkr_vbpr_step(cfg.ptr, *(_dev(st[n], f32, n) for n in VBPR_STATE), _dev(F, f32, "F"),
+                                   *(_dev(st.get(n), f32, n) for n in VBPR_SLOTS), _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"),
+                                   int(batch), int(n_steps), sampler.ptr if sampler is not None else None, int(first_draw),
+                                   _dev(loss, f32, "loss"), ws.data_ptr(), ws.numel(), _stream()))
 
 
 def bpr_sample(sampler: Sampler, first_draw, n, device="cuda"):
