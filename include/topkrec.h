@@ -190,6 +190,10 @@ int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, in
                       int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
                       void* stream);
 
+/* Profiling aid: device buffer of [n_ctas][10 warps][4] int64 cycle counters filled by the filter kernel
+ * (total / wait cycles per warp role); NULL (default) disables it. */
+void tkr_debug_set_filter_counters(long long* dev_buf);
+
 /* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
  * U_host/V_host/bias_host/rated_* in host memory, results to host memory.
  * `dev` is device scratch of >= tkr_score_topk_host_device_bytes(). */

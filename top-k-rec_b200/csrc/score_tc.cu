@@ -31,7 +31,8 @@ constexpr int A_CHUNK_BYTES = FM * FK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = FN * FK * 2;        // 32 KB
 constexpr int KPRIME = 64, CAP = 128;             // kept candidates / buffer capacity per row
 constexpr int F_EPI_WARPS = 8;                    // two per TMEM lane quarter: each takes half the columns of a tile
-constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;  // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
+constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;  // warps 0-7 epilogue, warp 8 TMA, warp 9 MMA + TMEM alloc
+constexpr int W_TMA = F_EPI_WARPS, W_MMA = F_EPI_WARPS + 1;   // highest warp ids: the SMSP arbiter favours them over the busy epilogue warps
 constexpr int MAX_KB = 4;                         // d_pad <= 256
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -46,16 +47,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;   // the hardware parks the thread up to the hint (ticks) before reporting "not yet"
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+    uint32_t ok;   // (no suspend-time hint: with one the compiler emits NANOSLEEP between polls and the MMA issue lags)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) __trap();
+        if (++spins > (1u << 26)) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -140,6 +141,7 @@ struct FilterParams {
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
     uint64_t* cand;          // [2 * n_splits][nu][CAP] scratch keys (list = split * 2 + column half)
+    long long* dbg;          // optional [gridDim.x*gridDim.y][10][4] cycle counters (profiling aid), may be NULL
     int32_t* out_idx;        // [2 * n_splits][nu][KPRIME] approximate lists, (score desc, col desc)
     float* out_score;
 };
@@ -202,37 +204,42 @@ __device__ __noinline__ float warp_compact(uint64_t* buf, int n, int lane, uint6
     return last ? ord_to_f32((uint32_t)(last >> 32)) : -INFINITY;
 }
 
-// returns 1 if the key was appended at buf[cnt]
-__device__ __noinline__ int push_candidate(float sv, int64_t col, const FilterParams& p, int64_t r_lo, int64_t r_hi,
-                                           uint64_t* __restrict__ buf, int cnt) {
-    if (col >= p.ni) return 0;
-    const int32_t gc = (int32_t)(col + p.col_offset);
-    if (p.rated_indptr != nullptr && rated_has(p.rated_idx, r_lo, r_hi, gc)) return 0;
-    buf[cnt] = make_key(sv + 0.0f, gc);
-    return 1;
-}
-
-// Fast path: a max tree over the thread's 32 scores (groups of 4) and one compare against its threshold.
-// Slow path (some score reaches the threshold; rare once the threshold has risen): only the groups whose
-// max passes are opened; survivors lose rated columns and are appended to the row's candidate buffer.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, const FilterParams& p, int64_t r_lo, int64_t r_hi,
-                                           uint64_t* __restrict__ buf, int& cnt, float tau) {
+// Fast path: a max tree over the thread's 32 scores and one compare against its threshold; the warp votes and
+// moves on when no lane has a hit (uniform branch, no divergence).
+// Slow path (rare once the thresholds have risen): for each hit lane the warp transposes that lane's 32 scores
+// with shuffles so that lane t holds column t, tests them against the row's threshold in parallel, drops rated
+// columns (parallel binary searches) and appends the survivors to the row's buffer with ballot-derived slots.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, int64_t ni, int64_t col_offset,
+                                           const int32_t* __restrict__ rated_idx, bool has_rated, int64_t r_lo, int64_t r_hi,
+                                           uint64_t* buf, int& cnt, float tau, int lane) {
     float m[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g)
         m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
     const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-    if (mx >= tau) {
+    unsigned hits = __ballot_sync(0xffffffffu, mx >= tau);
+    while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        float x = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (m[g] >= tau) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float sv = __uint_as_float(v[4 * g + e]);
-                    if (sv >= tau) cnt += push_candidate(sv, c0 + 4 * g + e, p, r_lo, r_hi, buf, cnt);
-                }
-            }
+        for (int t = 0; t < 32; ++t) {
+            const float y = __shfl_sync(0xffffffffu, __uint_as_float(v[t]), src);
+            if (lane == t) x = y;
         }
+        const float tau_s = __shfl_sync(0xffffffffu, tau, src);
+        const int cnt_s = __shfl_sync(0xffffffffu, cnt, src);
+        uint64_t* buf_s = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
+        const int64_t col = c0 + lane;
+        bool pass = x >= tau_s && col < ni;
+        const int32_t gc = (int32_t)(col + col_offset);
+        if (has_rated) {
+            const int64_t lo = __shfl_sync(0xffffffffu, r_lo, src), hi = __shfl_sync(0xffffffffu, r_hi, src);
+            if (pass) pass = !rated_has(rated_idx, lo, hi, gc);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+        if (pass) buf_s[cnt_s + __popc(bal & ((1u << lane) - 1u))] = make_key(x + 0.0f, gc);
+        if (lane == src) cnt += __popc(bal);
     }
 }
 
@@ -246,6 +253,7 @@ __device__ __forceinline__ void compact_if_needed(uint64_t* buf, int& cnt, float
         const int n_src = __shfl_sync(0xffffffffu, cnt, src);
         uint64_t* b_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
         const float nt = warp_compact(b_src, n_src, lane, skey);
+        __syncwarp();
         if (lane == src) { cnt = KPRIME; tau = fmaxf(tau, nt); *tau_pub = tau; }
     }
 }
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int t = threadIdx.x; t < 2 * FM; t += F_THREADS) tau_sh[t] = -INFINITY;
-    if (warp == 1) {   // whole TMEM: two 256-column fp32 accumulators (1 CTA per SM, smem-limited)
+    if (warp == W_MMA) {   // whole TMEM: two 256-column fp32 accumulators (1 CTA per SM, smem-limited)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -288,36 +296,47 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == W_TMA) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             mbar_expect_tx(afull, (uint32_t)p.kb * A_CHUNK_BYTES);
             for (int c = 0; c < p.kb; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmU, afull, c * FK, (int)row0);
             uint32_t it = 0;
+            long long dbg_wait0 = 0;
+            const long long dbg_t0 = clock64();
             for (int64_t tile = t0; tile < t1; ++tile) {
                 for (int c = 0; c < p.kb; ++c, ++it) {
                     const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+                    const long long w0 = clock64();
                     mbar_wait(empty + s, ph ^ 1);
+                    dbg_wait0 += clock64() - w0;
                     mbar_expect_tx(full + s, B_STAGE_BYTES);
                     tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmV, full + s, c * FK, (int)(tile * FN));
                 }
             }
+            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = clock64() - dbg_t0; o[1] = dbg_wait0; }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer (one thread) =====================
         if (lane == 0) {
             mbar_wait(afull, 0);
             tc_fence_after();
             uint32_t it = 0;
             int tl = 0;
+            long long dbg_w_e = 0, dbg_w_f = 0;
+            const long long dbg_t0 = clock64();
             for (int64_t tile = t0; tile < t1; ++tile, ++tl) {
                 const int acc = tl & 1;
+                const long long w0 = clock64();
                 mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
+                dbg_w_e += clock64() - w0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * FN;
                 for (int c = 0; c < p.kb; ++c, ++it) {
                     const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+                    const long long w1 = clock64();
                     mbar_wait(full + s, ph);                          // V chunk landed
+                    dbg_w_f += clock64() - w1;
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + (size_t)c * A_CHUNK_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
 #pragma unroll
@@ -327,27 +346,35 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
                 }
                 umma_commit(tfull + acc);                             // accumulator ready for the epilogue
             }
+            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = clock64() - dbg_t0; o[1] = dbg_w_e; o[2] = dbg_w_f; }
         }
     } else {
         // ===================== epilogue: thread == (user row, column half) =====================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                             // columns [half*128, half*128 + 128) of every tile
+        const int half = warp >> 2;                                   // columns [half*128, half*128 + 128) of every tile
         const int row = q * 32 + lane;
         const bool row_ok = row0 + row < p.nu;
         const int list = split * 2 + half;                            // each (split, half) produces its own candidate list
         uint64_t* buf = p.cand + ((size_t)list * p.nu + (size_t)(row_ok ? row0 + row : 0)) * CAP;
         const int64_t r_lo = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row) : 0;
         const int64_t r_hi = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row + 1) : 0;
-        float tau = row_ok ? -INFINITY : INFINITY;                    // padded rows never collect
+        float tau = (row_ok && !(p.dbg && p.dbg[0] == -12345)) ? -INFINITY : INFINITY;   // padded rows never collect (dbg: no row collects)
+        const int64_t ni = p.ni, col_offset = p.col_offset;
+        const int32_t* rated_idx = p.rated_idx;
+        const bool has_rated = p.rated_indptr != nullptr;
         volatile float* tau_mine = tau_sh + half * FM + row;
         volatile float* tau_other = tau_sh + (half ^ 1) * FM + row;
         int cnt = 0;
         uint64_t skey[4];
         constexpr int NCHUNK = FN / 2 / 32;                           // 4 chunks of 32 columns per thread per tile
         int tl = 0;
+        long long dbg_w = 0, dbg_c = 0, dbg_s = 0, dbg_k = 0;
+        const long long dbg_t0 = clock64();
         for (int64_t tile = t0; tile < t1; ++tile, ++tl) {
             const int acc = tl & 1;
+            const long long w0 = clock64();
             mbar_wait(tfull + acc, (tl >> 1) & 1);
+            dbg_w += clock64() - w0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * FN + (uint32_t)half * (FN / 2);
             const int64_t cbase = tile * FN + half * (FN / 2);
@@ -358,19 +385,30 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             tmem_ld32(taddr, va);
 #pragma unroll 1
             for (int cc = 0; cc < NCHUNK; cc += 2) {
+                long long c0_ = clock64();
                 tmem_ld_wait();
                 tmem_ld32(taddr + (cc + 1) * 32, vb);
-                scan_chunk(va, cbase + cc * 32, p, r_lo, r_hi, buf, cnt, tau);
+                long long c1_ = clock64();
+                scan_chunk(va, cbase + cc * 32, ni, col_offset, rated_idx, has_rated, r_lo, r_hi, buf, cnt, tau, lane);
+                long long c2_ = clock64();
                 compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
+                long long c3_ = clock64();
+                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_; dbg_k += c3_ - c2_;
+                c0_ = clock64();
                 tmem_ld_wait();
                 if (cc + 2 < NCHUNK) tmem_ld32(taddr + (cc + 2) * 32, va);
-                scan_chunk(vb, cbase + (cc + 1) * 32, p, r_lo, r_hi, buf, cnt, tau);
+                c1_ = clock64();
+                scan_chunk(vb, cbase + (cc + 1) * 32, ni, col_offset, rated_idx, has_rated, r_lo, r_hi, buf, cnt, tau, lane);
+                c2_ = clock64();
                 compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
+                c3_ = clock64();
+                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_; dbg_k += c3_ - c2_;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; o[3] = dbg_k; }
         // final: sorted best-KPRIME list of every (row, half) of this warp
         __syncwarp();
         for (int src = 0; src < 32; ++src) {
@@ -390,7 +428,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
@@ -494,6 +532,8 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int dpad, i
     return TKR_OK;
 }
 
+long long* g_filter_dbg = nullptr;   // set through tkr_debug_set_filter_counters (profiling aid)
+
 struct TcPlan {
     int dpad, kb, stages, ns, tps;
     size_t smem;
@@ -534,6 +574,8 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
 }  // namespace tkr
 
 using namespace tkr;
+
+extern "C" void tkr_debug_set_filter_counters(long long* dev_buf) { g_filter_dbg = dev_buf; }
 
 extern "C" size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k, int32_t has_bias) {
     TcPlan P;
@@ -579,6 +621,7 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
     fp.out_idx = sidx; fp.out_score = sscore;
+    fp.dbg = g_filter_dbg;
     TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
     dim3 grid((unsigned)((nu + FM - 1) / FM), (unsigned)P.ns);
     score_filter_kernel<<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
