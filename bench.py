@@ -342,7 +342,11 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
     need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(nb, Vfull_rows, D, k, 0) if eng == "tc" else topkrec.lib().tkr_score_topk_workspace_bytes(nb, Vfull_rows, D, k)
     wsb = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
 
+    nfb = torch.zeros(1, dtype=torch.int32, device=dev)
+
     def step(t):
+        if world == 1:
+            return topkrec.score_topk(Ub[t % 4], V, k, col_offset=beg, engine=eng, ws=wsb, n_fallback=nfb if eng == "tc" else None)
         return tdist.sharded_score_topk(Ub[t % 4], V, k, beg, engine=eng, ws=wsb)
     for t in range(W):
         step(t)
@@ -363,7 +367,7 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
                                   % (nb, NI, D, world, Vfull_rows * D * 4 / 1e6)},
            "dtype": "bf16 tcgen05 filter (fp32 accumulate in TMEM) + exact fp32 fma-chain refine; results bit-identical to the fp32 oracle"
                     if eng == "tc" else "f32 (exact fma-chain scores, CUDA cores)",
-           "gpu_launches": launches, "clocks": clk.summary(),
+           "gpu_launches": launches, "clocks": clk.summary(), "rows_redone_by_exact_fallback_last_step": int(nfb.item()),
            "roofline": {"bound": "tensor", "kernel": "score_filter_kernel" if eng == "tc" else "score_topk_kernel",
                         "achieved": flops / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
                         "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),

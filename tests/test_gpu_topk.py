@@ -212,3 +212,16 @@ def test_tc_large_norm_spread():
     U = (rng.standard_normal((400, 96)) * np.exp(rng.uniform(-6, 3, (400, 1)))).astype(np.float32)
     V = (rng.standard_normal((9000, 96)) * np.exp(rng.uniform(-6, 3, (9000, 1)))).astype(np.float32)
     _check(U, V, 30, None, None, None)
+
+
+def test_tc_fallback_rows_use_item_splits():
+    """uncertified rows over a wide item table go through the item-split fallback (+ merge through the row map)
+    and must still be bit-identical; > 1024 failing rows also exercises the unsplit tail."""
+    rng = np.random.default_rng(24)
+    nu, ni, d, k = 1500, 40000, 64, 30
+    U = (0.1 * rng.standard_normal((nu, d))).astype(np.float32)
+    V = (0.1 * rng.standard_normal((ni, d))).astype(np.float32)
+    V[5000:5200] = V[4999]                                   # 200 exact duplicates: every row that ranks them high ties at the cut
+    U[:1200] = np.abs(U[:1200]) * np.sign(V[4999])           # make the duplicate block score high for 1200 rows
+    fb = _check(U, V, k, None, None, None, engines=("tc",))
+    assert fb["tc"] >= 1100

@@ -24,15 +24,34 @@ namespace tkr {
 
 int launch_exact_rows(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
                       const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, const int32_t* row_map,
-                      const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st);
+                      const int32_t* n_rows_dev, int32_t* oi, float* os, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t exact_rows_workspace_bytes(int64_t ni, int k);
 
 constexpr int FM = 128, FN = 256, FK = 64;        // MMA tile; FK bf16 = one 128-byte swizzle span
 constexpr int A_CHUNK_BYTES = FM * FK * 2;        // 16 KB
 constexpr int B_STAGE_BYTES = FN * FK * 2;        // 32 KB
 constexpr int KPRIME = 64, CAP = 128;             // kept candidates / buffer capacity per row
 constexpr int F_EPI_WARPS = 8;                    // two per TMEM lane quarter: each takes half the columns of a tile
-constexpr int F_THREADS = 64 + 32 * F_EPI_WARPS;  // warps 0-7 epilogue, warp 8 TMA, warp 9 MMA + TMEM alloc
-constexpr int W_TMA = F_EPI_WARPS, W_MMA = F_EPI_WARPS + 1;   // highest warp ids: the SMSP arbiter favours them over the busy epilogue warps
+constexpr int F_SEL_WARPS = 4;                    // selection warps: one per lane quarter, own the rows' candidate lists
+// Warp roles by id: the SMSP arbiter favours high warp ids, so the latency-tolerant selection warps get the
+// lowest ids, the TMEM-draining epilogue the middle ones, and the two single-thread issuers the highest.
+constexpr int W_SEL = 0, W_EPI = F_SEL_WARPS, W_TMA = F_SEL_WARPS + F_EPI_WARPS, W_MMA = W_TMA + 1;
+constexpr int F_THREADS = 32 * (W_MMA + 1);       // warps 0-3 selection, 4-11 epilogue, 12 TMA, 13 MMA + TMEM alloc
+constexpr int RING = 64;                          // hand-off slots per selection warp
+
+// Hand-off from the epilogue (which must drain TMEM at MMA pace) to the selection warps (which do the rare,
+// latency-bound work): an epilogue thread whose 32-score chunk reaches its row's threshold copies the chunk
+// into a ring slot and moves on.
+struct SelShared {
+    uint4 data[RING];             // 4 consecutive scores (one max-tree group)
+    long long col0[RING];         // global tile-space column of data[.].x
+    int row[RING];
+    volatile int flag[RING];      // slot s holds reservation number flag[s]-1 once published
+    int head;                     // next reservation (atomicAdd by producers)
+    volatile int tail;            // reservations consumed
+    volatile int done;            // producer warps finished (2 per selection warp)
+    int pad;
+};
 constexpr int MAX_KB = 4;                         // d_pad <= 256
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -138,11 +157,13 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
 struct FilterParams {
     int64_t nu, ni, col_offset;
     int kb, stages, tiles_per_split;
+    int seed_tiles;          // first tiles of each sweep scanned in seed mode and replayed at the end (0 = off)
+    float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
-    uint64_t* cand;          // [2 * n_splits][nu][CAP] scratch keys (list = split * 2 + column half)
-    long long* dbg;          // optional [gridDim.x*gridDim.y][10][4] cycle counters (profiling aid), may be NULL
-    int32_t* out_idx;        // [2 * n_splits][nu][KPRIME] approximate lists, (score desc, col desc)
+    uint64_t* cand;          // [n_splits][nu][CAP] scratch keys
+    long long* dbg;          // optional [gridDim.x*gridDim.y][14][4] cycle counters (profiling aid), may be NULL
+    int32_t* out_idx;        // [n_splits][nu][KPRIME] approximate lists, (score desc, col desc)
     float* out_score;
 };
 
@@ -188,9 +209,55 @@ __device__ __forceinline__ void warp_sort128_desc(uint64_t (&key)[4], int lane) 
     }
 }
 
-// Sort row buffer `buf` (n <= CAP valid keys) and keep the best KPRIME in place; returns the KPRIME-th score
-// (or -inf when fewer are valid) to every lane.
-__device__ __noinline__ float warp_compact(uint64_t* buf, int n, int lane, uint64_t (&key)[4]) {
+template <bool DBG> __device__ __forceinline__ long long tick() { return DBG ? clock64() : 0ll; }
+
+// Epilogue fast path: a max tree over the thread's 32 scores (groups of 4) and one compare against its row's
+// threshold.  On a hit, each group whose max passes is handed to the row's selection warp through its ring
+// (all hit lanes of the warp do this in one short divergent pass).
+__device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
+    // 3-input max tree (FMNMX3): 32 -> 11 -> 4 -> 2 -> 1
+    float a[11];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) a[t] = fmaxf(fmaxf(__uint_as_float(v[3 * t]), __uint_as_float(v[3 * t + 1])), __uint_as_float(v[3 * t + 2]));
+    a[10] = fmaxf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float b0 = fmaxf(fmaxf(a[0], a[1]), a[2]), b1 = fmaxf(fmaxf(a[3], a[4]), a[5]), b2 = fmaxf(fmaxf(a[6], a[7]), a[8]), b3 = fmaxf(a[9], a[10]);
+    return fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+}
+
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, int row, float tau, SelShared* hs) {
+    if (max32(v) >= tau) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float mg = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+            if (mg >= tau) {
+                const int slot = atomicAdd(&hs->head, 1);
+                while (slot - hs->tail >= RING) __nanosleep(64);     // ring full: wait for the selection warp
+                const int sl = slot & (RING - 1);
+                hs->data[sl] = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                hs->col0[sl] = c0 + 4 * g;
+                hs->row[sl] = row;
+                __threadfence_block();
+                hs->flag[sl] = slot + 1;                             // publish
+            }
+        }
+    }
+}
+
+// Seed mode (first tiles of a sweep): nothing is handed off; the thread only tracks its 4 largest chunk maxima.
+// s4 is then an actual score with at least 4 scores >= it among the columns seen, a cheap rigorous seed for the
+// row threshold that skips the hit-heavy warm-up of a running top-k.
+__device__ __forceinline__ void seed_chunk(const uint32_t (&v)[32], float& s1, float& s2, float& s3, float& s4) {
+    float a = max32(v);
+    float t;
+    t = fmaxf(s1, a); a = fminf(s1, a); s1 = t;
+    t = fmaxf(s2, a); a = fminf(s2, a); s2 = t;
+    t = fmaxf(s3, a); a = fminf(s3, a); s3 = t;
+    s4 = fmaxf(s4, a);
+}
+
+// Selection warp: sort the row buffer (n <= CAP keys, global memory) in registers, keep the best KPRIME in place,
+// return the KPRIME-th score (or -inf) to every lane.  `key` holds the sorted keys of elements r*32+lane afterwards.
+__device__ __forceinline__ float sel_compact(uint64_t* buf, int n, int lane, uint64_t (&key)[4]) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int e = r * 32 + lane;
@@ -204,60 +271,7 @@ __device__ __noinline__ float warp_compact(uint64_t* buf, int n, int lane, uint6
     return last ? ord_to_f32((uint32_t)(last >> 32)) : -INFINITY;
 }
 
-// Fast path: a max tree over the thread's 32 scores and one compare against its threshold; the warp votes and
-// moves on when no lane has a hit (uniform branch, no divergence).
-// Slow path (rare once the thresholds have risen): for each hit lane the warp transposes that lane's 32 scores
-// with shuffles so that lane t holds column t, tests them against the row's threshold in parallel, drops rated
-// columns (parallel binary searches) and appends the survivors to the row's buffer with ballot-derived slots.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, int64_t ni, int64_t col_offset,
-                                           const int32_t* __restrict__ rated_idx, bool has_rated, int64_t r_lo, int64_t r_hi,
-                                           uint64_t* buf, int& cnt, float tau, int lane) {
-    float m[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g)
-        m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-    const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-    unsigned hits = __ballot_sync(0xffffffffu, mx >= tau);
-    while (hits) {
-        const int src = __ffs(hits) - 1;
-        hits &= hits - 1;
-        float x = 0.f;
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-            const float y = __shfl_sync(0xffffffffu, __uint_as_float(v[t]), src);
-            if (lane == t) x = y;
-        }
-        const float tau_s = __shfl_sync(0xffffffffu, tau, src);
-        const int cnt_s = __shfl_sync(0xffffffffu, cnt, src);
-        uint64_t* buf_s = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
-        const int64_t col = c0 + lane;
-        bool pass = x >= tau_s && col < ni;
-        const int32_t gc = (int32_t)(col + col_offset);
-        if (has_rated) {
-            const int64_t lo = __shfl_sync(0xffffffffu, r_lo, src), hi = __shfl_sync(0xffffffffu, r_hi, src);
-            if (pass) pass = !rated_has(rated_idx, lo, hi, gc);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (pass) buf_s[cnt_s + __popc(bal & ((1u << lane) - 1u))] = make_key(x + 0.0f, gc);
-        if (lane == src) cnt += __popc(bal);
-    }
-}
-
-// Rows whose buffer could overflow on the next chunk are compacted to their best KPRIME (warp-wide sort),
-// which also raises their threshold.
-__device__ __forceinline__ void compact_if_needed(uint64_t* buf, int& cnt, float& tau, int lane, uint64_t (&skey)[4], volatile float* tau_pub) {
-    unsigned fullm = __ballot_sync(0xffffffffu, cnt > CAP - 32);
-    while (fullm) {
-        const int src = __ffs(fullm) - 1;
-        fullm &= fullm - 1;
-        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-        uint64_t* b_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
-        const float nt = warp_compact(b_src, n_src, lane, skey);
-        __syncwarp();
-        if (lane == src) { cnt = KPRIME; tau = fmaxf(tau, nt); *tau_pub = tau; }
-    }
-}
-
+template <bool DBG>
 __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid_constant__ CUtensorMap tmU,
                                                                     const __grid_constant__ CUtensorMap tmV, FilterParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -271,7 +285,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     uint64_t* tempty = bars + 18;          // [2]       epilogue -> MMA
     uint64_t* afull = bars + 20;           //           U tile landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-    float* tau_sh = reinterpret_cast<float*>(bars + 22);   // [2][FM]: thresholds the two column halves publish to each other
+    volatile float* tau_sh = reinterpret_cast<float*>(bars + 22);        // [FM] row thresholds (selection warps write, epilogue reads)
+    int* cnt_sh = reinterpret_cast<int*>(bars + 22) + FM;                // [FM] candidates buffered per row
+    long long* rlo_sh = reinterpret_cast<long long*>(cnt_sh + FM);       // [FM] rated CSR range of each row
+    long long* rhi_sh = rlo_sh + FM;
+    float* seed_sh = reinterpret_cast<float*>(rhi_sh + FM);              // [2][FM] per-half seeds
+    SelShared* sel = reinterpret_cast<SelShared*>(seed_sh + 2 * FM);     // [F_SEL_WARPS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row0 = (int64_t)blockIdx.x * FM;
@@ -279,6 +298,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     const int64_t ntiles = (p.ni + FN - 1) / FN;
     const int64_t t0 = (int64_t)split * p.tiles_per_split;
     const int64_t t1 = (t0 + p.tiles_per_split < ntiles) ? t0 + p.tiles_per_split : ntiles;
+    // Tile sequence of a sweep: [t0, t1) once, the first T0 of them in seed mode, then those T0 tiles again.
+    const int ntl = (int)(t1 - t0);
+    const int T0 = (p.seed_tiles > 0 && ntl >= 4 * p.seed_tiles) ? p.seed_tiles : 0;
+    const int nseq = ntl + T0;
+    auto tile_of = [&](int tl) -> int64_t { return t0 + (tl < ntl ? tl : tl - ntl); };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -286,7 +310,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
         mbar_init(afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = threadIdx.x; t < 2 * FM; t += F_THREADS) tau_sh[t] = -INFINITY;
+    for (int t = threadIdx.x; t < FM; t += F_THREADS) {
+        const bool ok = row0 + t < p.nu;   // padded rows never collect
+        tau_sh[t] = ok ? -INFINITY : INFINITY;
+        if (row0 + t < p.nu && T0 == 0) p.out_tau0[(int64_t)split * p.nu + row0 + t] = -INFINITY;
+        cnt_sh[t] = 0;
+        rlo_sh[t] = (ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + t) : 0;
+        rhi_sh[t] = (ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + t + 1) : 0;
+    }
+    for (int t = threadIdx.x; t < F_SEL_WARPS * (int)(sizeof(SelShared) / 4); t += F_THREADS) reinterpret_cast<int*>(sel)[t] = 0;
     if (warp == W_MMA) {   // whole TMEM: two 256-column fp32 accumulators (1 CTA per SM, smem-limited)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -303,18 +335,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             for (int c = 0; c < p.kb; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmU, afull, c * FK, (int)row0);
             uint32_t it = 0;
             long long dbg_wait0 = 0;
-            const long long dbg_t0 = clock64();
-            for (int64_t tile = t0; tile < t1; ++tile) {
+            const long long dbg_t0 = tick<DBG>();
+            for (int tl = 0; tl < nseq; ++tl) {
+                const int64_t tile = tile_of(tl);
                 for (int c = 0; c < p.kb; ++c, ++it) {
                     const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-                    const long long w0 = clock64();
+                    const long long w0 = tick<DBG>();
                     mbar_wait(empty + s, ph ^ 1);
-                    dbg_wait0 += clock64() - w0;
+                    dbg_wait0 += tick<DBG>() - w0;
                     mbar_expect_tx(full + s, B_STAGE_BYTES);
                     tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmV, full + s, c * FK, (int)(tile * FN));
                 }
             }
-            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = clock64() - dbg_t0; o[1] = dbg_wait0; }
+            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_wait0; }
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer (one thread) =====================
@@ -324,19 +357,19 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             uint32_t it = 0;
             int tl = 0;
             long long dbg_w_e = 0, dbg_w_f = 0;
-            const long long dbg_t0 = clock64();
-            for (int64_t tile = t0; tile < t1; ++tile, ++tl) {
+            const long long dbg_t0 = tick<DBG>();
+            for (; tl < nseq; ++tl) {
                 const int acc = tl & 1;
-                const long long w0 = clock64();
+                const long long w0 = tick<DBG>();
                 mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-                dbg_w_e += clock64() - w0;
+                dbg_w_e += tick<DBG>() - w0;
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)acc * FN;
                 for (int c = 0; c < p.kb; ++c, ++it) {
                     const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
-                    const long long w1 = clock64();
+                    const long long w1 = tick<DBG>();
                     mbar_wait(full + s, ph);                          // V chunk landed
-                    dbg_w_f += clock64() - w1;
+                    dbg_w_f += tick<DBG>() - w1;
                     tc_fence_after();
                     const uint32_t a0 = smem_u32(sA + (size_t)c * A_CHUNK_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
 #pragma unroll
@@ -346,84 +379,136 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
                 }
                 umma_commit(tfull + acc);                             // accumulator ready for the epilogue
             }
-            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = clock64() - dbg_t0; o[1] = dbg_w_e; o[2] = dbg_w_f; }
+            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_w_e; o[2] = dbg_w_f; }
         }
     } else {
-        // ===================== epilogue: thread == (user row, column half) =====================
+        if (warp >= W_EPI) {
+        // ===================== epilogue: thread == (user row, column half); drains TMEM at MMA pace =====================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-        const int half = warp >> 2;                                   // columns [half*128, half*128 + 128) of every tile
+        const int half = (warp - W_EPI) >> 2;                                   // columns [half*128, half*128 + 128) of every tile
         const int row = q * 32 + lane;
-        const bool row_ok = row0 + row < p.nu;
-        const int list = split * 2 + half;                            // each (split, half) produces its own candidate list
-        uint64_t* buf = p.cand + ((size_t)list * p.nu + (size_t)(row_ok ? row0 + row : 0)) * CAP;
-        const int64_t r_lo = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row) : 0;
-        const int64_t r_hi = (row_ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + row + 1) : 0;
-        float tau = (row_ok && !(p.dbg && p.dbg[0] == -12345)) ? -INFINITY : INFINITY;   // padded rows never collect (dbg: no row collects)
-        const int64_t ni = p.ni, col_offset = p.col_offset;
-        const int32_t* rated_idx = p.rated_idx;
-        const bool has_rated = p.rated_indptr != nullptr;
-        volatile float* tau_mine = tau_sh + half * FM + row;
-        volatile float* tau_other = tau_sh + (half ^ 1) * FM + row;
-        int cnt = 0;
-        uint64_t skey[4];
+        SelShared* hs = sel + q;
         constexpr int NCHUNK = FN / 2 / 32;                           // 4 chunks of 32 columns per thread per tile
-        int tl = 0;
-        long long dbg_w = 0, dbg_c = 0, dbg_s = 0, dbg_k = 0;
-        const long long dbg_t0 = clock64();
-        for (int64_t tile = t0; tile < t1; ++tile, ++tl) {
+        long long dbg_w = 0, dbg_c = 0, dbg_s = 0;
+        float s1 = -INFINITY, s2 = -INFINITY, s3 = -INFINITY, s4 = -INFINITY;
+        for (int tl = 0; tl < nseq; ++tl) {
+            const int64_t tile = tile_of(tl);
             const int acc = tl & 1;
-            const long long w0 = clock64();
+            const bool seeding = tl < T0;
+            if (T0 > 0 && tl == T0) {
+                // end of seed mode: row threshold = the smaller of its two column halves' seeds
+                seed_sh[half * FM + row] = s4;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * F_EPI_WARPS) : "memory");
+                if (half == 0) {
+                    const float tau0 = fminf(seed_sh[row], seed_sh[FM + row]);
+                    if (row0 + row < p.nu) {
+                        tau_sh[row] = fmaxf(tau_sh[row], tau0);
+                        p.out_tau0[(int64_t)split * p.nu + row0 + row] = tau0;
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * F_EPI_WARPS) : "memory");
+            }
+            const long long w0 = tick<DBG>();
             mbar_wait(tfull + acc, (tl >> 1) & 1);
-            dbg_w += clock64() - w0;
+            dbg_w += tick<DBG>() - w0;
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * FN + (uint32_t)half * (FN / 2);
             const int64_t cbase = tile * FN + half * (FN / 2);
-            // the 64-th best of EITHER half bounds the row's 64-th best from below: adopt the partner's threshold
-            tau = fmaxf(tau, *tau_other);
             // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is scanned
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
+            const float tau = tau_sh[row];                            // refreshed once per tile (a stale value only costs extra hand-offs)
 #pragma unroll 1
             for (int cc = 0; cc < NCHUNK; cc += 2) {
-                long long c0_ = clock64();
+                long long c0_ = tick<DBG>();
                 tmem_ld_wait();
                 tmem_ld32(taddr + (cc + 1) * 32, vb);
-                long long c1_ = clock64();
-                scan_chunk(va, cbase + cc * 32, ni, col_offset, rated_idx, has_rated, r_lo, r_hi, buf, cnt, tau, lane);
-                long long c2_ = clock64();
-                compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
-                long long c3_ = clock64();
-                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_; dbg_k += c3_ - c2_;
-                c0_ = clock64();
+                long long c1_ = tick<DBG>();
+                if (seeding) seed_chunk(va, s1, s2, s3, s4); else scan_chunk(va, cbase + cc * 32, row, tau, hs);
+                long long c2_ = tick<DBG>();
+                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_;
+                c0_ = tick<DBG>();
                 tmem_ld_wait();
                 if (cc + 2 < NCHUNK) tmem_ld32(taddr + (cc + 2) * 32, va);
-                c1_ = clock64();
-                scan_chunk(vb, cbase + (cc + 1) * 32, ni, col_offset, rated_idx, has_rated, r_lo, r_hi, buf, cnt, tau, lane);
-                c2_ = clock64();
-                compact_if_needed(buf, cnt, tau, lane, skey, tau_mine);
-                c3_ = clock64();
-                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_; dbg_k += c3_ - c2_;
+                c1_ = tick<DBG>();
+                if (seeding) seed_chunk(vb, s1, s2, s3, s4); else scan_chunk(vb, cbase + (cc + 1) * 32, row, tau, hs);
+                c2_ = tick<DBG>();
+                dbg_c += c1_ - c0_; dbg_s += c2_ - c1_;
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty + acc);
         }
-        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 10 + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; o[3] = dbg_k; }
-        // final: sorted best-KPRIME list of every (row, half) of this warp
         __syncwarp();
-        for (int src = 0; src < 32; ++src) {
-            const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-            uint64_t* b_src = (uint64_t*)__shfl_sync(0xffffffffu, (unsigned long long)buf, src);
-            const int64_t grow = row0 + q * 32 + src;
-            if (grow >= p.nu) continue;                               // warp-uniform
-            warp_compact(b_src, n_src, lane, skey);
-            const int64_t o = ((int64_t)list * p.nu + grow) * KPRIME;
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const uint64_t key = skey[r];
-                p.out_idx[o + r * 32 + lane] = key ? (int32_t)(uint32_t)key : -1;
-                p.out_score[o + r * 32 + lane] = key ? ord_to_f32((uint32_t)(key >> 32)) : -INFINITY;
+        if (lane == 0) { __threadfence_block(); atomicAdd((int*)&hs->done, 1); }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; }
+        } else {
+        // ===================== selection: one warp per lane quarter owns the candidate lists of its 32 rows =====================
+        const int q = warp - W_SEL;
+        SelShared* hs = sel + q;
+        const int64_t ni = p.ni, col_offset = p.col_offset;
+        const int32_t* rated_idx = p.rated_idx;
+        const bool has_rated = p.rated_indptr != nullptr;
+        uint64_t* bufq = p.cand + ((size_t)split * p.nu + (size_t)row0) * CAP;     // row r of the tile at bufq + r*CAP
+        uint64_t skey[4];
+        int tail = 0;
+        long long dbg_idle = 0, dbg_busy = 0, dbg_n = 0, dbg_cmp = 0;
+        for (;;) {
+            const int sl = tail & (RING - 1);
+            const long long i0 = tick<DBG>();
+            bool finished = false;
+            for (;;) {
+                if (hs->flag[sl] == tail + 1) break;
+                if (hs->done == 2 && *(volatile int*)&hs->head == tail) { finished = true; break; }
+                __nanosleep(200);                                              // idle: do not steal issue slots from the epilogue
             }
+            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;       // one decision for the warp
+            if (finished) break;
+            const long long i1 = tick<DBG>();
+            dbg_idle += i1 - i0;
+            const int row = hs->row[sl];
+            const int64_t c0 = hs->col0[sl];
+            const float x = lane < 4 ? __uint_as_float(reinterpret_cast<const volatile uint32_t*>(&hs->data[sl])[lane]) : -INFINITY;
+            __syncwarp();
+            ++tail;
+            if (lane == 0) hs->tail = tail;                                    // slot free again: the chunk is in registers
+            const float tau_r = tau_sh[row];
+            int cnt_r = cnt_sh[row];
+            const int64_t col = c0 + lane;
+            const int32_t gc = (int32_t)(col + col_offset);
+            bool pass = lane < 4 && x >= tau_r && col < ni;
+            if (has_rated && pass) pass = !rated_has(rated_idx, rlo_sh[row], rhi_sh[row], gc);
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            uint64_t* buf = bufq + (size_t)row * CAP;
+            if (pass) buf[cnt_r + __popc(bal & ((1u << lane) - 1u))] = make_key(x + 0.0f, gc);
+            cnt_r += __popc(bal);
+            __syncwarp();
+            if (cnt_r > CAP - 32) {                                            // could overflow on the next chunk: keep the best KPRIME
+                const long long k0 = tick<DBG>();
+                const float nt = sel_compact(buf, cnt_r, lane, skey);
+                cnt_r = KPRIME;
+                if (lane == 0) tau_sh[row] = fmaxf(tau_r, nt);
+                dbg_cmp += tick<DBG>() - k0;
+            }
+            if (lane == 0) cnt_sh[row] = cnt_r;
+            __syncwarp();
+            dbg_busy += tick<DBG>() - i1; ++dbg_n;
+        }
+        // final: sorted best-KPRIME list of every row of this quarter
+        for (int r = 0; r < 32; ++r) {
+            const int row = q * 32 + r;
+            const int64_t grow = row0 + row;
+            if (grow >= p.nu) break;
+            sel_compact(bufq + (size_t)row * CAP, cnt_sh[row], lane, skey);
+            const int64_t o = ((int64_t)split * p.nu + grow) * KPRIME;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const uint64_t key = skey[h2];
+                p.out_idx[o + h2 * 32 + lane] = key ? (int32_t)(uint32_t)key : -1;
+                p.out_score[o + h2 * 32 + lane] = key ? ord_to_f32((uint32_t)(key >> 32)) : -INFINITY;
+            }
+        }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = dbg_busy; o[1] = dbg_idle; o[2] = dbg_n; o[3] = dbg_cmp; }
         }
     }
     tc_fence_before();
@@ -440,7 +525,8 @@ __global__ void __launch_bounds__(256) score_refine_kernel(const float* __restri
                                                            int d, const float* __restrict__ bias, int64_t col_offset,
                                                            const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                            const float* __restrict__ unorm, const unsigned int* __restrict__ vnorm_max,
-                                                           const unsigned int* __restrict__ bias_max, float coef, int k,
+                                                           const unsigned int* __restrict__ bias_max, const float* __restrict__ tau0,
+                                                           int n_splits, float coef, int k,
                                                            int32_t* __restrict__ out_idx, float* __restrict__ out_score,
                                                            int32_t* __restrict__ fail_rows, int32_t* __restrict__ n_fail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -490,10 +576,12 @@ __global__ void __launch_bounds__(256) score_refine_kernel(const float* __restri
     if (lane == 0) {
         // Everything the filter dropped has approximate score <= D = the KPRIME-th approximate score, hence exact
         // score <= D + eps.  Certified iff nothing was dropped, or the k-th exact score is strictly above that.
-        const bool dropped = cand_idx[row * KPRIME + KPRIME - 1] >= 0;
+        // (a seeded sweep also dropped whatever scored below its seed threshold tau0)
+        float D = cand_idx[row * KPRIME + KPRIME - 1] >= 0 ? cand_score[row * KPRIME + KPRIME - 1] : -INFINITY;
+        for (int sp = 0; sp < n_splits; ++sp) D = fmaxf(D, tau0[(int64_t)sp * nu + row]);
+        const bool dropped = D > -INFINITY;
         bool ok = !dropped;
         if (dropped) {
-            const float D = cand_score[row * KPRIME + KPRIME - 1];
             const float eps = coef * unorm[row] * __uint_as_float(*vnorm_max) + 1e-6f * __uint_as_float(*bias_max) + 1e-30f;
             ok = kth > D + eps + fabsf(D) * 1e-6f;
         }
@@ -537,7 +625,8 @@ long long* g_filter_dbg = nullptr;   // set through tkr_debug_set_filter_counter
 struct TcPlan {
     int dpad, kb, stages, ns, tps;
     size_t smem;
-    size_t o_ubf, o_vbf, o_unorm, o_scal, o_cand, o_sidx, o_sscore, o_midx, o_mscore, o_fail, total;
+    int seed_tiles;
+    size_t o_ubf, o_vbf, o_unorm, o_scal, o_cand, o_sidx, o_sscore, o_midx, o_mscore, o_fail, o_tau0, o_fb, fb_bytes, total;
 };
 
 static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan* P) {
@@ -546,13 +635,13 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
     P->kb = P->dpad / FK;
     if (P->kb > MAX_KB || k > 48 || nu <= 0 || ni <= 0) return false;
     P->stages = P->kb >= 4 ? 4 : 5;
-    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * B_STAGE_BYTES + 256 + 2 * FM * 4;
+    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * B_STAGE_BYTES + 256 + FM * (4 + 4 + 8 + 8 + 8) + F_SEL_WARPS * sizeof(SelShared);
     const int64_t row_tiles = (nu + FM - 1) / FM, ntiles = (ni + FN - 1) / FN;
     // one CTA per SM; split the items only when the user tiles alone cannot fill the chip
     int64_t ns = row_tiles >= kNumSMs ? 1 : (kNumSMs + row_tiles - 1) / row_tiles;
     const int64_t maxs = ntiles / 16 > 0 ? ntiles / 16 : 1;
     if (ns > maxs) ns = maxs;
-    if (ns > 16) ns = 16;
+    if (ns > 32) ns = 32;
     P->tps = (int)((ntiles + ns - 1) / ns);
     P->ns = (int)((ntiles + P->tps - 1) / P->tps);
     size_t o = 0;
@@ -561,12 +650,17 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
     P->o_vbf = take((size_t)ni * P->dpad * 2);
     P->o_unorm = take((size_t)nu * 4);
     P->o_scal = take(64);                                   // [0] vnorm_max  [1] bias_max  [2] n_fail
-    P->o_cand = take((size_t)2 * P->ns * nu * CAP * 8);            // one list per (item split, column half)
-    P->o_sidx = take((size_t)2 * P->ns * nu * KPRIME * 4);
-    P->o_sscore = take((size_t)2 * P->ns * nu * KPRIME * 4);
+    P->o_cand = take((size_t)P->ns * nu * CAP * 8);                // one candidate list per (item split, row)
+    P->o_sidx = take((size_t)P->ns * nu * KPRIME * 4);
+    P->o_sscore = take((size_t)P->ns * nu * KPRIME * 4);
     P->o_midx = take((size_t)nu * KPRIME * 4);
     P->o_mscore = take((size_t)nu * KPRIME * 4);
     P->o_fail = take((size_t)nu * 4);
+    P->o_tau0 = take((size_t)P->ns * nu * 4);
+    P->fb_bytes = exact_rows_workspace_bytes(ni, k);
+    P->o_fb = take(P->fb_bytes + 256);
+    // seed on ~1/64 of a sweep (expected ~500 columns above the seed); sweeps under 256 tiles run unseeded
+    P->seed_tiles = P->tps >= 256 ? (P->tps / 64 < 64 ? P->tps / 64 : 64) : 0;
     P->total = o;
     return true;
 }
@@ -620,23 +714,30 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     FilterParams fp;
     fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
-    fp.out_idx = sidx; fp.out_score = sscore;
+    fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
-    TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+    fp.seed_tiles = P.seed_tiles; fp.out_tau0 = (float*)(w + P.o_tau0);
     dim3 grid((unsigned)((nu + FM - 1) / FM), (unsigned)P.ns);
-    score_filter_kernel<<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
+    if (fp.dbg != nullptr) {
+        TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        score_filter_kernel<true><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
+    } else {
+        TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        score_filter_kernel<false><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
+    }
     TKR_LAUNCH_CHECK();
-    if (int rc = tkr_topk_merge(sidx, sscore, 2 * P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
+    if (P.ns > 1)
+        if (int rc = tkr_topk_merge(sidx, sscore, P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
 
     // |bf16 tensor-core score - exact fma-chain score| <= coef * |u| * |v|: two roundings to 8-bit significands
     // (2^-8 + 2^-18 on every product, Cauchy-Schwarz over the row) + fp32 accumulation slack on both sides.
     const float coef = 0.00390625f * 1.01f + (float)(d + 8) * 9.5367431640625e-7f;
     const size_t rsmem = (size_t)8 * d * 4 + (size_t)8 * KPRIME * 8;
     score_refine_kernel<<<(unsigned)((nu + 7) / 8), 256, rsmem, st>>>(U, V, nu, d, bias, col_offset, midx, mscore, unorm, scal + 0, scal + 1,
-                                                                     coef, k, out_idx, out_score, fail, (int32_t*)(scal + 2));
+                                                                     (const float*)(w + P.o_tau0), P.ns, coef, k, out_idx, out_score, fail, (int32_t*)(scal + 2));
     TKR_LAUNCH_CHECK();
     // uncertified rows -> exact engine, driven by the device-side row list (no host round trip)
-    if (int rc = launch_exact_rows(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, fail, (const int32_t*)(scal + 2), out_idx, out_score, st)) return rc;
+    if (int rc = launch_exact_rows(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, fail, (const int32_t*)(scal + 2), out_idx, out_score, w + P.o_fb, P.fb_bytes, st)) return rc;
     if (n_fallback_rows != nullptr) TKR_CUDA(cudaMemcpyAsync(n_fallback_rows, scal + 2, 4, cudaMemcpyDeviceToDevice, st));
     return TKR_OK;
 }

@@ -75,12 +75,15 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
     const float* __restrict__ U, int64_t nu, const float* __restrict__ V, int64_t ni, int d, int dpad,
     const float* __restrict__ bias, const int64_t* __restrict__ rated_indptr, const int32_t* __restrict__ rated_idx,
     int k, int64_t col_offset, int tiles_per_split, const int32_t* __restrict__ row_map, const int32_t* __restrict__ n_rows_dev,
-    int32_t* __restrict__ out_idx, float* __restrict__ out_score) {
+    int64_t row_begin, int64_t row_limit, int64_t out_rows, int32_t* __restrict__ out_idx, float* __restrict__ out_score) {
     constexpr int RM = BM / 16;  // rows per thread
     // optional indirection: logical row r of this launch is row row_map[r] of U / rated / out, and only
     // the first *n_rows_dev logical rows exist (the tensor-core path hands its uncertified rows over this way)
-    const int64_t n_rows = n_rows_dev ? (int64_t)*n_rows_dev : nu;
-    if ((int64_t)blockIdx.x * BM >= n_rows) return;
+    // Logical rows [row_begin, min(n_rows, row_limit)) are processed.  out_rows > 0: lists are written at the LOGICAL
+    // row (stride out_rows per split) for a later merge; otherwise at the actual row (stride nu).
+    int64_t n_rows = n_rows_dev ? (int64_t)*n_rows_dev : nu;
+    if (row_limit > 0 && n_rows > row_limit) n_rows = row_limit;
+    if (row_begin + (int64_t)blockIdx.x * BM >= n_rows) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* As = reinterpret_cast<float*>(smem_raw);
     float* Bs = As + (size_t)dpad * BM;
@@ -93,7 +96,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = tid & 15, ty = tid >> 4;
-    const int64_t row0 = (int64_t)blockIdx.x * BM;
+    const int64_t row0 = row_begin + (int64_t)blockIdx.x * BM;
     const int split = blockIdx.y;
     const int64_t ntiles = (ni + BN - 1) / BN;
     const int64_t tile_beg = (int64_t)split * tiles_per_split;
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
         const int row = idx / k, p = idx % k;
         if (arow[row] >= 0) {
             const uint64_t key = T[(size_t)row * KCAP + p];
-            const int64_t o = ((int64_t)split * nu + arow[row]) * k + p;
+            const int64_t o = (out_rows > 0 ? (int64_t)split * out_rows + (row0 - row_begin + row) : (int64_t)split * nu + arow[row]) * k + p;
             out_idx[o] = key ? (int32_t)(uint32_t)key : -1;
             out_score[o] = key ? ord_to_f32((uint32_t)(key >> 32)) : -INFINITY;
         }
@@ -251,19 +254,23 @@ __global__ void __launch_bounds__(256) score_topk_kernel(
 // own list + the number of greater keys in every other list (binary search; keys unique).
 __global__ void __launch_bounds__(128) topk_merge_kernel(const int32_t* __restrict__ idx, const float* __restrict__ score,
                                                          int n_lists, int64_t nu, int k, int32_t* __restrict__ out_idx,
-                                                         float* __restrict__ out_score) {
+                                                         float* __restrict__ out_score, const int32_t* __restrict__ row_map,
+                                                         const int32_t* __restrict__ n_rows_dev) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw) + (size_t)warp * n_lists * k;
     const int tot = n_lists * k;
-    for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < nu; row += (int64_t)gridDim.x * 4) {
+    // optional indirection: input row r (of the first *n_rows_dev) is written to output row row_map[r]
+    const int64_t n_in = n_rows_dev ? ((int64_t)*n_rows_dev < nu ? (int64_t)*n_rows_dev : nu) : nu;
+    for (int64_t row = (int64_t)blockIdx.x * 4 + warp; row < n_in; row += (int64_t)gridDim.x * 4) {
+        const int64_t orow = row_map ? (int64_t)row_map[row] : row;
         for (int e = lane; e < tot; e += 32) {
             const int g = e / k, p = e % k;
             const int64_t o = ((int64_t)g * nu + row) * k + p;
             const int32_t c = idx[o];
             keys[e] = c >= 0 ? make_key(score[o], c) : 0;
         }
-        for (int p = lane; p < k; p += 32) { out_idx[row * k + p] = -1; out_score[row * k + p] = -INFINITY; }
+        for (int p = lane; p < k; p += 32) { out_idx[orow * k + p] = -1; out_score[orow * k + p] = -INFINITY; }
         __syncwarp();
         for (int e = lane; e < tot; e += 32) {
             const uint64_t ke = keys[e];
@@ -278,8 +285,8 @@ __global__ void __launch_bounds__(128) topk_merge_kernel(const int32_t* __restri
                 rank += lo;
             }
             if (rank < k) {
-                out_idx[row * k + rank] = (int32_t)(uint32_t)ke;
-                out_score[row * k + rank] = ord_to_f32((uint32_t)(ke >> 32));
+                out_idx[orow * k + rank] = (int32_t)(uint32_t)ke;
+                out_score[orow * k + rank] = ord_to_f32((uint32_t)(ke >> 32));
             }
         }
         __syncwarp();
@@ -312,8 +319,8 @@ extern "C" size_t tkr_score_topk_workspace_bytes(int64_t nu, int64_t ni, int32_t
     return 2 * align_up((size_t)ns * nu * k * 4, 256);
 }
 
-extern "C" int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,
-                              int32_t* out_idx, float* out_score, void* stream) {
+static int merge_lists(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k, int32_t* out_idx,
+                       float* out_score, const int32_t* row_map, const int32_t* n_rows_dev, void* stream) {
     TKR_CHECK_ARG(idx && score && out_idx && out_score, "NULL list pointer");
     TKR_CHECK_ARG(n_lists >= 1 && nu >= 0 && k >= 1, "bad n_lists/nu/k");
     TKR_CHECK_ARG((int64_t)n_lists * k <= 4096, "n_lists*k = %lld exceeds 4096", (long long)n_lists * k);
@@ -322,35 +329,42 @@ extern "C" int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_
     if (smem > 48 * 1024) TKR_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t blocks = (nu + 3) / 4;
     if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-    topk_merge_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(idx, score, n_lists, nu, k, out_idx, out_score);
+    topk_merge_kernel<<<(unsigned)blocks, 128, smem, (cudaStream_t)stream>>>(idx, score, n_lists, nu, k, out_idx, out_score, row_map, n_rows_dev);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
+}
+
+extern "C" int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,
+                              int32_t* out_idx, float* out_score, void* stream) {
+    return merge_lists(idx, score, n_lists, nu, k, out_idx, out_score, nullptr, nullptr, stream);
 }
 
 template <int BM, int KCAP, bool VEC4>
 static int launch_score(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
                         const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, int ns, int tps,
-                        const int32_t* row_map, const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
+                        const int32_t* row_map, const int32_t* n_rows_dev, int64_t row_begin, int64_t row_limit, int64_t out_rows,
+                        int64_t grid_rows, int32_t* oi, float* os, cudaStream_t st) {
     const int dpad = (d + BK - 1) / BK * BK;
     const size_t smem = ScoreSmem<BM, KCAP>::bytes(dpad);
     if (smem > 227 * 1024) { set_error("score_topk: d=%d k=%d needs %zu B of shared memory (> 227 KB)", d, k, smem); return TKR_ERR_UNSUPPORTED; }
     auto kern = score_topk_kernel<BM, KCAP, VEC4>;
     TKR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((nu + BM - 1) / BM), (unsigned)ns);
-    kern<<<grid, 256, smem, st>>>(U, nu, V, ni, d, dpad, bias, rp, ri, k, col_offset, tps, row_map, n_rows_dev, oi, os);
+    dim3 grid((unsigned)((grid_rows + BM - 1) / BM), (unsigned)ns);
+    kern<<<grid, 256, smem, st>>>(U, nu, V, ni, d, dpad, bias, rp, ri, k, col_offset, tps, row_map, n_rows_dev, row_begin, row_limit, out_rows, oi, os);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
 
 static int dispatch_score(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
                           const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, int ns, int tps,
-                          const int32_t* row_map, const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
+                          const int32_t* row_map, const int32_t* n_rows_dev, int64_t row_begin, int64_t row_limit,
+                          int64_t out_rows, int64_t grid_rows, int32_t* oi, float* os, cudaStream_t st) {
     if (d > 512) { set_error("score_topk: d=%d > 512 is not supported by the exact kernel", d); return TKR_ERR_UNSUPPORTED; }
     const int BM = pick_bm(d);
     const bool vec4 = (d % 4 == 0) && ((uintptr_t)U % 16 == 0) && ((uintptr_t)V % 16 == 0);
     const int kcap = k <= 32 ? 32 : 64;
     int rc;
-#define TKR_SCORE(BM_, KC_, V4_) rc = launch_score<BM_, KC_, V4_>(U, nu, V, ni, d, bias, rp, ri, k, col_offset, ns, tps, row_map, n_rows_dev, oi, os, st)
+#define TKR_SCORE(BM_, KC_, V4_) rc = launch_score<BM_, KC_, V4_>(U, nu, V, ni, d, bias, rp, ri, k, col_offset, ns, tps, row_map, n_rows_dev, row_begin, row_limit, out_rows, grid_rows, oi, os, st)
 #define TKR_SCORE_BM(BM_)                                                   \
     do {                                                                    \
         if (kcap == 32) { if (vec4) TKR_SCORE(BM_, 32, true); else TKR_SCORE(BM_, 32, false); } \
@@ -363,13 +377,45 @@ static int dispatch_score(const float* U, int64_t nu, const float* V, int64_t ni
 }
 
 namespace tkr {
+constexpr int64_t kFallbackRows = 1024;   // uncertified rows that get the item-split (fast) treatment
+
+static int64_t fallback_splits(int64_t ni, int k) {
+    const int64_t ntiles = (ni + BN - 1) / BN;
+    int64_t ns = ntiles / 8;
+    if (ns > 4096 / k) ns = 4096 / k;      // the merge kernel handles n_lists * k <= 4096 keys per row
+    if (ns > 128) ns = 128;
+    return ns < 1 ? 1 : ns;
+}
+
+size_t exact_rows_workspace_bytes(int64_t ni, int k) {
+    const int64_t ns = fallback_splits(ni, k);
+    return ns > 1 ? 2 * align_up((size_t)ns * kFallbackRows * k * 4, 256) : 0;
+}
+
 // Exact engine over a device-side list of rows (row_map[0 .. *n_rows_dev)), results written in place into
-// out[row_map[r]].  One item split; CTAs beyond the list exit immediately.
+// out[row_map[r]].  The first kFallbackRows listed rows are swept with the items split over many CTAs and
+// merged (a handful of rows must not serialise a whole item sweep on one SM); any further rows take the
+// unsplit kernel.  CTAs beyond the list exit immediately, so both launches are always issued.
 int launch_exact_rows(const float* U, int64_t nu, const float* V, int64_t ni, int d, const float* bias,
                       const int64_t* rp, const int32_t* ri, int k, int64_t col_offset, const int32_t* row_map,
-                      const int32_t* n_rows_dev, int32_t* oi, float* os, cudaStream_t st) {
+                      const int32_t* n_rows_dev, int32_t* oi, float* os, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int64_t ntiles = (ni + BN - 1) / BN;
-    return dispatch_score(U, nu, V, ni, d, bias, rp, ri, k, col_offset, 1, (int)ntiles, row_map, n_rows_dev, oi, os, st);
+    const int64_t ns = fallback_splits(ni, k);
+    const size_t half = align_up((size_t)ns * kFallbackRows * k * 4, 256);
+    const int64_t head = kFallbackRows < nu ? kFallbackRows : nu;
+    if (ns > 1 && ws != nullptr && ws_bytes >= 2 * half) {
+        const int tps = (int)((ntiles + ns - 1) / ns);
+        const int ns_eff = (int)((ntiles + tps - 1) / tps);
+        int32_t* pi = (int32_t*)ws; float* ps = (float*)((char*)ws + half);
+        if (int rc = dispatch_score(U, nu, V, ni, d, bias, rp, ri, k, col_offset, ns_eff, tps, row_map, n_rows_dev, 0, head, kFallbackRows,
+                                    head, pi, ps, st)) return rc;
+        if (int rc = merge_lists(pi, ps, ns_eff, kFallbackRows, k, oi, os, row_map, n_rows_dev, st)) return rc;
+        if (nu > head)
+            if (int rc = dispatch_score(U, nu, V, ni, d, bias, rp, ri, k, col_offset, 1, (int)ntiles, row_map, n_rows_dev, head, 0, 0,
+                                        nu - head, oi, os, st)) return rc;
+        return TKR_OK;
+    }
+    return dispatch_score(U, nu, V, ni, d, bias, rp, ri, k, col_offset, 1, (int)ntiles, row_map, n_rows_dev, 0, 0, 0, nu, oi, os, st);
 }
 }  // namespace tkr
 
@@ -393,7 +439,7 @@ extern "C" int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_
         if (ws == nullptr || ws_bytes < 2 * half) { set_error("score_topk workspace too small: have %zu, need %zu", ws_bytes, 2 * half); return TKR_ERR_WORKSPACE; }
         oi = (int32_t*)ws; os = (float*)((char*)ws + half);
     }
-    if (int rc = dispatch_score(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, ns, tps, nullptr, nullptr, oi, os, st)) return rc;
+    if (int rc = dispatch_score(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, ns, tps, nullptr, nullptr, 0, 0, 0, nu, oi, os, st)) return rc;
     if (ns > 1) return tkr_topk_merge(oi, os, ns, nu, k, out_idx, out_score, stream);
     return TKR_OK;
 }
