@@ -369,9 +369,10 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
                     if eng == "tc" else "f32 (exact fma-chain scores, CUDA cores)",
            "gpu_launches": launches, "clocks": clk.summary(), "rows_redone_by_exact_fallback_last_step": int(nfb.item()),
            "roofline": {"bound": "tensor", "kernel": "score_filter_kernel" if eng == "tc" else "score_topk_kernel",
-                        "achieved": flops / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
-                        "frac": flops / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
-                        "note": "FLOP = 2*nu*ni*d over the whole step (convert + filter + refine + fallback), against the burst bf16 peak"}}
+                        "achieved": flops / world / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
+                        "frac": flops / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
+                        "note": "per GPU: FLOP = 2*nu*(ni/world)*d over the whole step (convert + filter + merge + refine + fallback [+ all-gather]), against the burst bf16 peak"},
+           "scaling": "strong (fixed user batch and item table; item columns sharded over the GPUs)"}
     if world == 1:
         # e2e: host U batch + host V (copied once per pass of K batches) -> device -> lists back on the host
         Vh = V.cpu().pin_memory(); Uh = [u.cpu().pin_memory() for u in Ub]
