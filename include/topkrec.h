@@ -183,12 +183,14 @@ int tkr_score_topk(const float* U, int64_t nu, const float* V, int64_t ni, int32
  * re-scoring of the <= 64 survivors per row, a per-row error-bound certificate, and the exact kernel
  * above for the rows that cannot be certified (their count is written to *n_fallback_rows, a DEVICE
  * int32, if not NULL).  Shapes the filter does not cover (d + 3 > 256 after padding, k > 48) are
- * routed to tkr_score_topk entirely. */
+ * routed to tkr_score_topk entirely.
+ * items_prepared != 0: the previous call on this workspace used the same V / bias / ni / d / k and the same
+ * nu, so its BF16 item table is reused (an evaluator scores many user batches against one item table). */
 size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k, int32_t has_bias);
 int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
                       const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
                       int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
-                      void* stream);
+                      int32_t items_prepared, void* stream);
 
 /* Profiling aid: device buffer of [n_ctas][10 warps][4] int64 cycle counters filled by the filter kernel
  * (total / wait cycles per warp role); NULL (default) disables it. */

@@ -225,3 +225,18 @@ def test_tc_fallback_rows_use_item_splits():
     U[:1200] = np.abs(U[:1200]) * np.sign(V[4999])           # make the duplicate block score high for 1200 rows
     fb = _check(U, V, k, None, None, None, engines=("tc",))
     assert fb["tc"] >= 1100
+
+
+def test_tc_items_prepared_reuses_bf16_table():
+    """an evaluator scores several user batches against one item table: the second batch reuses the converted items"""
+    U, V, b, p, i = _case(600, 5000, 128, 30, seed=25, bias=True, rated=30)
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
+    need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(300, 5000, 128, 30, 1)
+    ws = torch.empty(need, dtype=torch.uint8, device="cuda")
+    Vd, bd, idx_d = t(V), t(b), t(i)
+    for h, prepared in ((0, False), (1, True)):
+        rows = slice(300 * h, 300 * (h + 1))
+        ptr = p[300 * h:300 * (h + 1) + 1]
+        gi, gs = topkrec.score_topk(t(U[rows].copy()), Vd, 30, bd, t(ptr.copy()), idx_d, engine="tc", ws=ws, items_prepared=prepared)
+        ri, rs = topk_ref.score_topk(U[rows], V, 30, b, ptr - ptr[0], i[ptr[0]:ptr[-1]])
+        assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gs.cpu().numpy().view(np.uint32), rs.view(np.uint32))

@@ -680,7 +680,7 @@ extern "C" size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int3
 extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
                                  const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
                                  int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
-                                 void* stream) {
+                                 int32_t items_prepared, void* stream) {
     TKR_CHECK_ARG(U && V && out_idx && out_score, "U, V and the outputs must not be NULL");
     TKR_CHECK_ARG(nu >= 0 && ni >= 1 && d >= 1 && k >= 1, "bad nu/ni/d/k");
     TKR_CHECK_ARG(rated_indptr == nullptr || rated_idx != nullptr, "rated_indptr without rated_idx");
@@ -701,12 +701,16 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     int32_t* midx = (int32_t*)(w + P.o_midx); float* mscore = (float*)(w + P.o_mscore);
     int32_t* fail = (int32_t*)(w + P.o_fail);
 
-    TKR_CUDA(cudaMemsetAsync(scal, 0, 64, st));
     const int has_bias = bias != nullptr;
+    // scal: [0] max item norm, [1] max |bias| (both belong to the prepared item table), [2] uncertified rows
+    if (items_prepared) TKR_CUDA(cudaMemsetAsync(scal + 2, 0, 4, st));
+    else TKR_CUDA(cudaMemsetAsync(scal, 0, 64, st));
     convert_rows_kernel<<<(unsigned)((nu + 7) / 8), 256, 0, st>>>(U, nu, d, P.dpad, nullptr, 1, has_bias, Ubf, unorm, nullptr, nullptr);
     TKR_LAUNCH_CHECK();
-    convert_rows_kernel<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(V, ni, d, P.dpad, bias, 0, has_bias, Vbf, nullptr, scal + 0, scal + 1);
-    TKR_LAUNCH_CHECK();
+    if (!items_prepared) {   // the BF16 item table + its norms stay valid in the workspace for later user batches
+        convert_rows_kernel<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(V, ni, d, P.dpad, bias, 0, has_bias, Vbf, nullptr, scal + 0, scal + 1);
+        TKR_LAUNCH_CHECK();
+    }
 
     CUtensorMap tmU, tmV;
     if (int rc = make_tmap(&tmU, Ubf, nu, P.dpad, FM)) return rc;

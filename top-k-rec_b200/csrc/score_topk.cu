@@ -450,7 +450,8 @@ extern "C" size_t tkr_score_topk_host_device_bytes(int64_t nu, int64_t ni, int32
     n += align_up((size_t)nu * d * 4, 256) + align_up((size_t)ni * d * 4, 256) + align_up((size_t)ni * 4, 256);
     n += align_up((size_t)(nu + 1) * 8, 256) + align_up((size_t)(n_rated > 0 ? n_rated : 1) * 4, 256);
     n += 2 * align_up((size_t)nu * k * 4, 256);
-    n += tkr_score_topk_workspace_bytes(nu, ni, d, k);
+    const size_t a = tkr_score_topk_workspace_bytes(nu, ni, d, k), b = tkr_score_topk_tc_workspace_bytes(nu, ni, d, k, 1);
+    n += (a > b ? a : b) + 1024;
     return n;
 }
 
@@ -484,8 +485,9 @@ extern "C" int tkr_score_topk_host(const float* U_host, int64_t nu, const float*
         TKR_CUDA(cudaMemcpyAsync(dP, rated_indptr_host, (size_t)(nu + 1) * 8, cudaMemcpyHostToDevice, st));
         if (n_rated > 0) TKR_CUDA(cudaMemcpyAsync(dI, rated_idx_host, (size_t)n_rated * 4, cudaMemcpyHostToDevice, st));
     }
-    if (int rc = tkr_score_topk(dU, nu, dV, ni, d, bias_host ? dB : nullptr, rated_indptr_host ? dP : nullptr,
-                                rated_indptr_host ? dI : nullptr, k, 0, dOi, dOs, ws, ws_bytes, stream)) return rc;
+    // tensor-core filter + exact refine (bit-identical to the exact engine; shapes it does not cover fall through to it)
+    if (int rc = tkr_score_topk_tc(dU, nu, dV, ni, d, bias_host ? dB : nullptr, rated_indptr_host ? dP : nullptr,
+                                   rated_indptr_host ? dI : nullptr, k, 0, dOi, dOs, ws, ws_bytes, nullptr, 0, stream)) return rc;
     TKR_CUDA(cudaMemcpyAsync(out_idx_host, dOi, (size_t)nu * k * 4, cudaMemcpyDeviceToHost, st));
     TKR_CUDA(cudaMemcpyAsync(out_score_host, dOs, (size_t)nu * k * 4, cudaMemcpyDeviceToHost, st));
     TKR_CUDA(cudaStreamSynchronize(st));

@@ -31,11 +31,17 @@ def filtered_topk(umat, temat, total, bias, rated_indptr, rated_idx, user_batch=
     b = torch.from_numpy(bias).to(dev) if bias is not None else None
     ridx = torch.from_numpy(rated_idx).to(dev)
     lists = np.empty((umat.shape[0], total), np.int32)
+    ws = None
     for r0 in range(0, umat.shape[0], user_batch):
         r1 = min(umat.shape[0], r0 + user_batch)
         U = torch.from_numpy(umat[r0:r1]).to(dev)
         rptr = torch.from_numpy(rated_indptr[r0:r1 + 1].copy()).to(dev)
-        idx, _ = topkrec.score_topk(U, V, total, b, rptr, ridx)
+        full = r1 - r0 == user_batch
+        if ws is None:
+            need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(user_batch, V.shape[0], V.shape[1], total, int(b is not None))
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        # the BF16 item table converted for the first full batch is reused by the following full batches
+        idx, _ = topkrec.score_topk(U, V, total, b, rptr, ridx, engine='tc', ws=ws, items_prepared=(r0 > 0 and full))
         lists[r0:r1] = idx.cpu().numpy()
     return lists
 

@@ -64,7 +64,7 @@ def lib():
     L.tkr_score_topk_workspace_bytes.restype = sz; L.tkr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.tkr_score_topk.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
     L.tkr_score_topk_tc_workspace_bytes.restype = sz; L.tkr_score_topk_tc_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
-    L.tkr_score_topk_tc.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp, vp]
+    L.tkr_score_topk_tc.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp, i32, vp]
     L.tkr_score_topk_host_device_bytes.restype = sz
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
@@ -276,10 +276,11 @@ def bpr_sample(sampler: Sampler, first_draw, n, device="cuda"):
 
 
 def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset=0, out=None, ws=None, engine="exact",
-               n_fallback=None):
+               n_fallback=None, items_prepared=False):
     """Device tensors in, device tensors out: (idx int32 [nu,k], score fp32 [nu,k]).
     engine='exact': fp32 CUDA-core kernel; engine='tc': tcgen05 BF16 filter + exact refine (same bits).
-    n_fallback (tc only): optional int32 CUDA tensor [1] receiving the number of rows the exact kernel re-did."""
+    n_fallback (tc only): optional int32 CUDA tensor [1] receiving the number of rows the exact kernel re-did.
+    items_prepared (tc only): reuse the BF16 item table the previous call left in `ws` (same V, bias, shapes)."""
     f32 = torch.float32
     _need_cuda(U, V)
     nu, d = U.shape
@@ -303,7 +304,7 @@ def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset
             int(k), int(col_offset), out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws.numel())
     with torch.cuda.device(U.device):
         if engine == "tc":
-            _check(lib().tkr_score_topk_tc(*args, _dev(n_fallback, torch.int32, "n_fallback"), _stream()))
+            _check(lib().tkr_score_topk_tc(*args, _dev(n_fallback, torch.int32, "n_fallback"), int(bool(items_prepared)), _stream()))
         else:
             _check(lib().tkr_score_topk(*args, _stream()))
     return out

@@ -49,12 +49,12 @@ def _gather(t, group):
 
 
 def sharded_score_topk(U, V_shard, k, col_offset, bias_shard=None, rated_indptr=None, rated_idx=None, group=None,
-                       score_fn=None, merge_fn=None, engine="tc", ws=None):
+                       score_fn=None, merge_fn=None, engine="tc", ws=None, items_prepared=False):
     """Filtered top-k over item-sharded V.  ``score_fn`` / ``merge_fn`` default to the CUDA engine
     (tests on CPU/gloo inject checkers to exercise the exchange logic)."""
     if score_fn is None or merge_fn is None:
         import topkrec
-        score_fn = score_fn or (lambda *a, **kw: topkrec.score_topk(*a, engine=engine, ws=ws, **kw))
+        score_fn = score_fn or (lambda *a, **kw: topkrec.score_topk(*a, engine=engine, ws=ws, items_prepared=items_prepared, **kw))
         merge_fn = merge_fn or topkrec.topk_merge
     idx, score = score_fn(U, V_shard, k, bias_shard, rated_indptr, rated_idx, col_offset=col_offset)
     if group is None and not dist.is_initialized():
