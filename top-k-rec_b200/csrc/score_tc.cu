@@ -537,22 +537,32 @@ __global__ void __launch_bounds__(256) score_refine_kernel(const float* __restri
     if (row >= nu) return;
     for (int c = lane; c < d; c += 32) us[c] = U[row * d + c];
     __syncwarp();
+    // each lane scores two candidates; the two fma chains are interleaved (ILP) and V is read 128 bits at a time
     uint64_t mykey[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int32_t gc = cand_idx[row * KPRIME + h * 32 + lane];
-        uint64_t key = 0;
-        if (gc >= 0) {
-            const int64_t lc = gc - col_offset;
-            const float* v = V + lc * d;
-            float acc = 0.f;
-            for (int c = 0; c < d; ++c) acc = fmaf(us[c], __ldg(v + c), acc);   // ascending-index chain = the oracle's definition
-            if (bias != nullptr) acc = acc + __ldg(bias + lc);
-            key = make_key(acc + 0.0f, gc);
+    const int32_t gc0 = cand_idx[row * KPRIME + lane], gc1 = cand_idx[row * KPRIME + 32 + lane];
+    const float* v0 = V + (gc0 >= 0 ? gc0 - col_offset : 0) * d;
+    const float* v1 = V + (gc1 >= 0 ? gc1 - col_offset : 0) * d;
+    float acc0 = 0.f, acc1 = 0.f;
+    if ((d & 3) == 0 && (((uintptr_t)V) & 15) == 0) {
+        for (int c = 0; c < d; c += 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(v0 + c)), b4 = __ldg(reinterpret_cast<const float4*>(v1 + c));
+            const float u0 = us[c], u1 = us[c + 1], u2 = us[c + 2], u3 = us[c + 3];
+            acc0 = fmaf(u0, a.x, acc0); acc1 = fmaf(u0, b4.x, acc1);     // ascending-index chains = the oracle's definition
+            acc0 = fmaf(u1, a.y, acc0); acc1 = fmaf(u1, b4.y, acc1);
+            acc0 = fmaf(u2, a.z, acc0); acc1 = fmaf(u2, b4.z, acc1);
+            acc0 = fmaf(u3, a.w, acc0); acc1 = fmaf(u3, b4.w, acc1);
         }
-        mykey[h] = key;
-        keys[h * 32 + lane] = key;
+    } else {
+        for (int c = 0; c < d; ++c) { acc0 = fmaf(us[c], __ldg(v0 + c), acc0); acc1 = fmaf(us[c], __ldg(v1 + c), acc1); }
     }
+    if (bias != nullptr) {
+        if (gc0 >= 0) acc0 = acc0 + __ldg(bias + (gc0 - col_offset));
+        if (gc1 >= 0) acc1 = acc1 + __ldg(bias + (gc1 - col_offset));
+    }
+    mykey[0] = gc0 >= 0 ? make_key(acc0 + 0.0f, gc0) : 0ull;
+    mykey[1] = gc1 >= 0 ? make_key(acc1 + 0.0f, gc1) : 0ull;
+    keys[lane] = mykey[0];
+    keys[32 + lane] = mykey[1];
     __syncwarp();
     int rank[2] = {0, 0};
     for (int e = 0; e < KPRIME; ++e) {
