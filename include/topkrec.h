@@ -192,9 +192,14 @@ int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, in
                       int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
                       int32_t items_prepared, void* stream);
 
-/* Profiling aid: device buffer of [n_ctas][10 warps][4] int64 cycle counters filled by the filter kernel
- * (total / wait cycles per warp role); NULL (default) disables it. */
+/* Profiling aid: device buffer of [n_ctas][14 warps][4] int64 cycle counters filled by the filter kernel
+ * (total / wait cycles per warp role); NULL (default) disables it.  While counters are set,
+ * tkr_debug_set_filter_mode selects 1 = normal, 2 = epilogue never reads TMEM (TMA + MMA ceiling probe),
+ * 3 = epilogue drains TMEM without scanning (TMEM read ceiling probe); 2 and 3 return after the filter
+ * kernel without producing lists. */
 void tkr_debug_set_filter_counters(long long* dev_buf);
+void tkr_debug_set_filter_mode(int32_t mode);
+int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */
 
 /* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
  * U_host/V_host/bias_host/rated_* in host memory, results to host memory.

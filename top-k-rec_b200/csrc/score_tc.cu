@@ -27,9 +27,13 @@ int launch_exact_rows(const float* U, int64_t nu, const float* V, int64_t ni, in
                       const int32_t* n_rows_dev, int32_t* oi, float* os, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t exact_rows_workspace_bytes(int64_t ni, int k);
 
-constexpr int FM = 128, FN = 256, FK = 64;        // MMA tile; FK bf16 = one 128-byte swizzle span
-constexpr int A_CHUNK_BYTES = FM * FK * 2;        // 16 KB
-constexpr int B_STAGE_BYTES = FN * FK * 2;        // 32 KB
+constexpr int FM = 128;                           // user rows per CTA = its 128 TMEM lanes; a CTA pair covers 256
+constexpr int FN = 256, FK = 64;                  // item columns per MMA tile; FK bf16 = one 128-byte swizzle span
+constexpr int A_CHUNK_BYTES = FM * FK * 2;        // 16 KB: this CTA's rows of one K chunk of U
+constexpr int B_HALF = FN / 2;                    // V rows (tile columns) each CTA of the pair stages; the MMA reads both halves
+constexpr int B_CHUNK_BYTES = B_HALF * FK * 2;    // 16 KB per CTA per K chunk
+// smem ring depth is 4 stages (8 when a tile is a single K chunk); a stage holds cps K chunks
+constexpr int MAX_CPS = 2;                        // K chunks per stage: 2 (d_pad >= 128) or 1
 constexpr int KPRIME = 64, CAP = 128;             // kept candidates / buffer capacity per row
 constexpr int F_EPI_WARPS = 8;                    // two per TMEM lane quarter: each takes half the columns of a tile
 constexpr int F_SEL_WARPS = 4;                    // selection warps: one per lane quarter, own the rows' candidate lists
@@ -37,16 +41,15 @@ constexpr int F_SEL_WARPS = 4;                    // selection warps: one per la
 // lowest ids, the TMEM-draining epilogue the middle ones, and the two single-thread issuers the highest.
 constexpr int W_SEL = 0, W_EPI = F_SEL_WARPS, W_TMA = F_SEL_WARPS + F_EPI_WARPS, W_MMA = W_TMA + 1;
 constexpr int F_THREADS = 32 * (W_MMA + 1);       // warps 0-3 selection, 4-11 epilogue, 12 TMA, 13 MMA + TMEM alloc
-constexpr int RING = 64;                          // hand-off slots per selection warp
+constexpr int RING = 128;                         // hand-off slots per selection warp
+constexpr int COL_BITS = 26;                      // a sweep (item split) spans < 2^26 tile-space columns
 
 // Hand-off from the epilogue (which must drain TMEM at MMA pace) to the selection warps (which do the rare,
-// latency-bound work): an epilogue thread whose 32-score chunk reaches its row's threshold copies the chunk
-// into a ring slot and moves on.
+// latency-bound work).  One message = one score that reached its row's threshold, published with a single
+// 64-bit shared-memory store (no fence on the producer side): score bits << 32 | 1 << 31 | row-in-quarter << 26 |
+// column relative to the sweep.  0 = empty slot; the consumer clears a slot before it advances `tail`.
 struct SelShared {
-    uint4 data[RING];             // 4 consecutive scores (one max-tree group)
-    long long col0[RING];         // global tile-space column of data[.].x
-    int row[RING];
-    volatile int flag[RING];      // slot s holds reservation number flag[s]-1 once published
+    unsigned long long msg[RING];
     int head;                     // next reservation (atomicAdd by producers)
     volatile int tail;            // reservations consumed
     volatile int done;            // producer warps finished (2 per selection warp)
@@ -78,18 +81,42 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (++spins > (1u << 26)) __trap();
     }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+// CTA-pair plumbing (cta_group::2): both CTAs of a cluster stage operands in their own shared memory, the
+// leader (cluster rank 0) issues the MMAs for both, and completion events are multicast to both.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {   // same smem offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// (default .release.cta semantics: a cluster-scope release here costs a fence per arrival; the data the MMA
+// depends on is ordered by tcgen05.fence + tcgen05.wait::ld, not by this arrive)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA into this CTA's shared memory, transaction bytes credited to the barrier at cluster address `bar_cluster`
+// (the leader's): the leader's MMA thread waits once for both halves.
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives on `bar` when all prior MMAs of this thread are done
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+// Arrives on `bar` (same offset) in both CTAs of the pair when all prior MMAs of this thread are done.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -112,8 +139,8 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D = F32 (bits 4-5 = 1), A = B = BF16 (bits 7-9, 10-12 = 1), both K-major,
-// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)(FM >> 4) << 24);
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.  cta_group::2: M = 256 (128 rows from each CTA), N = 256.
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(FN >> 3) << 17) | ((uint32_t)((2 * FM) >> 4) << 24);
 
 // ------------------------------------------------------------------ convert
 // One warp per row: fp32 -> bf16 (round to nearest even), zero padded to d_pad; optional bias split
@@ -156,7 +183,7 @@ __global__ void __launch_bounds__(256) convert_rows_kernel(const float* __restri
 // ------------------------------------------------------------------ filter
 struct FilterParams {
     int64_t nu, ni, col_offset;
-    int kb, stages, tiles_per_split;
+    int kb, cps, stages, tiles_per_split;   // K chunks of 64, chunks per smem stage, ring depth
     int seed_tiles;          // first tiles of each sweep scanned in seed mode and replayed at the end (0 = off)
     float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
     const int64_t* rated_indptr;
@@ -210,6 +237,9 @@ __device__ __forceinline__ void warp_sort128_desc(uint64_t (&key)[4], int lane) 
 }
 
 template <bool DBG> __device__ __forceinline__ long long tick() { return DBG ? clock64() : 0ll; }
+// MODE 0 = product; 1 = product + role cycle counters; 2 = counters, epilogue never reads TMEM (TMA + MMA ceiling);
+// 3 = counters, epilogue drains TMEM but does not scan (TMEM read ceiling); 4 = 2 without V loads (barrier handshake
+// only); 5 = full scan but thresholds pinned at +inf after seeding (no hand-offs).  2-5 produce no lists (profiling only).
 
 // Epilogue fast path: a max tree over the thread's 32 scores (groups of 4) and one compare against its row's
 // threshold.  On a hit, each group whose max passes is handed to the row's selection warp through its ring
@@ -224,21 +254,29 @@ __device__ __forceinline__ float max32(const uint32_t (&v)[32]) {
     return fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
 }
 
-__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], int64_t c0, int row, float tau, SelShared* hs) {
+// Slow path of the epilogue, kept out of line so the drain loop stays small: publish every score of a 4-score
+// group that reaches the threshold.  rc = 1 << 31 | row-in-quarter << 26 | sweep-relative column of x0.
+__device__ __noinline__ void push_hits(float x0, float x1, float x2, float x3, uint32_t rc, float tau, SelShared* hs) {
+    const float x[4] = {x0, x1, x2, x3};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (x[e] >= tau) {
+            const int slot = atomicAdd(&hs->head, 1);
+            while (slot - hs->tail >= RING) __nanosleep(64);          // ring full: wait for the selection warp
+            reinterpret_cast<volatile unsigned long long*>(hs->msg)[slot & (RING - 1)] =
+                ((unsigned long long)__float_as_uint(x[e]) << 32) | (unsigned long long)(rc + (uint32_t)e);
+        }
+    }
+}
+
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], uint32_t rc0, float tau, SelShared* hs) {
     if (max32(v) >= tau) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const float mg = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])), fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-            if (mg >= tau) {
-                const int slot = atomicAdd(&hs->head, 1);
-                while (slot - hs->tail >= RING) __nanosleep(64);     // ring full: wait for the selection warp
-                const int sl = slot & (RING - 1);
-                hs->data[sl] = make_uint4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
-                hs->col0[sl] = c0 + 4 * g;
-                hs->row[sl] = row;
-                __threadfence_block();
-                hs->flag[sl] = slot + 1;                             // publish
-            }
+            if (mg >= tau)
+                push_hits(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]),
+                          rc0 + 4 * g, tau, hs);
         }
     }
 }
@@ -271,19 +309,29 @@ __device__ __forceinline__ float sel_compact(uint64_t* buf, int n, int lane, uin
     return last ? ord_to_f32((uint32_t)(last >> 32)) : -INFINITY;
 }
 
-template <bool DBG>
-__global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid_constant__ CUtensorMap tmU,
-                                                                    const __grid_constant__ CUtensorMap tmV, FilterParams p) {
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
+score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV, FilterParams p) {
+    constexpr bool DBG = MODE != 0;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024 B alignment
+    // SWIZZLE_128B needs 1024 B alignment; both CTAs of the pair compute the same offsets (the MMA addresses the
+    // peer's operands by the leader's offsets)
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
     unsigned char* sA = base;
     unsigned char* sB = sA + (size_t)p.kb * A_CHUNK_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * B_STAGE_BYTES);
-    uint64_t* full = bars;                 // [stages]  TMA -> MMA
-    uint64_t* empty = bars + 8;            // [stages]  MMA -> TMA
-    uint64_t* tfull = bars + 16;           // [2]       MMA -> epilogue
-    uint64_t* tempty = bars + 18;          // [2]       epilogue -> MMA
-    uint64_t* afull = bars + 20;           //           U tile landed
+    const int cps = p.cps, spt = p.kb / p.cps;                          // K chunks per stage, stages per tile
+    const uint32_t smask = (uint32_t)p.stages - 1u;                     // stages is a power of two and a multiple of spt
+    const uint32_t sshift = 31u - (uint32_t)__clz(p.stages);
+    const uint32_t stage_bytes = (uint32_t)cps * B_CHUNK_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * stage_bytes);
+    // full[s]: stage s landed in both CTAs (the leader's copy is the live one).  The first stage of a tile also
+    // collects the 2 * F_EPI_WARPS arrivals with which the epilogues of both CTAs hand back the accumulator that
+    // tile will overwrite, so the MMA thread does ONE barrier wait per stage and none per accumulator
+    // (a try_wait costs ~160 cycles even on a completed phase; the issuing thread has ~1000 cycles per tile).
+    uint64_t* full = bars;                 // [STAGES]
+    uint64_t* empty = bars + 8;            // [STAGES]  MMA -> TMA, multicast to both CTAs
+    uint64_t* tfull = bars + 16;           // [2]       MMA -> epilogue, multicast to both CTAs
+    uint64_t* afull = bars + 20;           //           U tiles of both CTAs landed (leader's copy)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
     volatile float* tau_sh = reinterpret_cast<float*>(bars + 22);        // [FM] row thresholds (selection warps write, epilogue reads)
     int* cnt_sh = reinterpret_cast<int*>(bars + 22) + FM;                // [FM] candidates buffered per row
@@ -293,8 +341,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     SelShared* sel = reinterpret_cast<SelShared*>(seed_sh + 2 * FM);     // [F_SEL_WARPS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                            // 0 = leader (issues the pair's MMAs)
     const int64_t row0 = (int64_t)blockIdx.x * FM;
     const int split = blockIdx.y;
+    const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
     const int64_t ntiles = (p.ni + FN - 1) / FN;
     const int64_t t0 = (int64_t)split * p.tiles_per_split;
     const int64_t t1 = (t0 + p.tiles_per_split < ntiles) ? t0 + p.tiles_per_split : ntiles;
@@ -302,11 +352,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
     const int ntl = (int)(t1 - t0);
     const int T0 = (p.seed_tiles > 0 && ntl >= 4 * p.seed_tiles) ? p.seed_tiles : 0;
     const int nseq = ntl + T0;
-    auto tile_of = [&](int tl) -> int64_t { return t0 + (tl < ntl ? tl : tl - ntl); };
+    auto tile_rel = [&](int tl) -> int { return tl < ntl ? tl : tl - ntl; };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull + a, 1); mbar_init(tempty + a, F_EPI_WARPS); }
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full + s, (s % spt) == 0 ? 1 + 2 * F_EPI_WARPS : 1);   // stages % spt == 0: stage s opens a tile iff s % spt == 0
+            mbar_init(empty + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) mbar_init(tfull + a, 1);
         mbar_init(afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -319,80 +372,98 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
         rhi_sh[t] = (ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + t + 1) : 0;
     }
     for (int t = threadIdx.x; t < F_SEL_WARPS * (int)(sizeof(SelShared) / 4); t += F_THREADS) reinterpret_cast<int*>(sel)[t] = 0;
-    if (warp == W_MMA) {   // whole TMEM: two 256-column fp32 accumulators (1 CTA per SM, smem-limited)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (warp == W_MMA) {   // whole TMEM of both SMs: two 256-column fp32 accumulators each (1 CTA per SM, smem-limited)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();                    // barriers of both CTAs initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == W_TMA) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (both CTAs: own U rows, own half of every V tile) =====================
         if (lane == 0) {
-            mbar_expect_tx(afull, (uint32_t)p.kb * A_CHUNK_BYTES);
-            for (int c = 0; c < p.kb; ++c) tma_load_2d(sA + (size_t)c * A_CHUNK_BYTES, &tmU, afull, c * FK, (int)row0);
+            const uint32_t afull_leader = mapa_shared(smem_u32(afull), 0);
+            if (rank == 0) mbar_expect_tx(afull, 2u * (uint32_t)p.kb * A_CHUNK_BYTES);
+            for (int c = 0; c < p.kb; ++c) tma_load_2d_pair(sA + (size_t)c * A_CHUNK_BYTES, &tmU, afull_leader, c * FK, (int)row0);
             uint32_t it = 0;
             long long dbg_wait0 = 0;
             const long long dbg_t0 = tick<DBG>();
             for (int tl = 0; tl < nseq; ++tl) {
-                const int64_t tile = tile_of(tl);
-                for (int c = 0; c < p.kb; ++c, ++it) {
-                    const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+                const int vrow = (int)((t0 + tile_rel(tl)) * FN) + (int)rank * B_HALF;
+                for (int j = 0; j < spt; ++j, ++it) {
+                    const uint32_t s = it & smask, ph = (it >> sshift) & 1;
                     const long long w0 = tick<DBG>();
                     mbar_wait(empty + s, ph ^ 1);
                     dbg_wait0 += tick<DBG>() - w0;
-                    mbar_expect_tx(full + s, B_STAGE_BYTES);
-                    tma_load_2d(sB + (size_t)s * B_STAGE_BYTES, &tmV, full + s, c * FK, (int)(tile * FN));
+                    if (MODE == 4) {                                   // probe: no V traffic, barrier handshake only
+                        if (rank == 0) mbar_arrive(full + s);
+                        continue;
+                    }
+                    if (rank == 0) mbar_expect_tx(full + s, 2u * stage_bytes);
+                    const uint32_t fbar = mapa_shared(smem_u32(full + s), 0);
+                    for (int c = 0; c < cps; ++c)
+                        tma_load_2d_pair(sB + (size_t)s * stage_bytes + (size_t)c * B_CHUNK_BYTES, &tmV, fbar, (j * cps + c) * FK, vrow);
                 }
             }
-            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_wait0; }
+            if (p.dbg) { long long* o = p.dbg + ((size_t)cta_lin * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_wait0; }
         }
     } else if (warp == W_MMA) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (lane == 0 && rank == 0) {
             mbar_wait(afull, 0);
             tc_fence_after();
             uint32_t it = 0;
-            int tl = 0;
-            long long dbg_w_e = 0, dbg_w_f = 0;
+            long long dbg_w_f = 0;
             const long long dbg_t0 = tick<DBG>();
-            for (; tl < nseq; ++tl) {
-                const int acc = tl & 1;
-                const long long w0 = tick<DBG>();
-                mbar_wait(tempty + acc, ((tl >> 1) & 1) ^ 1);       // epilogue has drained this accumulator
-                dbg_w_e += tick<DBG>() - w0;
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)acc * FN;
-                for (int c = 0; c < p.kb; ++c, ++it) {
-                    const uint32_t s = it % p.stages, ph = (it / p.stages) & 1;
+            unsigned long long dbg_g0 = 0, dbg_g1 = 0;
+            if (DBG) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+            // descriptors differ only in the start-address field (bits 0-13, units of 16 B): hoist the constant part
+            const uint64_t desc_hi = make_sw128_desc(0);
+            const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+            for (int tl = 0; tl < nseq; ++tl) {
+                const uint32_t tmem_d = tmem_base + (uint32_t)(tl & 1) * FN;
+                for (int j = 0; j < spt; ++j, ++it) {
+                    const uint32_t s = it & smask, ph = (it >> sshift) & 1;
                     const long long w1 = tick<DBG>();
-                    mbar_wait(full + s, ph);                          // V chunk landed
+                    mbar_wait(full + s, ph);          // V stage landed in both CTAs (+ accumulator handed back, if j == 0)
                     dbg_w_f += tick<DBG>() - w1;
                     tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + (size_t)c * A_CHUNK_BYTES), b0 = smem_u32(sB + (size_t)s * B_STAGE_BYTES);
+                    const uint32_t a0 = a_lo + (uint32_t)(j * cps) * (A_CHUNK_BYTES >> 4), b0 = b_lo + s * (stage_bytes >> 4);
 #pragma unroll
-                    for (int ks = 0; ks < FK / 16; ++ks)              // K = 16 bf16 = 32 bytes per instruction
-                        umma_bf16(tmem_d, make_sw128_desc(a0 + ks * 32), make_sw128_desc(b0 + ks * 32), kIdescBf16, (c | ks) != 0);
-                    umma_commit(empty + s);                           // smem stage reusable once these MMAs retire
+                    for (int c = 0; c < MAX_CPS; ++c) {
+                        if (c < cps) {
+#pragma unroll
+                            for (int ks = 0; ks < FK / 16; ++ks)      // K = 16 bf16 = 32 bytes per instruction
+                                umma_bf16_pair(tmem_d, desc_hi | (uint64_t)(a0 + c * (A_CHUNK_BYTES >> 4) + ks * 2),
+                                               desc_hi | (uint64_t)(b0 + c * (B_CHUNK_BYTES >> 4) + ks * 2), kIdescBf16, (j | c | ks) != 0);
+                        }
+                    }
+                    umma_commit_pair(empty + s);                      // smem stage reusable (both CTAs) once these MMAs retire
                 }
-                umma_commit(tfull + acc);                             // accumulator ready for the epilogue
+                umma_commit_pair(tfull + (tl & 1));                   // accumulator ready for both epilogues
             }
-            if (p.dbg) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_w_e; o[2] = dbg_w_f; }
+            if (DBG) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g1));
+            if (p.dbg) { long long* o = p.dbg + ((size_t)cta_lin * 14 + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = 0; o[2] = dbg_w_f; o[3] = (long long)(dbg_g1 - dbg_g0); }
         }
     } else {
         if (warp >= W_EPI) {
         // ===================== epilogue: thread == (user row, column half); drains TMEM at MMA pace =====================
         const int q = warp & 3;                                       // TMEM lane quarter this warp may read
-        const int half = (warp - W_EPI) >> 2;                                   // columns [half*128, half*128 + 128) of every tile
+        const int half = (warp - W_EPI) >> 2;                         // columns [half*128, half*128 + 128) of every tile
         const int row = q * 32 + lane;
         SelShared* hs = sel + q;
+        // accumulator hand-back: after tile tl, arrive on the leader's full barrier of the first stage of tile tl + 2
+        const uint32_t full_leader = mapa_shared(smem_u32(full), 0);
+        if (lane == 0) {                                              // tiles 0 and 1 find their accumulators free
+            mbar_arrive_cluster(full_leader);
+            mbar_arrive_cluster(full_leader + 8u * ((uint32_t)spt & smask));
+        }
         constexpr int NCHUNK = FN / 2 / 32;                           // 4 chunks of 32 columns per thread per tile
         long long dbg_w = 0, dbg_c = 0, dbg_s = 0;
         float s1 = -INFINITY, s2 = -INFINITY, s3 = -INFINITY, s4 = -INFINITY;
         for (int tl = 0; tl < nseq; ++tl) {
-            const int64_t tile = tile_of(tl);
             const int acc = tl & 1;
             const bool seeding = tl < T0;
             if (T0 > 0 && tl == T0) {
@@ -412,41 +483,50 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
             mbar_wait(tfull + acc, (tl >> 1) & 1);
             dbg_w += tick<DBG>() - w0;
             tc_fence_after();
+            const uint32_t handback = full_leader + 8u * ((uint32_t)((tl + 2) * spt) & smask);
+            if (MODE == 2 || MODE == 4) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(handback);
+                continue;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * FN + (uint32_t)half * (FN / 2);
-            const int64_t cbase = tile * FN + half * (FN / 2);
+            // message header of this thread's first column of the tile (sweep-relative column < 2^COL_BITS)
+            const uint32_t rcb = 0x80000000u | ((uint32_t)lane << COL_BITS) | (uint32_t)(tile_rel(tl) * FN + half * (FN / 2));
             // two register buffers: the tcgen05.ld of chunk c+1 is in flight while chunk c is scanned
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
-            const float tau = tau_sh[row];                            // refreshed once per tile (a stale value only costs extra hand-offs)
+            const float tau = MODE == 5 ? INFINITY : tau_sh[row];     // refreshed once per tile (a stale value only costs extra hand-offs)
 #pragma unroll 1
             for (int cc = 0; cc < NCHUNK; cc += 2) {
                 long long c0_ = tick<DBG>();
                 tmem_ld_wait();
                 tmem_ld32(taddr + (cc + 1) * 32, vb);
                 long long c1_ = tick<DBG>();
-                if (seeding) seed_chunk(va, s1, s2, s3, s4); else scan_chunk(va, cbase + cc * 32, row, tau, hs);
+                if (MODE == 3) s1 = fmaxf(s1, __uint_as_float(va[0] ^ va[31])); else if (seeding) seed_chunk(va, s1, s2, s3, s4); else scan_chunk(va, rcb + cc * 32, tau, hs);
                 long long c2_ = tick<DBG>();
                 dbg_c += c1_ - c0_; dbg_s += c2_ - c1_;
                 c0_ = tick<DBG>();
                 tmem_ld_wait();
                 if (cc + 2 < NCHUNK) tmem_ld32(taddr + (cc + 2) * 32, va);
                 c1_ = tick<DBG>();
-                if (seeding) seed_chunk(vb, s1, s2, s3, s4); else scan_chunk(vb, cbase + (cc + 1) * 32, row, tau, hs);
+                if (MODE == 3) s1 = fmaxf(s1, __uint_as_float(vb[0] ^ vb[31])); else if (seeding) seed_chunk(vb, s1, s2, s3, s4); else scan_chunk(vb, rcb + (cc + 1) * 32, tau, hs);
                 c2_ = tick<DBG>();
                 dbg_c += c1_ - c0_; dbg_s += c2_ - c1_;
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + acc);
+            if (lane == 0) mbar_arrive_cluster(handback);
         }
         __syncwarp();
         if (lane == 0) { __threadfence_block(); atomicAdd((int*)&hs->done, 1); }
-        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)cta_lin * 14 + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; }
         } else {
         // ===================== selection: one warp per lane quarter owns the candidate lists of its 32 rows =====================
         const int q = warp - W_SEL;
         SelShared* hs = sel + q;
-        const int64_t ni = p.ni, col_offset = p.col_offset;
+        volatile unsigned long long* vmsg = hs->msg;
+        const int64_t ni = p.ni, col_offset = p.col_offset, sweep_col0 = t0 * FN;
         const int32_t* rated_idx = p.rated_idx;
         const bool has_rated = p.rated_indptr != nullptr;
         uint64_t* bufq = p.cand + ((size_t)split * p.nu + (size_t)row0) * CAP;     // row r of the tile at bufq + r*CAP
@@ -454,52 +534,62 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
         int tail = 0;
         long long dbg_idle = 0, dbg_busy = 0, dbg_n = 0, dbg_cmp = 0;
         for (;;) {
-            const int sl = tail & (RING - 1);
+            // lane l looks at slot tail + l; the published prefix is consumed as one lane-parallel batch
             const long long i0 = tick<DBG>();
+            unsigned long long m;
+            int n;
             bool finished = false;
             for (;;) {
-                if (hs->flag[sl] == tail + 1) break;
-                if (hs->done == 2 && *(volatile int*)&hs->head == tail) { finished = true; break; }
-                __nanosleep(200);                                              // idle: do not steal issue slots from the epilogue
+                m = vmsg[(tail + lane) & (RING - 1)];
+                const unsigned bal = __ballot_sync(0xffffffffu, ((uint32_t)m >> 31) != 0u);
+                n = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
+                if (n > 0) break;
+                int fin = 0;
+                if (lane == 0) fin = (hs->done == 2 && *(volatile int*)&hs->head == tail) ? 1 : 0;
+                fin = __shfl_sync(0xffffffffu, fin, 0);
+                if (fin) { finished = true; break; }
+                __nanosleep(100);                                              // idle: do not steal issue slots from the epilogue
             }
-            finished = __shfl_sync(0xffffffffu, (int)finished, 0) != 0;       // one decision for the warp
             if (finished) break;
             const long long i1 = tick<DBG>();
             dbg_idle += i1 - i0;
-            const int row = hs->row[sl];
-            const int64_t c0 = hs->col0[sl];
-            const float x = lane < 4 ? __uint_as_float(reinterpret_cast<const volatile uint32_t*>(&hs->data[sl])[lane]) : -INFINITY;
-            __syncwarp();
-            ++tail;
-            if (lane == 0) hs->tail = tail;                                    // slot free again: the chunk is in registers
-            const float tau_r = tau_sh[row];
-            int cnt_r = cnt_sh[row];
-            const int64_t col = c0 + lane;
+            const bool act = lane < n;
+            if (act) vmsg[(tail + lane) & (RING - 1)] = 0ull;                  // slot free again: the message is in a register
+            __threadfence_block();
+            tail += n;
+            if (lane == 0) hs->tail = tail;
+            const int row = q * 32 + (int)((uint32_t)(m >> COL_BITS) & 31u);
+            const int64_t col = sweep_col0 + (int64_t)((uint32_t)m & ((1u << COL_BITS) - 1u));
+            const float x = __uint_as_float((uint32_t)(m >> 32));
             const int32_t gc = (int32_t)(col + col_offset);
-            bool pass = lane < 4 && x >= tau_r && col < ni;
+            bool pass = act && col < ni && x >= tau_sh[row];
             if (has_rated && pass) pass = !rated_has(rated_idx, rlo_sh[row], rhi_sh[row], gc);
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            uint64_t* buf = bufq + (size_t)row * CAP;
-            if (pass) buf[cnt_r + __popc(bal & ((1u << lane) - 1u))] = make_key(x + 0.0f, gc);
-            cnt_r += __popc(bal);
-            __syncwarp();
-            if (cnt_r > CAP - 32) {                                            // could overflow on the next chunk: keep the best KPRIME
+            const uint64_t key = make_key(x + 0.0f, gc);
+            while (__any_sync(0xffffffffu, pass)) {
+                const int pos = pass ? atomicAdd(&cnt_sh[row], 1) : 0;
+                if (pass && pos < CAP) { bufq[(size_t)row * CAP + pos] = key; pass = false; }
+                const unsigned ovf = __ballot_sync(0xffffffffu, pass);         // lanes whose row buffer is full
+                if (ovf == 0u) break;
+                const int r = __shfl_sync(0xffffffffu, row, __ffs(ovf) - 1);
+                __syncwarp();
                 const long long k0 = tick<DBG>();
-                const float nt = sel_compact(buf, cnt_r, lane, skey);
-                cnt_r = KPRIME;
-                if (lane == 0) tau_sh[row] = fmaxf(tau_r, nt);
+                const float nt = sel_compact(bufq + (size_t)r * CAP, CAP, lane, skey);     // keep the best KPRIME of row r
+                const float tr = fmaxf(tau_sh[r], nt);
+                __syncwarp();
+                if (lane == 0) { tau_sh[r] = tr; cnt_sh[r] = KPRIME; }
+                __syncwarp();
+                if (pass && row == r && !(x >= tr)) pass = false;
                 dbg_cmp += tick<DBG>() - k0;
             }
-            if (lane == 0) cnt_sh[row] = cnt_r;
-            __syncwarp();
-            dbg_busy += tick<DBG>() - i1; ++dbg_n;
+            dbg_busy += tick<DBG>() - i1; dbg_n += n;
         }
         // final: sorted best-KPRIME list of every row of this quarter
         for (int r = 0; r < 32; ++r) {
             const int row = q * 32 + r;
             const int64_t grow = row0 + row;
             if (grow >= p.nu) break;
-            sel_compact(bufq + (size_t)row * CAP, cnt_sh[row], lane, skey);
+            const int cn = cnt_sh[row];
+            sel_compact(bufq + (size_t)row * CAP, cn < CAP ? cn : CAP, lane, skey);
             const int64_t o = ((int64_t)split * p.nu + grow) * KPRIME;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
@@ -508,14 +598,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) score_filter_kernel(const __grid
                 p.out_score[o + h2 * 32 + lane] = key ? ord_to_f32((uint32_t)(key >> 32)) : -INFINITY;
             }
         }
-        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 14 + warp) * 4; o[0] = dbg_busy; o[1] = dbg_idle; o[2] = dbg_n; o[3] = dbg_cmp; }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)cta_lin * 14 + warp) * 4; o[0] = dbg_busy; o[1] = dbg_idle; o[2] = dbg_n; o[3] = dbg_cmp; }
         }
     }
+    // Neither CTA may exit (or free TMEM) while its peer can still signal its barriers or read its operands.
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == W_MMA) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -631,9 +722,10 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int dpad, i
 }
 
 long long* g_filter_dbg = nullptr;   // set through tkr_debug_set_filter_counters (profiling aid)
+int g_filter_mode = 1;               // kernel MODE used while the counters are set (tkr_debug_set_filter_mode)
 
 struct TcPlan {
-    int dpad, kb, stages, ns, tps;
+    int dpad, kb, cps, stages, ns, tps;
     size_t smem;
     int seed_tiles;
     size_t o_ubf, o_vbf, o_unorm, o_scal, o_cand, o_sidx, o_sscore, o_midx, o_mscore, o_fail, o_tau0, o_fb, fb_bytes, total;
@@ -644,14 +736,18 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
     P->dpad = (dext + FK - 1) / FK * FK;
     P->kb = P->dpad / FK;
     if (P->kb > MAX_KB || k > 48 || nu <= 0 || ni <= 0) return false;
-    P->stages = P->kb >= 4 ? 4 : 5;
-    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * B_STAGE_BYTES + 256 + FM * (4 + 4 + 8 + 8 + 8) + F_SEL_WARPS * sizeof(SelShared);
-    const int64_t row_tiles = (nu + FM - 1) / FM, ntiles = (ni + FN - 1) / FN;
+    if (P->kb == 3) { P->kb = 4; P->dpad = 4 * FK; }       // stages per tile must divide the ring depth
+    P->cps = P->kb >= 2 ? 2 : 1;                           // kb in {1, 2, 4}: stages per tile = kb / cps in {1, 1, 2}
+    P->stages = P->kb == 1 ? 8 : 4;
+    P->smem = 1024 + (size_t)P->kb * A_CHUNK_BYTES + (size_t)P->stages * P->cps * B_CHUNK_BYTES + 256 + FM * (4 + 4 + 8 + 8 + 8) + F_SEL_WARPS * sizeof(SelShared);
+    const int64_t row_ctas = 2 * ((nu + 2 * FM - 1) / (2 * FM)), ntiles = (ni + FN - 1) / FN;   // CTAs come in pairs (256 user rows)
     // one CTA per SM; split the items only when the user tiles alone cannot fill the chip
-    int64_t ns = row_tiles >= kNumSMs ? 1 : (kNumSMs + row_tiles - 1) / row_tiles;
+    int64_t ns = row_ctas >= kNumSMs ? 1 : (kNumSMs + row_ctas - 1) / row_ctas;
     const int64_t maxs = ntiles / 16 > 0 ? ntiles / 16 : 1;
     if (ns > maxs) ns = maxs;
     if (ns > 32) ns = 32;
+    const int64_t max_tps = ((int64_t)1 << COL_BITS) / FN - 1;     // hand-off messages carry sweep-relative columns
+    if ((ntiles + ns - 1) / ns > max_tps) ns = (ntiles + max_tps - 1) / max_tps;
     P->tps = (int)((ntiles + ns - 1) / ns);
     P->ns = (int)((ntiles + P->tps - 1) / P->tps);
     size_t o = 0;
@@ -680,6 +776,21 @@ static bool tc_plan(int64_t nu, int64_t ni, int d, int k, bool has_bias, TcPlan*
 using namespace tkr;
 
 extern "C" void tkr_debug_set_filter_counters(long long* dev_buf) { g_filter_dbg = dev_buf; }
+extern "C" void tkr_debug_set_filter_mode(int32_t mode) { g_filter_mode = mode >= 1 && mode <= 5 ? mode : 1; }
+// CTA pairs of the filter kernel that can be resident at once on the current device (74 on a full B200), or < 0.
+extern "C" int32_t tkr_debug_filter_max_pairs(int32_t d) {
+    TcPlan P;
+    if (!tc_plan(256, 4096, d, 30, false, &P)) return -1;
+    if (cudaFuncSetAttribute(score_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem) != cudaSuccess) return -2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(148, 1, 1); cfg.blockDim = dim3(F_THREADS, 1, 1); cfg.dynamicSmemBytes = P.smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, score_filter_kernel<0>, &cfg) != cudaSuccess) return -3;
+    return n;
+}
 
 extern "C" size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int32_t d, int32_t k, int32_t has_bias) {
     TcPlan P;
@@ -724,22 +835,27 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
 
     CUtensorMap tmU, tmV;
     if (int rc = make_tmap(&tmU, Ubf, nu, P.dpad, FM)) return rc;
-    if (int rc = make_tmap(&tmV, Vbf, ni, P.dpad, FN)) return rc;
+    if (int rc = make_tmap(&tmV, Vbf, ni, P.dpad, B_HALF)) return rc;
     FilterParams fp;
-    fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.stages = P.stages; fp.tiles_per_split = P.tps;
+    fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.cps = P.cps; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
     fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
     fp.seed_tiles = P.seed_tiles; fp.out_tau0 = (float*)(w + P.o_tau0);
-    dim3 grid((unsigned)((nu + FM - 1) / FM), (unsigned)P.ns);
-    if (fp.dbg != nullptr) {
-        TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-        score_filter_kernel<true><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
-    } else {
-        TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
-        score_filter_kernel<false><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);
-    }
+    dim3 grid((unsigned)(2 * ((nu + 2 * FM - 1) / (2 * FM))), (unsigned)P.ns);   // clusters of 2 along x
+#define TKR_FILTER_LAUNCH(MODE)                                                                                                 \
+    do {                                                                                                                        \
+        TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem)); \
+        score_filter_kernel<MODE><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);                                            \
+    } while (0)
+    if (fp.dbg == nullptr) TKR_FILTER_LAUNCH(0);
+    else if (g_filter_mode == 2) TKR_FILTER_LAUNCH(2);
+    else if (g_filter_mode == 3) TKR_FILTER_LAUNCH(3);
+    else if (g_filter_mode == 4) TKR_FILTER_LAUNCH(4);
+    else if (g_filter_mode == 5) TKR_FILTER_LAUNCH(5);
+    else TKR_FILTER_LAUNCH(1);
     TKR_LAUNCH_CHECK();
+    if (fp.dbg != nullptr && g_filter_mode >= 2) return TKR_OK;   // ceiling probes: no lists were produced
     if (P.ns > 1)
         if (int rc = tkr_topk_merge(sidx, sscore, P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
 
