@@ -199,6 +199,7 @@ int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, in
  * kernel without producing lists. */
 void tkr_debug_set_filter_counters(long long* dev_buf);
 void tkr_debug_set_filter_mode(int32_t mode);
+void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 8); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */
 
 /* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
