@@ -2,12 +2,24 @@
 //
 //   convert   fp32 U / V rows -> BF16, K padded to a multiple of 64, bias folded in as three extra
 //             BF16 columns (hi+mid+lo = the fp32 bias exactly) against 1.0 in U; row norms for the bound
-//   filter    score_filter_kernel: TMA (cp.async.bulk.tensor, 128B swizzle) feeds a 4-5 stage smem ring,
-//             one elected thread issues tcgen05.mma (M=128, N=256, K=16, BF16 -> FP32 in TMEM), two
-//             256-column accumulators ping-pong so the MMA of tile t+1 overlaps the epilogue of tile t;
-//             4 epilogue warps read TMEM with tcgen05.ld (thread == user row), keep a register threshold,
-//             and append the (rare) survivors -- rated columns excluded -- to a per-row candidate buffer
-//             that a warp-wide bitonic sort compacts to the best 64.  The score matrix never leaves the SM.
+//   filter    score_filter_kernel, one CTA pair (cluster of 2) per 256 user rows, 1 CTA per SM:
+//             * TMA (cp.async.bulk.tensor, 128B swizzle) feeds a 4-stage smem ring; each CTA stages its own 128 user
+//               rows and half of every 256-item tile, and credits the leader CTA's mbarrier;
+//             * one thread of the leader issues tcgen05.mma.cta_group::2 (M=256 over the two SMs, N=256, K=16,
+//               BF16 -> FP32 in TMEM) into two 256-column accumulators that ping-pong; completion is multicast to both
+//               CTAs with tcgen05.commit.  The issuing thread does ONE mbarrier wait per stage: the epilogues'
+//               accumulator hand-back arrives on the same barrier as the TMA bytes (a try_wait costs ~160 cycles even
+//               when the phase is complete, a tcgen05.mma issue ~55: profiles/ubench/);
+//             * 16 epilogue warps (thread == user row x 64-column quarter) drain first and scan later: tcgen05.ld the
+//               64 scores to registers, hand the accumulator back (~300 cycles after the tile completed), then run a
+//               3-input max tree against the row threshold; a thread with a hit dumps its 32-score chunk to a
+//               shared-memory block ring;
+//             * 4 selection warps (one per TMEM lane quarter) consume the blocks four at a time, drop rated columns,
+//               append 64-bit keys to the row's candidate buffer and compact it to the best 64 with a warp-wide
+//               bitonic sort, raising the threshold;
+//             * the sweep starts with seed tiles spread evenly over the items (no hand-offs; each thread tracks its 4
+//               largest chunk maxima) so the threshold starts near the final one.
+//             The score matrix never leaves the SM.
 //   merge     item splits (few-user launches) are merged with topk_merge_kernel on the approximate keys
 //   refine    exact fp32 fma-chain scores of the <= 64 candidates, exact (score desc, column desc) top-k,
 //             and a certificate: the k-th exact score must beat (64th approximate score + eps_row), where
