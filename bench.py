@@ -9,7 +9,7 @@ items, d=128, reference optimiser (RMSProp), one "step" = one synchronous mini-b
 --batch triples (default 2^20) per GPU.  `value` = triples/s with the triples resident in
 HBM; `e2e` = the same through tkr_bpr_step_host (triples in pinned host memory, H2D + loss
 D2H inside the timed region).  The second path (score + top-30, BASELINE configs[4] slice:
-8192 users x 1M items, d=128) is reported in the same line under "score_topk".
+18944 users x 1M items, d=128) is reported in the same line under "score_topk".
 `--impl reference` times the CPU port of the reference step (oracle/bpr_ref.c, OpenMP, all
 host threads) on the same workload.
 """

@@ -198,6 +198,9 @@ int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, in
  * 3 = epilogue drains TMEM without scanning (TMEM read ceiling probe); 2 and 3 return after the filter
  * kernel without producing lists. */
 void tkr_debug_set_filter_counters(long long* dev_buf);
+/* tkr_bpr_step path choice: -1 automatic (default), 0 never / 1 always (when legal) take the counting path that
+ * updates rows occurring once in a batch in place; both paths follow the same step semantics. */
+void tkr_debug_set_count_mode(int32_t mode);
 void tkr_debug_set_filter_mode(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 8); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */

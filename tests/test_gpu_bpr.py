@@ -87,6 +87,57 @@ def test_bpr_step_modes(kw):
     _run_case(200, 150, 64, 256, 25, seed=4, cfg_kw=kw, init_scale=10.0)
 
 
+@pytest.fixture
+def count_mode():
+    """Force tkr_bpr_step onto the counting path (rows that occur once in a batch are updated in place by the
+    gradient kernel; chosen automatically only for tables far beyond L2)."""
+    import ctypes
+    L = topkrec.lib()
+    L.tkr_debug_set_count_mode.argtypes = [ctypes.c_int32]; L.tkr_debug_set_count_mode.restype = None
+    L.tkr_debug_set_count_mode(1)
+    yield
+    L.tkr_debug_set_count_mode(-1)
+
+
+@pytest.mark.parametrize("shape", [(300, 200, 128, 256, 12), (3000, 800, 50, 256, 40), (7, 5, 128, 512, 8),
+                                   (50000, 30000, 128, 4096, 6), (400, 300, 33, 64, 10), (5000, 1000, 256, 1 << 14, 3)])
+def test_bpr_step_count_mode_matches_oracle(count_mode, shape):
+    """same parity bar on the counting path: mixes of once-only rows (in place) and duplicated rows (accumulators)"""
+    nu, ni, d, B, steps = shape
+    _run_case(nu, ni, d, B, steps, seed=11 + d, item_skew=nu < 10000)
+
+
+@pytest.mark.parametrize("kw", [dict(optimizer="sgd"), dict(lambda_b=0.05), dict(lr=1e-2, lambda_u=0.1, lambda_i=0.05, lambda_j=0.01)])
+def test_bpr_step_count_mode_options(count_mode, kw):
+    _run_case(2000, 1500, 64, 256, 25, seed=12, cfg_kw=kw, init_scale=10.0)
+
+
+def test_bpr_step_count_mode_equals_accumulator_path():
+    """the two paths of tkr_bpr_step agree to rounding on the same stream (same update expression, different
+    summation route for the once-only rows: 0 + g)"""
+    import ctypes
+    L = topkrec.lib()
+    L.tkr_debug_set_count_mode.argtypes = [ctypes.c_int32]; L.tkr_debug_set_count_mode.restype = None
+    rng = np.random.default_rng(13)
+    nu, ni, d, B, steps = 20000, 9000, 128, 2048, 5
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    u = torch.from_numpy(rng.integers(0, nu, B * steps).astype(np.int32)).cuda()
+    i = torch.from_numpy(rng.integers(0, ni, B * steps).astype(np.int32)).cuda()
+    j = torch.from_numpy(rng.integers(0, ni, B * steps).astype(np.int32)).cuda()
+    cfg = topkrec.BprCfg(nu, ni, d)
+    outs = []
+    for mode in (0, 1):
+        L.tkr_debug_set_count_mode(mode)
+        dst = _to_dev(st)
+        ws = topkrec.bpr_workspace(cfg, B)
+        topkrec.bpr_step(cfg, dst["U"], dst["V"], dst["b"], dst["msU"], dst["msV"], dst["msb"], u, i, j, B, steps, ws)
+        outs.append({k: v.cpu().numpy() for k, v in dst.items()})
+        _assert_ws_clean(cfg, B, ws)
+    L.tkr_debug_set_count_mode(-1)
+    for name in outs[0]:
+        assert _rel(outs[1][name], outs[0][name]) <= 1e-6, name
+
+
 def test_bpr_step_lazy_rows_and_single_update():
     """Untouched rows and slots keep their bits; a touched row's rms slot moved exactly once."""
     rng = np.random.default_rng(5)

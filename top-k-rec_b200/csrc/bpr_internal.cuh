@@ -30,7 +30,10 @@ struct StepExtra {
     float* wq;
 };
 
-constexpr int MODE_LIST = 0, MODE_DENSE = 1;
+// MODE_LIST / MODE_DENSE: every touched row goes through the gradient accumulators (touched rows listed / flagged).
+// MODE_COUNT: a counting pre-pass tells how often each row occurs in the batch; rows that occur once are updated
+//             in place by the gradient kernel (no accumulator round trip), the others take the accumulator path.
+constexpr int MODE_LIST = 0, MODE_DENSE = 1, MODE_COUNT = 2;
 
 size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B);
 int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out);
@@ -39,7 +42,8 @@ int bpr_pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel);
 int bpr_make_sampler(const tkr_sampler* smp, SamplerDev* out);
 int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                       const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st);
+                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st,
+                      float* msU = nullptr, float* msV = nullptr);   // the slots are only needed by MODE_COUNT
 void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                       int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st);
 

@@ -13,6 +13,10 @@
 //                     re-zeroes the accumulator (the workspace is left clean for the next step).
 // All B gradients are therefore taken at the pre-step snapshot and every touched row gets
 // exactly ONE optimiser update per step.
+// Tables far larger than L2 (MODE_COUNT): the accumulator round trip (read-modify-write in bpr_grad, read + re-zero
+// in bpr_apply) would more than double the DRAM traffic of a row, so bpr_count_kernel first counts the occurrences
+// of every row in the batch and bpr_grad_kernel updates the rows that occur exactly once in place (no other triple
+// reads them, so the pre-step snapshot semantics hold); only duplicated rows take the accumulator path.
 #include "bpr_internal.cuh"
 
 namespace tkr {
@@ -102,10 +106,23 @@ template <bool L1> __device__ __forceinline__ float reg_val(float x, float lam) 
     return 0.5f * lam * x * x;
 }
 
+// One element of the optimiser update (App. A.4); shared by the apply kernel and the in-place path of the gradient
+// kernel so both produce the same bits.
+__device__ __forceinline__ void opt_update(const tkr_bpr_cfg& cfg, float g, float& v, float& m) {
+    if (cfg.optimizer == TKR_OPT_RMSPROP) {
+        m = cfg.rms_decay * m + (1.0f - cfg.rms_decay) * g * g;
+        v = v - cfg.lr * g / sqrtf(m + cfg.rms_eps);
+    } else {
+        v = v - cfg.lr * g;
+    }
+}
+
 // Rows of one triple held in registers: NCH chunks of 32*VW floats cover a row (d <= 32*VW*NCH).
-template <int VW, int NCH>
+// INPLACE: also the RMSProp slot rows of the rows this triple will update in place (MODE_COUNT).
+template <int VW, int NCH, bool INPLACE>
 struct TripleRows {
     Vec<VW> u[NCH], i[NCH], j[NCH];
+    Vec<VW> mu[INPLACE ? NCH : 1], mi[INPLACE ? NCH : 1], mj[INPLACE ? NCH : 1];
     __device__ __forceinline__ void load(const float* __restrict__ U, const float* __restrict__ V, int ru, int ri, int rj, int d, int lane) {
         const float* pu = U + (int64_t)ru * d;
         const float* pi = V + (int64_t)ri * d;
@@ -120,17 +137,40 @@ struct TripleRows {
             }
         }
     }
+    __device__ __forceinline__ void load_slots(const float* msU, const float* msV, int ru, int ri, int rj, bool su, bool si, bool sj, int d, int lane) {
+#pragma unroll
+        for (int c = 0; c < (INPLACE ? NCH : 0); ++c) {
+            const int off = (c * 32 + lane) * VW;
+            if (off < d) {
+                if (su) mu[c].load(msU + (int64_t)ru * d + off);
+                if (si) mi[c].load(msV + (int64_t)ri * d + off);
+                if (sj) mj[c].load(msV + (int64_t)rj * d + off);
+            }
+        }
+    }
 };
+
+// MODE_COUNT pre-pass: occurrences of every user / item row in the batch.
+__global__ void __launch_bounds__(256) bpr_count_kernel(const int32_t* __restrict__ ub, const int32_t* __restrict__ ib,
+                                                        const int32_t* __restrict__ jb, int64_t B, int32_t* __restrict__ cntU,
+                                                        int32_t* __restrict__ cntV) {
+    for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < B; n += (int64_t)gridDim.x * blockDim.x) {
+        atomicAdd(cntU + __ldg(ub + n), 1);
+        atomicAdd(cntV + __ldg(ib + n), 1);
+        atomicAdd(cntV + __ldg(jb + n), 1);
+    }
+}
 
 // One warp per block of up to 32 consecutive triples.  Lane t owns the scalar side of triple t (ids --
 // loaded coalesced or drawn by the fused sampler --, biases, touched flags, bias gradient, loss term);
 // the 32 row gathers run through the whole warp one triple after the other, software-pipelined so the
 // 128-bit gathers of triple t+1 are in flight while triple t is reduced and scattered.
-template <int VW, int NCH, bool L1, bool SAMPLE>
+template <int VW, int NCH, bool L1, bool SAMPLE, bool INPLACE>
 __global__ void __launch_bounds__(256) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
-    SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, StepExtra ex, float* __restrict__ loss_out) {
+    SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, StepExtra ex, float* __restrict__ loss_out,
+    float* msU, float* msV) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -161,13 +201,28 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
         const float bdiff = valid ? __ldg(b + i) - __ldg(b + j) : 0.f;
         const float bi = valid ? __ldg(ex.b_reg + i) : 0.f, bj = valid ? __ldg(ex.b_reg + j) : 0.f;   // regularised bias
         float x_mine = 0.f, s_mine = 0.f;
+        // MODE_COUNT: bit 0/1/2 = the u / i / j row of this triple occurs once in the batch -> updated in place
+        int single = 0;
+        if (INPLACE && valid) single = (int)(ws.cntU[u] == 1) | ((int)(ws.cntV[i] == 1) << 1) | ((int)(ws.cntV[j] == 1) << 2);
+        const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
 
-        TripleRows<VW, NCH> cur, nxt;
+        TripleRows<VW, NCH, INPLACE> cur, nxt;
         cur.load(U, V, __shfl_sync(FULL, u, 0), __shfl_sync(FULL, i, 0), __shfl_sync(FULL, j, 0), d, lane);
+        if (INPLACE && rms) {
+            const int s0 = __shfl_sync(FULL, single, 0);
+            cur.load_slots(msU, msV, __shfl_sync(FULL, u, 0), __shfl_sync(FULL, i, 0), __shfl_sync(FULL, j, 0), s0 & 1, s0 & 2, s0 & 4, d, lane);
+        }
         for (int t = 0; t < cnt; ++t) {
             const int ru = __shfl_sync(FULL, u, t), ri = __shfl_sync(FULL, i, t), rj = __shfl_sync(FULL, j, t);
-            if (t + 1 < cnt)   // next triple's gathers go out before this one's reduction
-                nxt.load(U, V, __shfl_sync(FULL, u, t + 1), __shfl_sync(FULL, i, t + 1), __shfl_sync(FULL, j, t + 1), d, lane);
+            const int sg = INPLACE ? __shfl_sync(FULL, single, t) : 0;
+            if (t + 1 < cnt) {   // next triple's gathers go out before this one's reduction
+                const int nu_ = __shfl_sync(FULL, u, t + 1), ni_ = __shfl_sync(FULL, i, t + 1), nj_ = __shfl_sync(FULL, j, t + 1);
+                nxt.load(U, V, nu_, ni_, nj_, d, lane);
+                if (INPLACE && rms) {
+                    const int s1 = __shfl_sync(FULL, single, t + 1);
+                    nxt.load_slots(msU, msV, nu_, ni_, nj_, s1 & 1, s1 & 2, s1 & 4, d, lane);
+                }
+            }
             float x = 0.f;
 #pragma unroll
             for (int c = 0; c < NCH; ++c)
@@ -197,14 +252,33 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
                         p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], lam_i[c]));                      // gV_i
                         q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], lam_j[c]));                       // gV_j
                     }
-                    a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
+                    if (INPLACE && (sg & 1)) {   // the only occurrence of this row: optimiser update in place
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) opt_update(cfg, a.v[e], cur.u[c].v[e], cur.mu[c].v[e]);
+                        cur.u[c].store(const_cast<float*>(U) + (int64_t)ru * d + off);
+                        if (rms) cur.mu[c].store(msU + (int64_t)ru * d + off);
+                    } else a.red_add(gu + off);
+                    if (INPLACE && (sg & 2)) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) opt_update(cfg, p.v[e], cur.i[c].v[e], cur.mi[c].v[e]);
+                        cur.i[c].store(const_cast<float*>(V) + (int64_t)ri * d + off);
+                        if (rms) cur.mi[c].store(msV + (int64_t)ri * d + off);
+                    } else p.red_add(gi + off);
+                    if (INPLACE && (sg & 4)) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) opt_update(cfg, q.v[e], cur.j[c].v[e], cur.mj[c].v[e]);
+                        cur.j[c].store(const_cast<float*>(V) + (int64_t)rj * d + off);
+                        if (rms) cur.mj[c].store(msV + (int64_t)rj * d + off);
+                    } else q.red_add(gj + off);
                 }
             }
             cur = nxt;
         }
         // lane-parallel scalar tail: lane t finishes triple t
         if (valid) {
-            if (mode == MODE_DENSE) {
+            if (mode == MODE_COUNT) {
+                // the counts are the touched flags
+            } else if (mode == MODE_DENSE) {
                 ws.cntU[u] = 1; ws.tchV[i] = 1.0f; ws.tchV[j] = 1.0f;
             } else {   // first toucher of a row appends it to the step's touched list
                 if (atomicAdd(ws.cntU + u, 1) == 0) ws.listU[atomicAdd(ws.n_touched + 0, 1)] = u;
@@ -244,18 +318,11 @@ __device__ __forceinline__ void apply_row(const tkr_bpr_cfg& cfg, float* __restr
     for (int off = lane * VW; off < d; off += 32 * VW) {
         Vec<VW> g, v, m, z;
         g.load(G + off); v.load(var + off);
-        if (cfg.optimizer == TKR_OPT_RMSPROP) {
-            m.load(ms + off);
+        const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
+        if (rms) m.load(ms + off);
 #pragma unroll
-            for (int t = 0; t < VW; ++t) {
-                m.v[t] = cfg.rms_decay * m.v[t] + (1.0f - cfg.rms_decay) * g.v[t] * g.v[t];   // App. A.4
-                v.v[t] = v.v[t] - cfg.lr * g.v[t] / sqrtf(m.v[t] + cfg.rms_eps);
-            }
-            m.store(ms + off);
-        } else {
-#pragma unroll
-            for (int t = 0; t < VW; ++t) v.v[t] = v.v[t] - cfg.lr * g.v[t];
-        }
+        for (int t = 0; t < VW; ++t) opt_update(cfg, g.v[t], v.v[t], m.v[t]);
+        if (rms) m.store(ms + off);
         v.store(var + off);
 #pragma unroll
         for (int t = 0; t < VW; ++t) z.v[t] = 0.f;
@@ -276,6 +343,31 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int d = cfg.d;
+    if (mode == MODE_COUNT) {
+        // 32 rows per warp step (coalesced count reads); rows that occur once were already updated by the gradient
+        // kernel -- only their bias (items) and the count remain; duplicated rows take the accumulator update.
+        const int64_t nu32 = ((int64_t)cfg.n_users + 31) / 32, ni32 = ((int64_t)cfg.n_items + 31) / 32;
+        for (int64_t w = warp0; w < nu32 + ni32; w += nwarps) {
+            const bool users = w < nu32;
+            const int64_t r = (users ? w : w - nu32) * 32 + lane;
+            const bool in = r < (users ? cfg.n_users : cfg.n_items);
+            int32_t* cnt = users ? ws.cntU : ws.cntV;
+            const int c = in ? cnt[r] : 0;
+            unsigned todo = __ballot_sync(0xffffffffu, c >= 2);
+            if (c != 0) {
+                cnt[r] = 0;
+                if (!users) { apply_row<1>(cfg, b + r, msb + r, ws.Gb + r, 1, 0); if (ex.wq) ex.wq[r] = 0.0f; }
+            }
+            while (todo) {
+                const int l = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t rr = (users ? w : w - nu32) * 32 + l;
+                if (users) apply_row<VW>(cfg, U + rr * d, msU + rr * d, ws.GU + rr * d, d, lane);
+                else apply_row<VW>(cfg, V + rr * d, msV + rr * d, ws.GV + rr * d, ex.item_cols, lane, d);
+            }
+        }
+        return;
+    }
     if (mode == MODE_DENSE) {
         const int64_t total = (int64_t)cfg.n_users + cfg.n_items;
         for (int64_t w = warp0; w < total; w += nwarps) {
@@ -366,26 +458,40 @@ int bpr_pick_mode(const tkr_bpr_cfg* cfg, int64_t B, int data_parallel) {
     return (data_parallel || 3 * B >= ((int64_t)cfg->n_users + cfg->n_items) / 8) ? MODE_DENSE : MODE_LIST;
 }
 
+// MODE_COUNT pays a counting pass and a scan of every row's count; it wins when the state is far beyond L2 (every
+// accumulator access is a DRAM round trip) and most rows of a batch occur once.  Single-GPU tkr_bpr_step only.
+int g_count_mode = -1;   // -1 auto, 0 never, 1 whenever legal (tkr_debug_set_count_mode; tests exercise both paths)
+static int pick_step_mode(const tkr_bpr_cfg* cfg, int64_t B, bool explicit_triples) {
+    const int base = bpr_pick_mode(cfg, B, 0);
+    if (!explicit_triples || cfg->l1 || g_count_mode == 0) return base;
+    if (g_count_mode == 1) return MODE_COUNT;
+    const int64_t rows = (int64_t)cfg->n_users + cfg->n_items;
+    const bool beyond_l2 = rows * cfg->d * 4 * 3 > ((int64_t)384 << 20);
+    return (beyond_l2 && 3 * B <= rows) ? MODE_COUNT : base;
+}
+
 template <int VW, int NCH>
 static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                         const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                        const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st) {
+                        const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st, float* msU, float* msV) {
     // triples per warp: spread small batches over all resident warps, cap at one per lane
     const int64_t max_warps = grid_cap() * 8;
     int64_t tpw64 = (B + max_warps - 1) / max_warps;
     const int tpw = tpw64 > 32 ? 32 : (int)tpw64;
     int64_t blocks = ((B + tpw - 1) / tpw + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-#define TKR_K(L1_, S_) bpr_grad_kernel<VW, NCH, L1_, S_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss)
-    if (cfg->l1) { if (u == nullptr) TKR_K(true, true); else TKR_K(true, false); }
-    else { if (u == nullptr) TKR_K(false, true); else TKR_K(false, false); }
+#define TKR_K(L1_, S_, IP_) bpr_grad_kernel<VW, NCH, L1_, S_, IP_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss, msU, msV)
+    if (mode == MODE_COUNT) TKR_K(false, false, true);   // (bpr_pick_mode only returns it for l2 + explicit triples)
+    else if (cfg->l1) { if (u == nullptr) TKR_K(true, true, false); else TKR_K(true, false, false); }
+    else { if (u == nullptr) TKR_K(false, true, false); else TKR_K(false, false, false); }
 #undef TKR_K
 }
 
 void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                       int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st) {
     const int d = cfg->d;
-    int64_t rows = mode == MODE_DENSE ? (int64_t)cfg->n_users + cfg->n_items
+    int64_t rows = mode == MODE_COUNT ? ((int64_t)cfg->n_users + cfg->n_items) / 32 + 2
+                 : mode == MODE_DENSE ? (int64_t)cfg->n_users + cfg->n_items
                                       : (B < cfg->n_users ? B : cfg->n_users) + (2 * B < cfg->n_items ? 2 * B : cfg->n_items);
     int64_t blocks = (rows + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
@@ -397,14 +503,24 @@ void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
 
 int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const float* b, const int32_t* u,
                       const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
-                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st) {
+                      const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st, float* msU, float* msV) {
     const int d = cfg->d;
+    if (mode == MODE_COUNT) {
+        if (u == nullptr || cfg->l1 || ex.item_cols != d || ex.wq != nullptr || (cfg->optimizer == TKR_OPT_RMSPROP && !(msU && msV))) {
+            set_error("internal: MODE_COUNT needs explicit triples, l2 regularisation, plain BPR rows and the RMSProp slots");
+            return TKR_ERR_INVALID;
+        }
+        int64_t cb = (B + 255) / 256;
+        if (cb > grid_cap()) cb = grid_cap();
+        bpr_count_kernel<<<(unsigned)cb, 256, 0, st>>>(u, i, j, B, ws.cntU, ws.cntV);
+        TKR_LAUNCH_CHECK();
+    }
     const int a = ex.item_cols;
     const int vw = (d % 4 == 0 && a % 4 == 0) ? 4 : (d % 2 == 0 && a % 2 == 0) ? 2 : 1;   // widest vector the row pitch allows
     const int nch = (d + 32 * vw - 1) / (32 * vw);
     if (nch > 8) { set_error("d=%d is too wide for the register-resident gather (max %d)", d, 32 * vw * 8); return TKR_ERR_UNSUPPORTED; }
     const int nchp = nch <= 1 ? 1 : nch <= 2 ? 2 : nch <= 4 ? 4 : 8;
-#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, ex, loss, st)
+#define TKR_GRAD(VW, NCH) launch_grad<VW, NCH>(cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, ex, loss, st, msU, msV)
     if (vw == 4) { if (nchp == 1) TKR_GRAD(4, 1); else if (nchp == 2) TKR_GRAD(4, 2); else if (nchp == 4) TKR_GRAD(4, 4); else TKR_GRAD(4, 8); }
     else if (vw == 2) { if (nchp == 1) TKR_GRAD(2, 1); else if (nchp == 2) TKR_GRAD(2, 2); else if (nchp == 4) TKR_GRAD(2, 4); else TKR_GRAD(2, 8); }
     else { if (nchp == 1) TKR_GRAD(1, 1); else if (nchp == 2) TKR_GRAD(1, 2); else if (nchp == 4) TKR_GRAD(1, 4); else TKR_GRAD(1, 8); }
@@ -420,6 +536,8 @@ size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B) { return ws_layout(cfg, B
 using namespace tkr;
 
 static inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) { return StepExtra{cfg->d, b, nullptr}; }
+
+extern "C" void tkr_debug_set_count_mode(int32_t m) { g_count_mode = m < -1 || m > 1 ? -1 : m; }
 
 extern "C" size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t B) {
     if (cfg == nullptr || B <= 0 || cfg->n_users <= 0 || cfg->n_items <= 0 || cfg->d <= 0) return 0;
@@ -521,7 +639,7 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     StepWs w;
     if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &w)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int mode = bpr_pick_mode(cfg, B, 0);
+    const int mode = pick_step_mode(cfg, B, u != nullptr);
     const StepExtra ex = plain_extra(cfg, b);
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     for (int64_t t = 0; t < n_steps; ++t) {
@@ -529,7 +647,7 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
         const int32_t* it = u ? i + t * B : nullptr;
         const int32_t* jt = u ? j + t * B : nullptr;
         float* lt = loss_out ? loss_out + t : nullptr;
-        if (int rc = bpr_dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, mode, ex, lt, st)) return rc;
+        if (int rc = bpr_dispatch_grad(cfg, U, V, b, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w, mode, ex, lt, st, msU, msV)) return rc;
         bpr_launch_apply(cfg, U, V, b, msU, msV, msb, B, w, mode, ex, st);
         TKR_LAUNCH_CHECK();
     }
