@@ -703,46 +703,80 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
 
 // ------------------------------------------------------------------ refine
 // One warp per user row: exact fp32 fma-chain scores of the <= KPRIME candidates, exact top-k, certificate.
+// The candidate item rows are gathered with coalesced 128-bit loads (one row per warp instruction, RR of them in
+// flight) into a padded shared-memory tile; each lane then runs the ascending-index fma chain of ITS candidate out of
+// shared memory (the chain order is the oracle's definition of a score, so the reduction cannot be split over lanes).
+template <int RR>   // candidates staged per round (16, or 8 for wide rows): 8 warps x RR rows x 3 CTAs per SM must fit
 __global__ void __launch_bounds__(256) score_refine_kernel(const float* __restrict__ U, const float* __restrict__ V, int64_t nu,
                                                            int d, const float* __restrict__ bias, int64_t col_offset,
                                                            const int32_t* __restrict__ cand_idx, const float* __restrict__ cand_score,
                                                            const float* __restrict__ unorm, const unsigned int* __restrict__ vnorm_max,
                                                            const unsigned int* __restrict__ bias_max, const float* __restrict__ tau0,
-                                                           int n_splits, float coef, int k,
+                                                           int n_splits, float coef, int k, int vec,
                                                            int32_t* __restrict__ out_idx, float* __restrict__ out_score,
                                                            int32_t* __restrict__ fail_rows, int32_t* __restrict__ n_fail) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* us = reinterpret_cast<float*>(smem_raw) + (size_t)warp * d;
-    uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + (size_t)8 * d) + (size_t)warp * KPRIME;
+    const int pitch = d + 4;                                              // floats; keeps 16-byte alignment, conflict-free LDS.128
+    float* us = reinterpret_cast<float*>(smem_raw) + (size_t)warp * pitch;
+    uint64_t* keys = reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + (size_t)8 * pitch) + (size_t)warp * KPRIME;
+    float* vs = reinterpret_cast<float*>(reinterpret_cast<uint64_t*>(reinterpret_cast<float*>(smem_raw) + (size_t)8 * pitch) + (size_t)8 * KPRIME)
+                + (size_t)warp * RR * pitch;
     const int64_t row = (int64_t)blockIdx.x * 8 + warp;
     if (row >= nu) return;
     for (int c = lane; c < d; c += 32) us[c] = U[row * d + c];
-    __syncwarp();
-    // each lane scores two candidates; the two fma chains are interleaved (ILP) and V is read 128 bits at a time
+    // candidate e = h * 32 + lane is scored by this lane
     uint64_t mykey[2];
-    const int32_t gc0 = cand_idx[row * KPRIME + lane], gc1 = cand_idx[row * KPRIME + 32 + lane];
-    const float* v0 = V + (gc0 >= 0 ? gc0 - col_offset : 0) * d;
-    const float* v1 = V + (gc1 >= 0 ? gc1 - col_offset : 0) * d;
-    float acc0 = 0.f, acc1 = 0.f;
-    if ((d & 3) == 0 && (((uintptr_t)V) & 15) == 0) {
-        for (int c = 0; c < d; c += 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(v0 + c)), b4 = __ldg(reinterpret_cast<const float4*>(v1 + c));
-            const float u0 = us[c], u1 = us[c + 1], u2 = us[c + 2], u3 = us[c + 3];
-            acc0 = fmaf(u0, a.x, acc0); acc1 = fmaf(u0, b4.x, acc1);     // ascending-index chains = the oracle's definition
-            acc0 = fmaf(u1, a.y, acc0); acc1 = fmaf(u1, b4.y, acc1);
-            acc0 = fmaf(u2, a.z, acc0); acc1 = fmaf(u2, b4.z, acc1);
-            acc0 = fmaf(u3, a.w, acc0); acc1 = fmaf(u3, b4.w, acc1);
+    int32_t gc[2];
+    float acc[2] = {0.f, 0.f};
+    gc[0] = cand_idx[row * KPRIME + lane]; gc[1] = cand_idx[row * KPRIME + 32 + lane];
+    if (vec) {
+        constexpr int ROUNDS = KPRIME / RR;
+        const int nv = d >> 2;                                            // float4 per row
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; ++r) {
+            __syncwarp();
+            // stage candidates [r*RR, r*RR + RR): lanes stride over the float4 of one row at a time
+            const int32_t gsel = ((r * RR) >> 5) ? gc[1] : gc[0];          // (a round never straddles the two halves)
+            for (int c0 = 0; c0 < nv; c0 += 32) {                          // 32 float4 (512 B) of every staged row per pass
+                const int c = c0 + lane;
+                float4 buf[RR];                                            // all RR row loads in flight before the first store
+#pragma unroll
+                for (int e = 0; e < RR; ++e) {
+                    const int32_t g = __shfl_sync(0xffffffffu, gsel, (r * RR + e) & 31);
+                    const float4* src = reinterpret_cast<const float4*>(V + (int64_t)(g >= 0 ? g - col_offset : 0) * d);
+                    if (c < nv) buf[e] = __ldg(src + c);
+                }
+#pragma unroll
+                for (int e = 0; e < RR; ++e)
+                    if (c < nv) reinterpret_cast<float4*>(vs + (size_t)e * pitch)[c] = buf[e];
+            }
+            __syncwarp();
+            // the RR lanes that own this round's candidates run their chains
+            const int h = (r * RR) >> 5, l0 = (r * RR) & 31;
+            if (lane >= l0 && lane < l0 + RR) {
+                const float4* mine = reinterpret_cast<const float4*>(vs + (size_t)(lane - l0) * pitch);
+                float a = 0.f;
+                for (int c = 0; c < nv; ++c) {
+                    const float4 v4 = mine[c];
+                    const float4 u4 = *reinterpret_cast<const float4*>(us + 4 * c);
+                    a = fmaf(u4.x, v4.x, a); a = fmaf(u4.y, v4.y, a); a = fmaf(u4.z, v4.z, a); a = fmaf(u4.w, v4.w, a);   // ascending index
+                }
+                acc[h] = a;
+            }
         }
     } else {
-        for (int c = 0; c < d; ++c) { acc0 = fmaf(us[c], __ldg(v0 + c), acc0); acc1 = fmaf(us[c], __ldg(v1 + c), acc1); }
+        __syncwarp();
+        const float* v0 = V + (int64_t)(gc[0] >= 0 ? gc[0] - col_offset : 0) * d;
+        const float* v1 = V + (int64_t)(gc[1] >= 0 ? gc[1] - col_offset : 0) * d;
+        for (int c = 0; c < d; ++c) { acc[0] = fmaf(us[c], __ldg(v0 + c), acc[0]); acc[1] = fmaf(us[c], __ldg(v1 + c), acc[1]); }
     }
     if (bias != nullptr) {
-        if (gc0 >= 0) acc0 = acc0 + __ldg(bias + (gc0 - col_offset));
-        if (gc1 >= 0) acc1 = acc1 + __ldg(bias + (gc1 - col_offset));
+        if (gc[0] >= 0) acc[0] = acc[0] + __ldg(bias + (gc[0] - col_offset));
+        if (gc[1] >= 0) acc[1] = acc[1] + __ldg(bias + (gc[1] - col_offset));
     }
-    mykey[0] = gc0 >= 0 ? make_key(acc0 + 0.0f, gc0) : 0ull;
-    mykey[1] = gc1 >= 0 ? make_key(acc1 + 0.0f, gc1) : 0ull;
+    mykey[0] = gc[0] >= 0 ? make_key(acc[0] + 0.0f, gc[0]) : 0ull;
+    mykey[1] = gc[1] >= 0 ? make_key(acc[1] + 0.0f, gc[1]) : 0ull;
     keys[lane] = mykey[0];
     keys[32 + lane] = mykey[1];
     __syncwarp();
@@ -956,9 +990,19 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     // |bf16 tensor-core score - exact fma-chain score| <= coef * |u| * |v|: two roundings to 8-bit significands
     // (2^-8 + 2^-18 on every product, Cauchy-Schwarz over the row) + fp32 accumulation slack on both sides.
     const float coef = 0.00390625f * 1.01f + (float)(d + 8) * 9.5367431640625e-7f;
-    const size_t rsmem = (size_t)8 * d * 4 + (size_t)8 * KPRIME * 8;
-    score_refine_kernel<<<(unsigned)((nu + 7) / 8), 256, rsmem, st>>>(U, V, nu, d, bias, col_offset, midx, mscore, unorm, scal + 0, scal + 1,
-                                                                     (const float*)(w + P.o_tau0), P.ns, coef, k, out_idx, out_score, fail, (int32_t*)(scal + 2));
+    {
+        const int vec = (d % 4 == 0 && ((uintptr_t)V % 16) == 0 && ((uintptr_t)U % 16) == 0) ? 1 : 0;
+        const int rr = d <= 128 ? 16 : 8;                                // staged candidates per round
+        const size_t rsmem = (size_t)8 * (d + 4) * 4 + (size_t)8 * KPRIME * 8 + (vec ? (size_t)8 * rr * (d + 4) * 4 : 0);
+#define TKR_REFINE(RR)                                                                                                            \
+        do {                                                                                                                       \
+            TKR_CUDA(cudaFuncSetAttribute(score_refine_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));       \
+            score_refine_kernel<RR><<<(unsigned)((nu + 7) / 8), 256, rsmem, st>>>(U, V, nu, d, bias, col_offset, midx, mscore, unorm, scal + 0, scal + 1, \
+                (const float*)(w + P.o_tau0), P.ns, coef, k, vec, out_idx, out_score, fail, (int32_t*)(scal + 2));                 \
+        } while (0)
+        if (rr == 16) TKR_REFINE(16); else TKR_REFINE(8);
+#undef TKR_REFINE
+    }
     TKR_LAUNCH_CHECK();
     // uncertified rows -> exact engine, driven by the device-side row list (no host round trip)
     if (int rc = launch_exact_rows(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, fail, (const int32_t*)(scal + 2), out_idx, out_score, w + P.o_fb, P.fb_bytes, st)) return rc;
