@@ -9,6 +9,7 @@
  *   tkr_bpr_sample         <- BPR._uniform_user_sampling                    single/bpr.py:155-165
  *   tkr_vbpr_step/_project <- sess.run(..., feed_dict={u,i,j,ic,jc})        single/vbpr.py:114 (graph :29-74, export :124-126)
  *   tkr_score_topk / _host <- np.dot + np.argsort + rated-filter walk       evaluate.py:78,81,96-105
+ *   tkr_eval_hits          <- the hits[] accumulation of the evaluation walk       evaluate.py:84-112
  *   tkr_topk_merge         <- (no reference equivalent: merges item-sharded candidates so the
  *                              sharded result equals the single-process one)
  *
@@ -213,6 +214,27 @@ int tkr_score_topk_host(const float* U_host, int64_t nu, const float* V_host, in
                         const float* bias_host, const int64_t* rated_indptr_host, const int32_t* rated_idx_host,
                         int32_t k, int32_t* out_idx_host, float* out_score_host, void* dev, size_t dev_bytes,
                         void* stream);
+
+/* Hit counting of evaluate.py:84-112 on the device.  lists[*][total] = filtered top-`total` columns per user row
+ * (output of tkr_score_topk*, -1 padded); the test file is given as n_lines entries: line_rows[l] = user row of line l,
+ * likes_idx[likes_indptr[l] .. likes_indptr[l+1]) = its liked test columns, ascending and distinct.
+ * pos_hits[p] (uint64[total], caller-zeroed, accumulated) += number of lines whose p-th kept column is liked;
+ * the reference's hits[q] (q < total/step) is the sum of pos_hits[p] over p < (q+1)*step. */
+int tkr_eval_hits(const int32_t* lists, int32_t total, const int32_t* line_rows, const int64_t* likes_indptr,
+                  const int32_t* likes_idx, int64_t n_lines, unsigned long long* pos_hits, void* stream);
+
+/* ---- the reference's text formats at native speed (host memory; SURVEY 8(f) NEXT-2) ----
+ * .dat (utils.py:28-55, evaluate.py:19-28): rows x cols text matrix, '%f ' per element, one row per line.
+ * tkr_dat_write is byte-identical to the reference writer; tkr_dat_read makes the roundings of np.float32(token). */
+int tkr_dat_shape(const char* path, int64_t* rows, int64_t* cols);
+int tkr_dat_read(const char* path, float* out, int64_t rows, int64_t cols);
+int tkr_dat_write(const char* path, const float* mat, int64_t rows, int64_t cols);
+/* Rating file "uid,iid:like,..." (utils.py:58-89, evaluate.py:30-45) -> flat arrays in file order.  Call once with
+ * line_user == NULL to get *n_lines / *n_pairs, allocate, call again.  line_user[l] / pair_item[p] = row of the id in
+ * uid_path / iid_path (one id per line), -1 when unknown; pair_like[p] = 1 iff the label text is exactly "1";
+ * the pairs of line l are [line_indptr[l], line_indptr[l+1]). */
+int tkr_ratings_parse(const char* ratings_path, const char* uid_path, const char* iid_path, int64_t* n_lines,
+                      int64_t* n_pairs, int32_t* line_user, int64_t* line_indptr, int32_t* pair_item, int8_t* pair_like);
 
 /* Merge n_lists candidate lists idx/score[n_lists][nu][k] (each in the order
  * above, padded with idx -1) into out[nu][k] in the same order. */

@@ -163,6 +163,48 @@ def test_evaluate_lists_match_golden_lists(golden, mini):
             assert np.array_equal(hi, lists[key_prefix + sc]), (model, sc)
 
 
+def test_eval_hits_matches_oracle_walk(golden, mini):
+    """tkr_eval_hits (evaluate.py:84-112 on the device) == the oracle's Python walk over the golden lists"""
+    import importlib.util
+    import utils
+    from conftest import PKG
+    from oracle import evaluate_ref
+    spec = importlib.util.spec_from_file_location("tkr_evaluate", os.path.join(PKG, "evaluate.py"))
+    ev = importlib.util.module_from_spec(spec); spec.loader.exec_module(ev)
+    lists = np.load(os.path.join(golden, "evaluate_mini_lists.npz"))
+    uids = utils.get_id_dict_from_file(os.path.join(mini, "uid"))
+    for key in ("im", "om", "all", "ties_im", "ties_all"):
+        sc = key.split("_")[-1]
+        teids = utils.get_id_dict_from_file(os.path.join(mini, "f0te.%s.idl" % sc))
+        te_file = os.path.join(mini, "f0te.%s.txt" % sc)
+        for step, total in ((5, 30), (1, 30), (7, 28), (10, 20)):
+            L = np.ascontiguousarray(lists[key][:, :total])
+            ref_hits, ref_cnt = evaluate_ref.hits_from_lists(L, uids, teids, te_file, step, total)
+            hits, cnt = ev.count_hits(torch.from_numpy(L).cuda(), os.path.join(mini, "uid"), te_file, os.path.join(mini, "f0te.%s.idl" % sc), step, total)
+            assert cnt == ref_cnt and np.array_equal(hits, ref_hits), (key, step, total)
+
+
+def test_eval_hits_random_large():
+    """synthetic: 50k lines x top-30, ragged like lists (some empty-list rows, -1 padding), vs numpy"""
+    rng = np.random.default_rng(21)
+    n_rows, n_cols, total, n_lines, step = 20000, 5000, 30, 50000, 5
+    lists = np.stack([rng.choice(n_cols, total, replace=False) for _ in range(n_rows)]).astype(np.int32)
+    lists[rng.random(n_rows) < 0.1, 20:] = -1
+    rows = rng.integers(0, n_rows, n_lines).astype(np.int32)
+    cnt = rng.integers(1, 40, n_lines)
+    indptr = np.zeros(n_lines + 1, np.int64); indptr[1:] = np.cumsum(cnt)
+    idx = np.concatenate([np.sort(rng.choice(n_cols, c, replace=False)) for c in cnt]).astype(np.int32)
+    pos = np.zeros(total, np.int64)
+    for l in range(0, n_lines, 1):
+        row = lists[rows[l]]
+        m = np.isin(row, idx[indptr[l]:indptr[l + 1]]) & (row >= 0)
+        pos += m
+    ref = np.array([pos[:(q + 1) * step].sum() for q in range(total // step)], np.float64)
+    hits, ph = topkrec.eval_hits(torch.from_numpy(lists).cuda(), torch.from_numpy(rows).cuda(), torch.from_numpy(indptr).cuda(),
+                                 torch.from_numpy(idx).cuda(), step)
+    assert np.array_equal(ph.cpu().numpy(), pos) and np.array_equal(hits, ref)
+
+
 def test_full_size_property_sharded_equals_whole():
     """C5-like width (1M items, d=128, k=30) on a small user batch: splitting the items into 8 shards and
     merging gives the same bits as the single call; the returned scores are the exact FMA-chain scores;

@@ -93,6 +93,77 @@ def test_loaders_match_reference(golden, mini):
     assert ivt[0] == "1000" and len(ivt) == 160
 
 
+def test_native_loader_matches_reference(golden, mini):
+    """the tkr_ratings_parse route (data_copy=False) builds the same structures as the reference's loader"""
+    g = json.load(open(os.path.join(golden, "loader.json")))
+    m = single.BPR(k=8)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    assert (m.n_users, m.n_items, m.epoch_sample_limit) == (g["n_users"], g["n_items"], g["epoch_sample_limit"])
+    assert m.tr_users == g["tr_users"]
+    assert {str(k): v for k, v in m.tr_data.items()} == g["tr_data"]
+
+
+def test_native_codec_edge_cases(tmp_path):
+    """tkr_dat_write / tkr_dat_read against Python's own '%f' and float(): signed zeros, denormals, huge values,
+    ragged whitespace, exponent notation (the legacy C++ writer's '%10.8e', old/cr/utils.cpp:90-97), empty matrix"""
+    import topkrec
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((257, 19)) * rng.choice([1e-6, 1e-3, 1.0, 1e4, 1e9], (257, 19))).astype(np.float32)
+    x[0, :10] = [0.0, -0.0, 1e-7, -1e-7, 123456.789, 3.4e38, -3.4e38, 1e-45, 0.5000005, 2.5000015]
+    p = str(tmp_path / "x.dat")
+    topkrec.dat_write(p, x)
+    want = "".join("".join("%f " % v for v in row) + "\n" for row in x.astype(np.float64))
+    assert open(p).read() == want
+    back = topkrec.dat_read(p)
+    ref = np.array([[np.float32(t) for t in line.split()] for line in want.splitlines()], np.float32)
+    assert np.array_equal(back.view(np.uint32), ref.view(np.uint32))
+    q = str(tmp_path / "e.dat")
+    open(q, "w").write(" 1.25000000e+00   -3.5e-3 7\n4e2 5.000000 -0.000001")      # no trailing newline on the last row
+    assert np.array_equal(topkrec.dat_read(q), np.array([[1.25, -3.5e-3, 7], [400, 5, -1e-6]], np.float32))
+    open(q, "w").write("1 2 3\n4 5\n")
+    with pytest.raises(topkrec.TkrError):
+        topkrec.dat_read(q)
+    topkrec.dat_write(q, np.zeros((0, 4), np.float32))
+    assert open(q).read() == "" and topkrec.dat_read(q).shape[0] == 0
+    with pytest.raises(topkrec.TkrError):
+        topkrec.dat_read(str(tmp_path / "missing.dat"))
+
+
+def test_native_rating_paths_match_python_routes(mini, tmp_path):
+    """rated_csr_from_files / test_lines_from_files (tkr_ratings_parse + numpy) == the dict-based routes that mirror
+    the reference; incl. a user listed twice (the reference keeps the LAST line), unknown ids and a bare-uid line"""
+    from oracle import evaluate_ref
+    uid_file = os.path.join(mini, "uid")
+    uids = utils.get_id_dict_from_file(uid_file)
+    for sc in ("im", "om", "all"):
+        idl = os.path.join(mini, "f0te.%s.idl" % sc)
+        teids = utils.get_id_dict_from_file(idl)
+        browsed, _ = utils.get_history_from_file(os.path.join(mini, "f0tr.txt"))
+        p0, i0 = utils.rated_csr(uids, browsed, teids)
+        p1, i1 = utils.rated_csr_from_files(uid_file, os.path.join(mini, "f0tr.txt"), idl, len(uids))
+        assert np.array_equal(p0, p1) and np.array_equal(i0, i1)
+        rows, ptr, idx = utils.test_lines_from_files(uid_file, os.path.join(mini, "f0te.%s.txt" % sc), idl)
+        want_rows, want = [], []
+        for line in open(os.path.join(mini, "f0te.%s.txt" % sc)):
+            t = line.strip().split(",")
+            likes = sorted({teids[x.split(":")[0]] for x in t[1:] if int(x.split(":")[1]) == 1})
+            if likes:
+                want_rows.append(uids[t[0]]); want.append(likes)
+        assert rows.tolist() == want_rows and [idx[ptr[l]:ptr[l + 1]].tolist() for l in range(len(want))] == want
+    # synthetic corner cases
+    d = tmp_path
+    (d / "uid").write_text("a\nb\nc\n"); (d / "vid").write_text("x\ny\nz\nw\n")
+    (d / "tr.txt").write_text("a,x:1,y:0\nzz,x:1\nb\nc,w:1,q:1,z:0\na,z:1\n")
+    browsed, _ = utils.get_history_from_file(str(d / "tr.txt"))
+    u = utils.get_id_dict_from_file(str(d / "uid")); v = utils.get_id_dict_from_file(str(d / "vid"))
+    p0, i0 = utils.rated_csr(u, browsed, v)
+    p1, i1 = utils.rated_csr_from_files(str(d / "uid"), str(d / "tr.txt"), str(d / "vid"), 3)
+    assert np.array_equal(p0, p1) and np.array_equal(i0, i1) and i1.tolist() == [2, 2, 3]
+    n, tr_users, tr_data = utils.positives_from_files(str(d / "uid"), str(d / "vid"), str(d / "tr.txt"))
+    data = utils.get_data_from_file(str(d / "tr.txt"), u, v)
+    assert n == len(data) == 3 and tr_users == [0, 2] and tr_data == {0: [0, 2], 2: [3]}
+
+
 def test_host_sampler_replays_reference_stream(golden, mini):
     z = np.load(os.path.join(golden, "sampler.npz"))
     m = single.BPR(k=8)

@@ -5,7 +5,8 @@ domainxz/top-k-rec): same flags, same ``<scenario>,a@5,...`` lines.
 The reference's ``np.dot`` (:78) + ``np.argsort`` (:81) + Python rated-filter walk
 (:96-105) become one fused device call per user batch (``tkr_score_topk``): scores
 never leave the SM, rated items are masked from a CSR, and only the filtered
-top-``total`` columns per user come back.  Hits are then counted on the host.
+top-``total`` columns per user stay on the device, where ``tkr_eval_hits`` counts the hits
+(``evaluate.py:84-112``); only ``total`` counters come back.
 Bias is gathered per test column (the intent of ``old/methods/bpr_test.py:18-32``;
 the shipped ``evaluate.py:80`` broadcast only works when n_te == n_items).
 """
@@ -19,18 +20,18 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
-from utils import get_id_dict_from_file, get_embed_from_file, get_history_from_file, rated_csr  # noqa: E402
+from utils import get_id_dict_from_file, get_embed_from_file, rated_csr_from_files, test_lines_from_files  # noqa: E402
 
 
 def filtered_topk(umat, temat, total, bias, rated_indptr, rated_idx, user_batch=65536):
-    """Per-user filtered top-``total`` test columns via the device engine."""
+    """Per-user filtered top-``total`` test columns via the device engine (device tensor [n_users, total])."""
     import torch
     import topkrec
     dev = torch.device('cuda')
     V = torch.from_numpy(temat).to(dev)
     b = torch.from_numpy(bias).to(dev) if bias is not None else None
     ridx = torch.from_numpy(rated_idx).to(dev)
-    lists = np.empty((umat.shape[0], total), np.int32)
+    lists = torch.empty((umat.shape[0], total), dtype=torch.int32, device=dev)
     ws = None
     for r0 in range(0, umat.shape[0], user_batch):
         r1 = min(umat.shape[0], r0 + user_batch)
@@ -42,27 +43,19 @@ def filtered_topk(umat, temat, total, bias, rated_indptr, rated_idx, user_batch=
             ws = torch.empty(need, dtype=torch.uint8, device=dev)
         # the BF16 item table converted for the first full batch is reused by the following full batches
         idx, _ = topkrec.score_topk(U, V, total, b, rptr, ridx, engine='tc', ws=ws, items_prepared=(r0 > 0 and full))
-        lists[r0:r1] = idx.cpu().numpy()
+        lists[r0:r1] = idx
     return lists
 
 
-def count_hits(lists, uids, teids, te_file, step, total):
-    """``evaluate.py:84-112``: hits@{step, 2*step, ...} over users with >= 1 like."""
-    interval = total // step
-    hits = np.zeros(interval, np.float64)
-    tcount = 0
-    with open(te_file) as f:
-        for line in f:
-            terms = line.strip().split(',')
-            likes = [teids[t.split(':')[0]] for t in terms[1:] if int(t.split(':')[1]) == 1]
-            if not likes:
-                continue
-            row = lists[uids[terms[0]]]
-            pos = np.nonzero(np.isin(row, likes) & (row >= 0))[0]
-            for p in pos:
-                hits[p // step:] += 1
-            tcount += len(set(likes))
-    return hits, tcount
+def count_hits(lists, uid_file, te_file, te_idl_file, step, total):
+    """``evaluate.py:84-112``: hits@{step, 2*step, ...} over test lines with >= 1 like, counted on the device."""
+    import torch
+    import topkrec
+    rows, indptr, idx = test_lines_from_files(uid_file, te_file, te_idl_file)
+    dev = lists.device
+    hits, _ = topkrec.eval_hits(lists, torch.from_numpy(rows).to(dev), torch.from_numpy(indptr).to(dev),
+                                torch.from_numpy(idx).to(dev), step)
+    return hits, int(indptr[-1])
 
 
 def main(argv=None):
@@ -75,21 +68,22 @@ def main(argv=None):
     parser.add_argument('-sl', '--scenarios', nargs='+', default=None, help='The test scenario list')
     args = parser.parse_args(argv)
 
-    uids = get_id_dict_from_file(os.path.join(args.data, 'uid'))
+    uid_file, tr_file = os.path.join(args.data, 'uid'), os.path.join(args.data, 'f%dtr.txt' % args.fold)
+    uids = get_id_dict_from_file(uid_file)
     vids = get_id_dict_from_file(os.path.join(args.data, 'vid'))
-    browsed, _ = get_history_from_file(os.path.join(args.data, 'f%dtr.txt' % args.fold))
     umat = get_embed_from_file(os.path.join(args.model, 'final-U.dat'), uids)
     vmat = get_embed_from_file(os.path.join(args.model, 'final-V.dat'), vids)
     bmat = get_embed_from_file(os.path.join(args.model, 'final-B.dat'), vids)
     lines = []
     for sc in args.scenarios:
-        teids = get_id_dict_from_file(os.path.join(args.data, 'f%dte.%s.idl' % (args.fold, sc)))
+        te_idl = os.path.join(args.data, 'f%dte.%s.idl' % (args.fold, sc))
+        teids = get_id_dict_from_file(te_idl)
         cols = np.fromiter((vids[v] for v in teids), np.int64, count=len(teids))
         temat = np.ascontiguousarray(vmat[cols])
         bias = np.ascontiguousarray(bmat.ravel()[cols]) if bmat is not None else None
-        indptr, idx = rated_csr(uids, browsed, teids)
+        indptr, idx = rated_csr_from_files(uid_file, tr_file, te_idl, len(uids))
         lists = filtered_topk(umat, temat, args.total, bias, indptr, idx)
-        hits, tcount = count_hits(lists, uids, teids, os.path.join(args.data, 'f%dte.%s.txt' % (args.fold, sc)),
+        hits, tcount = count_hits(lists, uid_file, os.path.join(args.data, 'f%dte.%s.txt' % (args.fold, sc)), te_idl,
                                   args.step, args.total)
         lines.append(sc + ''.join(',%.6f' % (h / tcount) for h in hits))
     for line in lines:

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 import topkrec
-from utils import tprint, get_id_dict_from_file, get_data_from_file, positives_csr
+from utils import tprint, get_id_dict_from_file, get_data_from_file, positives_csr, positives_from_files
 
 from .rec import REC
 
@@ -57,12 +57,14 @@ class BPR(REC):
         self.n_users, self.n_items = len(self.uids), len(self.iids)
         assert self.n_users > 0
         assert self.n_items > 0
-        data = get_data_from_file(tr_file, self.uids, self.iids)
-        self.epoch_sample_limit = len(data)
-        self.tr_data = self._data_to_training_dict(data, self.uids, self.iids)
-        self.tr_users = list(self.tr_data.keys())
-        if data_copy:
+        if data_copy:            # the reference keeps the (uid, iid) string pairs on request (bpr.py:66-67)
+            data = get_data_from_file(tr_file, self.uids, self.iids)
+            self.epoch_sample_limit = len(data)
+            self.tr_data = self._data_to_training_dict(data, self.uids, self.iids)
+            self.tr_users = list(self.tr_data.keys())
             self.data = data
+        else:                    # same structures from the native parser (tkr_ratings_parse)
+            self.epoch_sample_limit, self.tr_users, self.tr_data = positives_from_files(uid_file, iid_file, tr_file)
         self._smp = None
         tprint('Loading finished!')
 

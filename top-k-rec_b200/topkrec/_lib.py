@@ -69,8 +69,14 @@ def lib():
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.tkr_eval_hits.argtypes = [vp, i32, vp, vp, vp, i64, vp, vp]
+    L.tkr_dat_shape.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.tkr_dat_read.argtypes = [C.c_char_p, vp, i64, i64]
+    L.tkr_dat_write.argtypes = [C.c_char_p, vp, i64, i64]
+    L.tkr_ratings_parse.argtypes = [C.c_char_p] * 3 + [C.POINTER(C.c_int64)] * 2 + [vp] * 4
     for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
-                 "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge"):
+                 "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
+                 "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
     _lib = L
     return L
@@ -345,3 +351,54 @@ def topk_merge(idx, score, out=None):
         _check(lib().tkr_topk_merge(_dev(idx, torch.int32, "idx"), _dev(score, torch.float32, "score"), n_lists, nu, k,
                                     out[0].data_ptr(), out[1].data_ptr(), _stream()))
     return out
+
+
+def eval_hits(lists, line_rows, likes_indptr, likes_idx, step, pos_hits=None):
+    """Device hit counting (evaluate.py:84-112).  lists: int32 CUDA [n_rows, total]; line_rows int32 [n_lines];
+    likes_indptr int64 [n_lines+1]; likes_idx int32 (ascending, distinct per line).  Returns the reference's
+    cumulative hits[total // step] as float64 numpy (and the uint64 per-position histogram tensor)."""
+    _need_cuda(lists, line_rows, likes_indptr, likes_idx)
+    total = lists.shape[1]
+    n_lines = line_rows.numel()
+    if pos_hits is None:
+        pos_hits = torch.zeros(total, dtype=torch.int64, device=lists.device)
+    if likes_idx.numel() == 0:
+        likes_idx = torch.zeros(1, dtype=torch.int32, device=lists.device)
+    with torch.cuda.device(lists.device):
+        _check(lib().tkr_eval_hits(_dev(lists, torch.int32, "lists"), int(total), _dev(line_rows, torch.int32, "line_rows"),
+                                   _dev(likes_indptr, torch.int64, "likes_indptr"), _dev(likes_idx, torch.int32, "likes_idx"),
+                                   int(n_lines), pos_hits.data_ptr(), _stream()))
+    ph = pos_hits.cpu().numpy().astype(np.float64)
+    interval = total // step
+    return np.array([ph[:(q + 1) * step].sum() for q in range(interval)]), pos_hits
+
+
+# ------------------------------------------------------------------ text codecs (host memory, no GPU needed)
+def dat_read(path):
+    """``.dat`` text matrix -> float32 ndarray (same roundings as ``np.float32(token)``; utils.py:28-44)."""
+    rows, cols = C.c_int64(), C.c_int64()
+    _check(lib().tkr_dat_shape(os.fsencode(path), C.byref(rows), C.byref(cols)))
+    out = np.empty((rows.value, cols.value), np.float32)
+    _check(lib().tkr_dat_read(os.fsencode(path), out.ctypes.data, rows.value, cols.value))
+    return out
+
+
+def dat_write(path, mat):
+    """float32 matrix -> ``.dat`` text, byte-identical to the reference writer (utils.py:47-55)."""
+    mat = np.ascontiguousarray(mat, np.float32)
+    if mat.ndim != 2:
+        raise ValueError("embed must be a matrix, got shape %s" % (mat.shape,))
+    _check(lib().tkr_dat_write(os.fsencode(path), mat.ctypes.data, mat.shape[0], mat.shape[1]))
+
+
+def ratings_parse(ratings_path, uid_path, iid_path):
+    """Rating file -> (line_user int32[L], line_indptr int64[L+1], pair_item int32[P], pair_like int8[P]); ids are rows
+    of the two id files, -1 when unknown (utils.py:58-89, evaluate.py:30-45)."""
+    nl, npair = C.c_int64(), C.c_int64()
+    paths = [os.fsencode(p) for p in (ratings_path, uid_path, iid_path)]
+    _check(lib().tkr_ratings_parse(*paths, C.byref(nl), C.byref(npair), None, None, None, None))
+    line_user = np.empty(nl.value, np.int32); indptr = np.empty(nl.value + 1, np.int64)
+    item = np.empty(npair.value, np.int32); like = np.empty(npair.value, np.int8)
+    _check(lib().tkr_ratings_parse(*paths, C.byref(nl), C.byref(npair), line_user.ctypes.data, indptr.ctypes.data,
+                                   item.ctypes.data, like.ctypes.data))
+    return line_user, indptr, item, like

@@ -42,19 +42,16 @@ def get_iv_dict_from_file(file_path: str) -> dict:
 
 def get_embed_from_file(file_path: str, ids: dict = None):
     """Read a ``.dat`` matrix as fp32 (``utils.py:28-44``).  With ``ids`` the
-    result has ``len(ids)`` rows and row ``ids[x]`` comes from line ``ids[x]``."""
+    result has ``len(ids)`` rows and row ``ids[x]`` comes from line ``ids[x]``.
+    Parsing is the native codec ``tkr_dat_read`` (tokens -> double -> fp32, the
+    same two roundings as ``np.float32(str)``)."""
     if not _is_file(file_path):
         return None
-    with open(file_path) as f:
-        text = f.read()
-    first = text.find('\n')
-    n_col = len(text[:first if first >= 0 else len(text)].split())
-    # tokens -> double -> fp32: the same two roundings as np.float32(str)
-    flat = np.array(text.split(), dtype=np.float64)
-    mat = flat.reshape(-1, n_col).astype(np.float32)
+    import topkrec
+    mat = topkrec.dat_read(file_path)
     if ids is not None:
         rows = np.fromiter(ids.values(), np.int64, count=len(ids))
-        out = np.zeros((len(ids), n_col), np.float32)
+        out = np.zeros((len(ids), mat.shape[1]), np.float32)
         out[rows] = mat[rows]
         return out
     return mat
@@ -62,17 +59,15 @@ def get_embed_from_file(file_path: str, ids: dict = None):
 
 def export_embed_to_file(file_path: str, embed) -> None:
     """Write a ``.dat`` matrix, byte-identical to the reference writer
-    (``utils.py:47-55``): ``'%f '`` per element, newline per row."""
+    (``utils.py:47-55``): ``'%f '`` per element, newline per row (``tkr_dat_write``)."""
     parent = os.path.dirname(file_path)
     if parent and not os.path.isdir(parent):
         os.mkdir(parent)
     embed = np.asarray(embed)
     if embed.ndim != 2:
         raise ValueError('embed must be a matrix, got shape %s' % (embed.shape,))
-    fmt = '%f ' * embed.shape[1] + '\n'
-    rows = embed.astype(np.float64)          # exact: what '%f' % np.float32 formats
-    with open(file_path, 'w') as f:
-        f.writelines(fmt % tuple(r) for r in rows)
+    import topkrec
+    topkrec.dat_write(file_path, embed)
 
 
 def _iter_ratings(file_path):
@@ -135,3 +130,62 @@ def rated_csr(uids: dict, browsed: dict, teids: dict):
     indptr[1:] = np.cumsum([len(x) if x else 0 for x in lists])
     idx = np.fromiter((c for x in lists if x for c in x), np.int32, count=int(indptr[-1]))
     return indptr, idx
+
+
+# ----------------------------------------------------------------------------- native rating-file paths
+def positives_from_files(uid_file: str, iid_file: str, tr_file: str):
+    """The loader of ``bpr.py:51-69`` + ``:167-171`` on the native parser (``tkr_ratings_parse``): returns
+    ``(n_pairs, tr_users, tr_data)`` with ``tr_users`` in first-appearance order and ``tr_data[u]`` the user's
+    positives in file order -- the same structures ``get_data_from_file`` + ``_data_to_training_dict`` build."""
+    import topkrec
+    line_user, indptr, item, like = topkrec.ratings_parse(tr_file, uid_file, iid_file)
+    users = np.repeat(line_user, np.diff(indptr))
+    keep = (users >= 0) & (item >= 0) & (like == 1)
+    u, it = users[keep], item[keep]
+    order = np.argsort(u, kind='stable')                       # groups by user, file order kept inside a group
+    us, its = u[order], it[order]
+    starts = np.flatnonzero(np.r_[True, us[1:] != us[:-1]]) if us.size else np.zeros(0, np.int64)
+    first_pos = order[starts] if us.size else starts           # position of each user's first positive in the file
+    by_first = np.argsort(first_pos, kind='stable')
+    ends = np.r_[starts[1:], us.size]
+    tr_data = {int(us[starts[g]]): its[starts[g]:ends[g]].tolist() for g in by_first}
+    return int(u.size), list(tr_data.keys()), tr_data
+
+
+def rated_csr_from_files(uid_file: str, tr_file: str, te_idl_file: str, n_users: int):
+    """``rated_csr`` straight from the files (``evaluate.py:30-45,66,98``): per user row the ascending test columns
+    of every item on the user's LAST training line (the reference's dict keeps the last occurrence of a uid)."""
+    import topkrec
+    line_user, indptr, col, _ = topkrec.ratings_parse(tr_file, uid_file, te_idl_file)
+    n_lines = line_user.size
+    last = np.full(n_users, -1, np.int64)
+    known = line_user >= 0
+    np.maximum.at(last, line_user[known], np.flatnonzero(known))
+    line_of_pair = np.repeat(np.arange(n_lines), np.diff(indptr))
+    users = np.repeat(line_user, np.diff(indptr))
+    keep = (users >= 0) & (col >= 0)
+    keep[keep] &= last[users[keep]] == line_of_pair[keep]
+    key = np.unique(users[keep].astype(np.int64) * (int(col.max()) + 2 if col.size else 1) + col[keep])
+    mod = int(col.max()) + 2 if col.size else 1
+    rows, cols = key // mod, (key % mod).astype(np.int32)
+    out_ptr = np.zeros(n_users + 1, np.int64)
+    np.cumsum(np.bincount(rows, minlength=n_users), out=out_ptr[1:])
+    return out_ptr, cols
+
+
+def test_lines_from_files(uid_file: str, te_file: str, te_idl_file: str):
+    """The test file as the CSR ``tkr_eval_hits`` takes (``evaluate.py:84-93``): per line with >= 1 like its user row
+    and its distinct liked test columns, ascending."""
+    import topkrec
+    line_user, indptr, col, like = topkrec.ratings_parse(te_file, uid_file, te_idl_file)
+    line_of_pair = np.repeat(np.arange(line_user.size), np.diff(indptr))
+    keep = like == 1
+    if np.any(col[keep] < 0) or np.any(line_user[np.unique(line_of_pair[keep])] < 0):
+        raise KeyError('test file names an id that is not in the id lists')          # the reference raises KeyError too
+    mod = int(col.max()) + 2 if col.size else 1
+    key = np.unique(line_of_pair[keep].astype(np.int64) * mod + col[keep])
+    lines, cols = key // mod, (key % mod).astype(np.int32)
+    ulines, counts = np.unique(lines, return_counts=True)
+    out_ptr = np.zeros(ulines.size + 1, np.int64)
+    np.cumsum(counts, out=out_ptr[1:])
+    return line_user[ulines].astype(np.int32), out_ptr, cols
