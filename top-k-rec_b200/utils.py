@@ -133,6 +133,14 @@ def rated_csr(uids: dict, browsed: dict, teids: dict):
 
 
 # ----------------------------------------------------------------------------- native rating-file paths
+def _sorted_unique(key):
+    """np.unique for int64 keys via sort + neighbour mask (numpy 2.3's hash-based unique is ~20x slower here)."""
+    key = np.sort(key)
+    if key.size == 0:
+        return key
+    return key[np.r_[True, key[1:] != key[:-1]]]
+
+
 def positives_from_files(uid_file: str, iid_file: str, tr_file: str):
     """The loader of ``bpr.py:51-69`` + ``:167-171`` on the native parser (``tkr_ratings_parse``): returns
     ``(n_pairs, tr_users, tr_data)`` with ``tr_users`` in first-appearance order and ``tr_data[u]`` the user's
@@ -160,12 +168,12 @@ def rated_csr_from_files(uid_file: str, tr_file: str, te_idl_file: str, n_users:
     n_lines = line_user.size
     last = np.full(n_users, -1, np.int64)
     known = line_user >= 0
-    np.maximum.at(last, line_user[known], np.flatnonzero(known))
+    last[line_user[known]] = np.flatnonzero(known)                # repeated uid: the later (larger) line index is kept
     line_of_pair = np.repeat(np.arange(n_lines), np.diff(indptr))
     users = np.repeat(line_user, np.diff(indptr))
     keep = (users >= 0) & (col >= 0)
     keep[keep] &= last[users[keep]] == line_of_pair[keep]
-    key = np.unique(users[keep].astype(np.int64) * (int(col.max()) + 2 if col.size else 1) + col[keep])
+    key = _sorted_unique(users[keep].astype(np.int64) * (int(col.max()) + 2 if col.size else 1) + col[keep])
     mod = int(col.max()) + 2 if col.size else 1
     rows, cols = key // mod, (key % mod).astype(np.int32)
     out_ptr = np.zeros(n_users + 1, np.int64)
@@ -183,7 +191,7 @@ def test_lines_from_files(uid_file: str, te_file: str, te_idl_file: str):
     if np.any(col[keep] < 0) or np.any(line_user[np.unique(line_of_pair[keep])] < 0):
         raise KeyError('test file names an id that is not in the id lists')          # the reference raises KeyError too
     mod = int(col.max()) + 2 if col.size else 1
-    key = np.unique(line_of_pair[keep].astype(np.int64) * mod + col[keep])
+    key = _sorted_unique(line_of_pair[keep].astype(np.int64) * mod + col[keep])
     lines, cols = key // mod, (key % mod).astype(np.int32)
     ulines, counts = np.unique(lines, return_counts=True)
     out_ptr = np.zeros(ulines.size + 1, np.int64)
