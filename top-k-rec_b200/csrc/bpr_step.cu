@@ -669,10 +669,37 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
     int32_t* di = (int32_t*)p; p += align_up(n * 4, 256);
     int32_t* dj = (int32_t*)p; p += align_up(n * 4, 256);
     float* dl = (float*)p;
-    TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
-    TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
-    TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
-    if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du, di, dj, B, n_steps, nullptr, 0, dl, ws, ws_bytes, stream)) return rc;
+    if (n_steps == 1) {
+        TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
+        TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
+        TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
+        if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du, di, dj, B, 1, nullptr, 0, dl, ws, ws_bytes, stream)) return rc;
+    } else {
+        // Several steps in one call: the triples of step t+1 travel on a side stream while step t computes
+        // (pinned host memory assumed; pageable memory still works, without the overlap).
+        int dev = 0;
+        TKR_CUDA(cudaGetDevice(&dev));
+        static cudaStream_t copy_stream[64] = {};
+        static cudaEvent_t ready[64] = {}, idle[64] = {};
+        TKR_CHECK_ARG(dev >= 0 && dev < 64, "device ordinal out of range");
+        if (copy_stream[dev] == nullptr) {
+            TKR_CUDA(cudaStreamCreateWithFlags(&copy_stream[dev], cudaStreamNonBlocking));
+            TKR_CUDA(cudaEventCreateWithFlags(&ready[dev], cudaEventDisableTiming));
+            TKR_CUDA(cudaEventCreateWithFlags(&idle[dev], cudaEventDisableTiming));
+        }
+        cudaStream_t cs = copy_stream[dev];
+        TKR_CUDA(cudaEventRecord(idle[dev], st));                 // earlier work on `st` may still read the staging buffer
+        TKR_CUDA(cudaStreamWaitEvent(cs, idle[dev], 0));
+        for (int64_t t = 0; t < n_steps; ++t) {
+            const size_t o = (size_t)t * (size_t)B;
+            TKR_CUDA(cudaMemcpyAsync(du + o, u_host + o, (size_t)B * 4, cudaMemcpyHostToDevice, cs));
+            TKR_CUDA(cudaMemcpyAsync(di + o, i_host + o, (size_t)B * 4, cudaMemcpyHostToDevice, cs));
+            TKR_CUDA(cudaMemcpyAsync(dj + o, j_host + o, (size_t)B * 4, cudaMemcpyHostToDevice, cs));
+            TKR_CUDA(cudaEventRecord(ready[dev], cs));
+            TKR_CUDA(cudaStreamWaitEvent(st, ready[dev], 0));     // (captures this record: one event serves every step)
+            if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du + o, di + o, dj + o, B, 1, nullptr, 0, dl + t, ws, ws_bytes, stream)) return rc;
+        }
+    }
     if (loss_host != nullptr) TKR_CUDA(cudaMemcpyAsync(loss_host, dl, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, st));
     TKR_CUDA(cudaStreamSynchronize(st));
     return TKR_OK;

@@ -24,26 +24,15 @@ from utils import get_id_dict_from_file, get_embed_from_file, rated_csr_from_fil
 
 
 def filtered_topk(umat, temat, total, bias, rated_indptr, rated_idx, user_batch=65536):
-    """Per-user filtered top-``total`` test columns via the device engine (device tensor [n_users, total])."""
+    """Per-user filtered top-``total`` test columns via the device engine (device tensor [n_users, total]); user
+    batches are uploaded on a side stream while the previous batch is scored (``topkrec.score_topk_batches``)."""
     import torch
     import topkrec
     dev = torch.device('cuda')
     V = torch.from_numpy(temat).to(dev)
     b = torch.from_numpy(bias).to(dev) if bias is not None else None
     ridx = torch.from_numpy(rated_idx).to(dev)
-    lists = torch.empty((umat.shape[0], total), dtype=torch.int32, device=dev)
-    ws = None
-    for r0 in range(0, umat.shape[0], user_batch):
-        r1 = min(umat.shape[0], r0 + user_batch)
-        U = torch.from_numpy(umat[r0:r1]).to(dev)
-        rptr = torch.from_numpy(rated_indptr[r0:r1 + 1].copy()).to(dev)
-        full = r1 - r0 == user_batch
-        if ws is None:
-            need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(user_batch, V.shape[0], V.shape[1], total, int(b is not None))
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
-        # the BF16 item table converted for the first full batch is reused by the following full batches
-        idx, _ = topkrec.score_topk(U, V, total, b, rptr, ridx, engine='tc', ws=ws, items_prepared=(r0 > 0 and full))
-        lists[r0:r1] = idx
+    lists, _ = topkrec.score_topk_batches(umat, V, total, b, rated_indptr, ridx, user_batch=user_batch, engine='tc', to_host=False)
     return lists
 
 
