@@ -386,6 +386,39 @@ def bpr_hbm_streaming(dev, n_users=6_000_000, n_items=1_000_000, B=1 << 20, reps
     return out
 
 
+def score_sweep(dev, nb, NI, k, peaks, reps=5):
+    """BASELINE configs[4]: the same step at d = 64 / 256, and at d = 128 with a rated mask of 64 items per user
+    (SURVEY.md 8(d) C5), device-timed with the BF16 item table prepared once."""
+    import torch
+    import topkrec
+    res = []
+    for d, rated in ((64, 0), (256, 0), (128, 64)):
+        g = torch.Generator(device=dev); g.manual_seed(40 + d)
+        V = torch.randn(NI, d, device=dev, generator=g) * 0.1
+        U = torch.randn(nb, d, device=dev, generator=g) * 0.1
+        rp = ri = None
+        if rated:
+            ri = torch.sort(torch.randint(0, NI, (nb, rated), device=dev, generator=g, dtype=torch.int32), dim=1).values.reshape(-1).contiguous()
+            rp = torch.arange(0, (nb + 1) * rated, rated, device=dev, dtype=torch.int64)
+        ws = torch.empty(topkrec.lib().tkr_score_topk_tc_workspace_bytes(nb, NI, d, k, 0), dtype=torch.uint8, device=dev)
+        nfb = torch.zeros(1, dtype=torch.int32, device=dev)
+        for t in range(3):
+            topkrec.score_topk(U, V, k, None, rp, ri, engine="tc", ws=ws, items_prepared=t > 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for t in range(reps):
+            topkrec.score_topk(U, V, k, None, rp, ri, engine="tc", ws=ws, items_prepared=True, n_fallback=nfb)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = 2.0 * nb * NI * d / (ms / 1e3) / 1e12
+        res.append({"d": d, "rated_per_user": rated, "ms_per_step": ms, "users_per_sec": nb / (ms / 1e3), "tflops": tf,
+                    "roofline_frac": tf / peaks["bf16_tflops"], "rows_redone_by_exact_fallback": int(nfb.item())})
+        del V, U, ws
+        torch.cuda.empty_cache()
+    return res
+
+
 def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src):
     """score + top-30: 1M items (sharded over the ranks), d=128, user batches of --score-users."""
     import torch
@@ -440,6 +473,8 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
                         "frac": flops / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
                         "note": "per GPU: FLOP = 2*nu*(ni/world)*d over the whole step (convert + filter + merge + refine + fallback [+ all-gather]), against the burst bf16 peak"},
            "scaling": "strong (fixed user batch and item table; item columns sharded over the GPUs)"}
+    if world == 1 and not args.skip_sweep and eng == "tc":
+        out["sweep"] = score_sweep(dev, nb, NI, k, peaks)
     if world == 1:
         # e2e: the evaluator's flow through the public API (topkrec.score_topk_batches): host V copied once per pass,
         # K host user batches uploaded / K list batches downloaded on side streams while the neighbours compute
@@ -447,15 +482,17 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
         Ke = max(K, 16)       # user batches per pass of the item table (a real evaluation has n_users / 18944 of them)
         Uh = torch.cat([Ub[t % 4] for t in range(Ke)]).cpu().pin_memory()
         Vd = torch.empty_like(V)
-        topkrec.score_topk_batches(Uh[:2 * nb], V, k, user_batch=nb, engine=eng)          # warm-up
+        scorer = topkrec.BatchScorer(Vfull_rows, D, k, nb, engine=eng, device=dev)     # streams, double buffers, workspace
+        oi = (torch.empty((Ke * nb, k), dtype=torch.int32).pin_memory(), torch.empty((Ke * nb, k), dtype=torch.float32).pin_memory())
+        scorer.run(Uh[:2 * nb], V, out=(oi[0][:2 * nb], oi[1][:2 * nb]))                      # warm-up
         barrier()
         t0 = time.perf_counter()
         Vd.copy_(Vh, non_blocking=True)
-        oi, os_ = topkrec.score_topk_batches(Uh, Vd, k, user_batch=nb, engine=eng)       # synchronises before returning
+        scorer.run(Uh, Vd, out=oi)                                                           # synchronises before returning
         dt = time.perf_counter() - t0
         out["e2e"] = {"value": nb * Ke / dt, "unit": "users/s", "h2d_bytes_per_step": nb * D * 4 + Vfull_rows * D * 4 // Ke,
                       "d2h_bytes_per_step": nb * k * 8,
-                      "api": "topkrec.score_topk_batches (evaluate.py flow): V copied once per pass of %d batches, U batches up / lists down "
+                      "api": "topkrec.BatchScorer (evaluate.py flow): V copied once per pass of %d batches, U batches up / lists down "
                              "on side streams" % Ke}
         if rank == 0 and not args.skip_cpu:
             from oracle import topk_ref

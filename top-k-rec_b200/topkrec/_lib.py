@@ -341,67 +341,85 @@ def score_topk_host(U, V, k, bias=None, rated_indptr=None, rated_idx=None, dev=N
     return out_idx, out_score
 
 
-def score_topk_batches(umat, V, k, bias=None, rated_indptr=None, rated_idx=None, user_batch=18944, engine="tc", to_host=True):
-    """The evaluator's loop (evaluate.py:75-81 over all users) with the PCIe traffic hidden: ``umat`` is a HOST float32
-    matrix (numpy or a pinned torch tensor), scored ``user_batch`` rows at a time against the device item table ``V``;
-    the upload of batch t+1 and the download of the lists of batch t-1 run on side streams while batch t computes.
-    rated_indptr: host int64 [n_users+1] (numpy) over the device CSR ``rated_idx``.  Returns (idx, score) for all
-    users -- pinned host tensors when ``to_host`` else device tensors."""
-    _need_cuda(V)
-    dev = V.device
-    U_h = umat if isinstance(umat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(umat, np.float32))
-    if not U_h.is_pinned():
-        U_h = U_h.pin_memory()
-    n, d = U_h.shape
-    nb = min(int(user_batch), n)
-    f32, i32 = torch.float32, torch.int32
-    out_i = (torch.empty((n, k), dtype=i32).pin_memory(), torch.empty((n, k), dtype=f32).pin_memory()) if to_host else \
-            (torch.empty((n, k), dtype=i32, device=dev), torch.empty((n, k), dtype=f32, device=dev))
-    need = (lib().tkr_score_topk_tc_workspace_bytes(nb, V.shape[0], d, k, int(bias is not None)) if engine == "tc"
-            else lib().tkr_score_topk_workspace_bytes(nb, V.shape[0], d, k))
-    ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
-    main = torch.cuda.current_stream(dev)
-    up, down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    Ud = [torch.empty((nb, d), dtype=f32, device=dev) for _ in range(2)]
-    gi = [torch.empty((nb, k), dtype=i32, device=dev) for _ in range(2)]
-    gs = [torch.empty((nb, k), dtype=f32, device=dev) for _ in range(2)]
-    rp_d = [torch.empty(nb + 1, dtype=torch.int64, device=dev) for _ in range(2)] if rated_indptr is not None else None
-    rp_h = torch.from_numpy(np.ascontiguousarray(rated_indptr, np.int64)).pin_memory() if rated_indptr is not None else None
-    ev_up = [torch.cuda.Event() for _ in range(2)]; ev_free = [torch.cuda.Event() for _ in range(2)]
-    ev_out = [torch.cuda.Event() for _ in range(2)]; ev_down = [torch.cuda.Event() for _ in range(2)]
-    starts = list(range(0, n, nb))
+class BatchScorer:
+    """The evaluator's loop (evaluate.py:75-81 over all users) with the PCIe traffic hidden: a HOST float32 user matrix
+    is scored ``user_batch`` rows at a time against a device item table; the upload of batch t+1 and the download of
+    the lists of batch t-1 run on side streams while batch t computes.  Holds the streams, the double buffers and the
+    engine workspace, so it can be reused across passes (same shapes)."""
 
-    def upload(t):
-        r0 = starts[t]; r1 = min(n, r0 + nb); s = t & 1
-        with torch.cuda.stream(up):
+    def __init__(self, n_items, d, k, user_batch=18944, has_bias=False, rated=False, engine="tc", device="cuda"):
+        _need_cuda()
+        self.dev = dev = torch.device(device)
+        self.ni, self.d, self.k, self.nb, self.engine, self.has_bias = int(n_items), int(d), int(k), int(user_batch), engine, bool(has_bias)
+        f32, i32 = torch.float32, torch.int32
+        need = (lib().tkr_score_topk_tc_workspace_bytes(self.nb, self.ni, self.d, self.k, int(self.has_bias)) if engine == "tc"
+                else lib().tkr_score_topk_workspace_bytes(self.nb, self.ni, self.d, self.k))
+        self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        self.up, self.down = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.Ud = [torch.empty((self.nb, d), dtype=f32, device=dev) for _ in range(2)]
+        self.gi = [torch.empty((self.nb, k), dtype=i32, device=dev) for _ in range(2)]
+        self.gs = [torch.empty((self.nb, k), dtype=f32, device=dev) for _ in range(2)]
+        self.rp = [torch.empty(self.nb + 1, dtype=torch.int64, device=dev) for _ in range(2)] if rated else None
+        self.ev = [[torch.cuda.Event() for _ in range(2)] for _ in range(4)]      # up, free, out, down
+        self._prepared_for = None
+
+    def run(self, umat, V, bias=None, rated_indptr=None, rated_idx=None, out=None, to_host=True):
+        """umat: host float32 [n, d] (numpy or torch; pinned for real overlap).  rated_indptr: host int64 [n+1] over the
+        device CSR ``rated_idx``.  Returns (idx, score) for all users: pinned host tensors when ``to_host`` (or the
+        preallocated ``out``), else device tensors."""
+        _need_cuda(V)
+        dev, nb, k = self.dev, self.nb, self.k
+        U_h = umat if isinstance(umat, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(umat, np.float32))
+        n = U_h.shape[0]
+        if U_h.shape[1] != self.d or V.shape != (self.ni, self.d) or (bias is not None) != self.has_bias or (rated_indptr is not None) != (self.rp is not None):
+            raise ValueError("BatchScorer was built for other shapes / options")
+        if out is None:
+            out = ((torch.empty((n, k), dtype=torch.int32).pin_memory(), torch.empty((n, k), dtype=torch.float32).pin_memory()) if to_host
+                   else (torch.empty((n, k), dtype=torch.int32, device=dev), torch.empty((n, k), dtype=torch.float32, device=dev)))
+        rp_h = torch.from_numpy(np.ascontiguousarray(rated_indptr, np.int64)) if rated_indptr is not None else None
+        main = torch.cuda.current_stream(dev)
+        up, down = self.up, self.down
+        ev_up, ev_free, ev_out, ev_down = self.ev
+        starts = list(range(0, n, nb))
+
+        def upload(t):
+            r0 = starts[t]; r1 = min(n, r0 + nb); s = t & 1
+            with torch.cuda.stream(up):
+                if t >= 2:
+                    up.wait_event(ev_free[s])              # batch t-2 no longer reads this slot
+                self.Ud[s][:r1 - r0].copy_(U_h[r0:r1], non_blocking=True)
+                if rp_h is not None:
+                    self.rp[s][:r1 - r0 + 1].copy_(rp_h[r0:r1 + 1], non_blocking=True)
+                ev_up[s].record(up)
+
+        up.wait_stream(main); down.wait_stream(main)
+        if starts:
+            upload(0)
+        for t, r0 in enumerate(starts):
+            r1 = min(n, r0 + nb); m = r1 - r0; s = t & 1
+            if t + 1 < len(starts):
+                upload(t + 1)
+            main.wait_event(ev_up[s])
             if t >= 2:
-                up.wait_event(ev_free[s])                  # batch t-2 no longer reads this slot
-            Ud[s][:r1 - r0].copy_(U_h[r0:r1], non_blocking=True)
-            if rp_d is not None:
-                rp_d[s][:r1 - r0 + 1].copy_(rp_h[r0:r1 + 1], non_blocking=True)
-            ev_up[s].record(up)
+                main.wait_event(ev_down[s])                # the lists of batch t-2 have left this slot
+            score_topk(self.Ud[s][:m], V, k, bias, self.rp[s][:m + 1] if self.rp is not None else None, rated_idx, engine=self.engine,
+                       ws=self.ws, out=(self.gi[s][:m], self.gs[s][:m]), items_prepared=(self.engine == "tc" and t > 0 and m == nb))
+            ev_free[s].record(main); ev_out[s].record(main)
+            with torch.cuda.stream(down):
+                down.wait_event(ev_out[s])
+                out[0][r0:r1].copy_(self.gi[s][:m], non_blocking=True)
+                out[1][r0:r1].copy_(self.gs[s][:m], non_blocking=True)
+                ev_down[s].record(down)
+        main.wait_stream(down); main.wait_stream(up)
+        main.synchronize()
+        return out
 
-    up.wait_stream(main)
-    if starts:
-        upload(0)
-    for t, r0 in enumerate(starts):
-        r1 = min(n, r0 + nb); m = r1 - r0; s = t & 1
-        if t + 1 < len(starts):
-            upload(t + 1)
-        main.wait_event(ev_up[s])
-        if t >= 2:
-            main.wait_event(ev_down[s])                    # the lists of batch t-2 have left this slot
-        score_topk(Ud[s][:m], V, k, bias, rp_d[s][:m + 1] if rp_d is not None else None, rated_idx, engine=engine, ws=ws,
-                   out=(gi[s][:m], gs[s][:m]), items_prepared=(engine == "tc" and t > 0 and m == nb))
-        ev_free[s].record(main); ev_out[s].record(main)
-        with torch.cuda.stream(down):
-            down.wait_event(ev_out[s])
-            out_i[0][r0:r1].copy_(gi[s][:m], non_blocking=True)
-            out_i[1][r0:r1].copy_(gs[s][:m], non_blocking=True)
-            ev_down[s].record(down)
-    main.wait_stream(down)
-    main.synchronize()
-    return out_i
+
+def score_topk_batches(umat, V, k, bias=None, rated_indptr=None, rated_idx=None, user_batch=18944, engine="tc", to_host=True):
+    """One pass of ``BatchScorer`` (built for this call)."""
+    n = umat.shape[0]
+    sc = BatchScorer(V.shape[0], V.shape[1], k, min(int(user_batch), n), bias is not None, rated_indptr is not None, engine, V.device)
+    return sc.run(umat, V, bias, rated_indptr, rated_idx, to_host=to_host)
 
 
 def topk_merge(idx, score, out=None):
