@@ -337,23 +337,52 @@ __device__ __forceinline__ void seed_chunk(const uint32_t (&v)[32], float& s1, f
     s4 = fmaxf(s4, a);
 }
 
-// Selection warp: sort the row buffer (n <= CAP keys, global memory) in registers and keep the best KPRIME in place.
-// `key` holds the sorted keys of elements r*32+lane afterwards.
-__device__ __forceinline__ void sel_sort(uint64_t* buf, int n, int lane, uint64_t (&key)[4]) {
+// Rated filter of one row's candidates (evaluate.py:98 `if liid not in rated[uid]`): a candidate whose global column
+// is in the row's rated CSR slice [lo, hi) is erased (key 0 sorts last).  Done here, on whole buffers -- 4 keys per lane,
+// their binary searches in lockstep so the dependent loads overlap -- instead of per candidate on the selection
+// warps' critical path; the buffer may therefore hold rated columns between two compactions.
+__device__ __forceinline__ void erase_rated(uint64_t (&key)[4], const int32_t* __restrict__ rated_idx, long long lo0, long long hi0) {
+    const int n = (int)(hi0 - lo0);
+    if (n <= 0) return;
+    const int32_t* rl = rated_idx + lo0;
+    int lo[4], hi[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { lo[r] = 0; hi[r] = key[r] ? n : 0; }
+    while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (lo[r] < hi[r]) {
+                const int mid = (lo[r] + hi[r]) >> 1;
+                if (__ldg(rl + mid) < (int32_t)(uint32_t)key[r]) lo[r] = mid + 1; else hi[r] = mid;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (key[r] && lo[r] < n && __ldg(rl + lo[r]) == (int32_t)(uint32_t)key[r]) key[r] = 0ull;
+}
+
+// Selection warp: sort the row buffer (n <= CAP keys, global memory) in registers, rated columns erased first, and keep
+// the best KPRIME in place.  `key` holds the sorted keys of elements r*32+lane afterwards.
+__device__ __forceinline__ void sel_sort(uint64_t* buf, int n, int lane, uint64_t (&key)[4], const int32_t* rated_idx, long long rlo, long long rhi) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int e = r * 32 + lane;
         key[r] = e < n ? __ldcg(buf + e) : 0ull;
     }
+    if (rated_idx != nullptr) erase_rated(key, rated_idx, rlo, rhi);
     warp_sort128_desc(key, lane);
     buf[lane] = key[0];
     buf[32 + lane] = key[1];
     __syncwarp();
 }
-// Out of line (one copy of the 1100-instruction sort): returns the KPRIME-th score (or -inf) to every lane.
-__device__ __noinline__ float sel_compact(uint64_t* buf, int n, int lane) {
+// Out of line (one copy of the 1100-instruction sort): returns the KPRIME-th score (or -inf) to every lane and the
+// number of candidates kept (<= KPRIME) through *kept.
+__device__ __noinline__ float sel_compact(uint64_t* buf, int n, int lane, const int32_t* rated_idx, long long rlo, long long rhi, int* kept) {
     uint64_t key[4];
-    sel_sort(buf, n, lane, key);
+    sel_sort(buf, n, lane, key, rated_idx, rlo, rhi);
+    const unsigned live = __ballot_sync(0xffffffffu, key[0] != 0ull), live1 = __ballot_sync(0xffffffffu, key[1] != 0ull);
+    *kept = __popc(live) + __popc(live1);
     const uint64_t last = __shfl_sync(0xffffffffu, key[1], 31);
     return last ? ord_to_f32((uint32_t)(last >> 32)) : -INFINITY;
 }
@@ -634,17 +663,15 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
                     hb[j] = __shfl_sync(0xffffffffu, h, (b0 + j) & 31);
                     x[j] = __int_as_float(sh_ld_volatile(ring + 128u * (uint32_t)((tail + b0 + j) & (NBLK - 1)) + 4u * (uint32_t)lane));
                 }
+                bool pass[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float tr = __shfl_sync(0xffffffffu, tau_reg, (int)(hb[j] >> COL_BITS));   // shfl takes the row index mod 32
                     const uint32_t crel = (hb[j] & ((1u << COL_BITS) - 1u)) + (uint32_t)lane;       // sweep-relative column
-                    bool pass = b0 + j < n && crel < ni_rel && x[j] >= tr;
-                    if (has_rated) {                                           // (warp-uniform)
-                        const int row = q * 32 + (int)((hb[j] >> COL_BITS) & 31u);
-                        if (pass) pass = !rated_has(rated_idx, rlo_sh[row], rhi_sh[row], gc_base + (int32_t)crel);
-                    }
-                    bal[j] = __ballot_sync(0xffffffffu, pass);
+                    pass[j] = b0 + j < n && crel < ni_rel && x[j] >= tr;
                 }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bal[j] = __ballot_sync(0xffffffffu, pass[j]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (bal[j] == 0u) continue;                                // (also skips the blocks past n)
@@ -654,8 +681,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
                     if (cnt + __popc(bal[j]) > CAP) {                          // would overflow: keep the best KPRIME first
                         const long long k0 = tick<DBG>();
                         __syncwarp();
-                        const float nt = sel_compact(buf, cnt, lane);
-                        cnt = cnt < KPRIME ? cnt : KPRIME;
+                        const int row = q * 32 + rq;
+                        const float nt = sel_compact(buf, cnt, lane, has_rated ? rated_idx : nullptr, rlo_sh[row], rhi_sh[row], &cnt);
                         const float tr = fmaxf(__shfl_sync(0xffffffffu, tau_reg, rq), nt);
                         if (lane == rq) { tau_reg = tr; sh_st_volatile_u32(tau_a + 4u * (uint32_t)rq, __float_as_uint(tr)); }
                         bal[j] = __ballot_sync(0xffffffffu, ((bal[j] >> lane) & 1u) != 0u && x[j] >= tr);
@@ -680,7 +707,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             const int64_t grow = row0 + row;
             if (grow >= p.nu) break;
             const int cn = __shfl_sync(0xffffffffu, cnt_reg, r);
-            sel_sort(bufq + (size_t)r * CAP, cn < CAP ? cn : CAP, lane, skey);
+            sel_sort(bufq + (size_t)r * CAP, cn < CAP ? cn : CAP, lane, skey, has_rated ? rated_idx : nullptr, rlo_sh[row], rhi_sh[row]);
             const int64_t o = ((int64_t)split * p.nu + grow) * KPRIME;
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
