@@ -60,6 +60,48 @@ def test_score_topk_bit_exact_shapes(nu, ni, d, k):
         assert fb["tc"] <= nu // 50, "tensor-core filter should certify nearly every row on generic data (%d fell back)" % fb["tc"]
 
 
+@pytest.mark.parametrize("nu,ni,d,bias,rated", [
+    (300, 70000, 128, False, 0),      # 274 tiles: seeded sweep (22 seed tiles spread with stride 12), second CTA pair half empty
+    (700, 131072 + 77, 150, True, 50),   # d + 3 = 153 -> three K chunks, padded to four; ragged last tile; bias columns; mask
+    (260, 200000, 64, False, 300),    # one K chunk per tile (8-stage ring), long rated lists (filtered at compaction)
+    (40, 300000, 250, True, 0),       # few users: item splits over the chip (clusters along y), d + 3 = 253
+    (513, 66000, 96, False, 20),      # 5 CTA pairs, seeded, two K chunks with a half-empty second one
+])
+def test_score_topk_tc_pipeline_shapes(nu, ni, d, bias, rated):
+    """shapes that exercise the CTA-pair filter's corner paths (tensor-core engine only: the exact engine on these
+    sizes is slow and is itself pinned by the small cases); the oracle is the reference of both"""
+    U, V, b, p, i = _case(nu, ni, d, 30, seed=nu + d, bias=bias, rated=rated)
+    fb = _check(U, V, 30, b, p, i, engines=("tc",))
+    assert fb["tc"] <= max(2, nu // 50), "%d rows fell back to the exact engine" % fb["tc"]
+
+
+def test_score_topk_tc_biased_item_order():
+    """items sorted by norm (the best ones first): the seed tiles are spread over the sweep, so the seed threshold is
+    an unbiased sample and the rows still certify"""
+    rng = np.random.default_rng(31)
+    nu, ni, d = 256, 80000, 128
+    U = (0.1 * rng.standard_normal((nu, d))).astype(np.float32)
+    V = (0.1 * rng.standard_normal((ni, d))).astype(np.float32)
+    V *= np.linspace(3.0, 0.3, ni, dtype=np.float32)[:, None]
+    fb = _check(U, V, 30, None, None, None, engines=("tc",))
+    assert fb["tc"] <= 8
+
+
+def test_score_topk_mostly_rated_top():
+    """every user has rated nearly all of its best columns: the candidate buffers fill with rated columns between
+    compactions and the filter must still deliver the first 30 unrated ones"""
+    rng = np.random.default_rng(32)
+    nu, ni, d, k = 200, 30000, 64, 30
+    U = (0.1 * rng.standard_normal((nu, d))).astype(np.float32)
+    V = (0.1 * rng.standard_normal((ni, d))).astype(np.float32)
+    S = U @ V.T
+    top = np.argsort(-S, axis=1)[:, :400]
+    rated = [np.sort(rng.choice(top[r], 380, replace=False)) for r in range(nu)]
+    indptr = np.zeros(nu + 1, np.int64); indptr[1:] = np.cumsum([len(x) for x in rated])
+    idx = np.concatenate(rated).astype(np.int32)
+    _check(U, V, k, None, indptr, idx)
+
+
 @pytest.mark.parametrize("k", [5, 10, 15, 20, 25, 30])
 def test_score_topk_reference_cutoffs(k):
     """the reference's k in {5,...,30} (evaluate.py -s 5 -t 30)"""
