@@ -211,6 +211,8 @@ def run_ours(args, rank, local_rank, world):
     st = {k: torch.from_numpy(v).to(dev) for k, v in init_state_np(N_USERS, N_ITEMS, D).items()}
     cfg = topkrec.BprCfg(N_USERS, N_ITEMS, D)
     engine = tdist.DataParallelBpr(cfg, st, B)
+    if not args.no_hot_items:   # the items with the most positives get their gradients summed per thread block in shared memory
+        topkrec.bpr_set_hot_items(cfg, B, engine.ws, topkrec.popular_items(pos_idx, N_ITEMS))
     POOL = 16                                   # distinct batches cycled through: 16 * 12 B * B = 201 MB > L2
     pool = [topkrec.bpr_sample(smp, (rank * POOL + p) * B, B, dev) for p in range(POOL)]
     loss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -327,6 +329,7 @@ def bpr_sweep(cfg, st, smp, dev):
     out = []
     for B, fused, n_steps, reps in ((256, False, 512, 3), (256, True, 512, 3), (1 << 16, False, 16, 5), (1 << 20, True, 1, 10)):
         ws = topkrec.bpr_workspace(cfg, B, dev)
+        topkrec.bpr_set_hot_items(cfg, B, ws, topkrec.popular_items(smp.pos_idx, N_ITEMS))
         loss = torch.zeros(n_steps, dtype=torch.float32, device=dev)
         trip = (None, None, None) if fused else topkrec.bpr_sample(smp, 7 << 32, B * n_steps, dev)
 
@@ -517,6 +520,7 @@ def main():
     ap.add_argument("--score-engine", default="tc", choices=["tc", "exact"])
     ap.add_argument("--score-items", type=int, default=1 << 20)
     ap.add_argument("--score-steps", type=int, default=5)
+    ap.add_argument("--no-hot-items", action="store_true", help="do not privatise the most popular item rows (tkr_bpr_workspace_set_hot_items)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-score", action="store_true")
     ap.add_argument("--skip-sweep", action="store_true")

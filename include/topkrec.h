@@ -79,6 +79,12 @@ typedef struct tkr_sampler {
  * first step (tkr_bpr_workspace_init); every step leaves it zeroed again. */
 size_t tkr_bpr_workspace_bytes(const tkr_bpr_cfg* cfg, int64_t batch);
 int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes, void* stream);
+/* Optional: name up to TKR_MAX_HOT popular item rows (HOST array of distinct item ids, e.g. the items with the most
+ * positives).  The gradient kernel then sums their gradients in shared memory per thread block and adds each block's
+ * sum once, instead of one L2 atomic per occurrence -- popular items otherwise serialise on one L2 slice.  Results are
+ * the same sums in another order.  n = 0 clears the set. */
+int tkr_bpr_workspace_set_hot_items(const tkr_bpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes,
+                                    const int32_t* item_ids_host, int32_t n, void* stream);
 
 /* Byte offsets of the workspace regions, for callers that exchange gradients
  * between devices (data-parallel training): offsets[TKR_WS_*]. The fp32 region
@@ -92,8 +98,10 @@ int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t batch, void* ws, size
 #define TKR_WS_TCHV 6
 #define TKR_WS_CNTV 7
 #define TKR_WS_LISTV 8
-#define TKR_WS_TOTAL 9
-#define TKR_WS_NFIELDS 10
+#define TKR_WS_HOTV 9      /* int32 hot_slot[n_items] (0 = cold, s+1 = privatised slot s) then int32 hot_ids[TKR_MAX_HOT] */
+#define TKR_WS_TOTAL 10
+#define TKR_WS_NFIELDS 11
+#define TKR_MAX_HOT 32
 int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t batch, int64_t* offsets);
 
 /* The two halves of a step, for data-parallel training: users are

@@ -58,7 +58,7 @@ def _assert_ws_clean(cfg, B, ws):
     lay = topkrec.bpr_workspace_layout(cfg, B)
     order = sorted(lay.items(), key=lambda kv: kv[1])
     for (name, beg), (_, end) in zip(order[:-1], order[1:]):
-        if name not in ("listU", "listV"):
+        if name not in ("listU", "listV", "hotV"):
             assert int(ws[beg:end].count_nonzero().item()) == 0, "workspace region %s is not zero after the step" % name
 
 
@@ -136,6 +136,42 @@ def test_bpr_step_count_mode_equals_accumulator_path():
     L.tkr_debug_set_count_mode(-1)
     for name in outs[0]:
         assert _rel(outs[1][name], outs[0][name]) <= 1e-6, name
+
+
+@pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 40), (5000, 1000, 128, 1 << 15, 4), (7, 5, 128, 512, 8), (900, 700, 256, 4096, 5),
+                                   (400, 300, 33, 64, 10)])
+def test_bpr_step_hot_items_match_oracle(shape):
+    """popular item rows privatised per thread block in shared memory: same sums, same parity bar"""
+    nu, ni, d, B, steps = shape
+    rng = np.random.default_rng(17 + d)
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    st["b"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    n = B * steps
+    p = 1.0 / np.arange(1, ni + 1); p /= p.sum()
+    perm = rng.permutation(ni)                                   # popular items are not the low ids
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = perm[rng.choice(ni, n, p=p)].astype(np.int32)
+    j = rng.integers(0, ni, n).astype(np.int32)
+    ocfg = bpr_ref.BprCfg(lambda_b=0.01)
+    dst = _to_dev(st)
+    cfg = topkrec.BprCfg(nu, ni, d, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lr, ocfg.mode, ocfg.optimizer)
+    ws = topkrec.bpr_workspace(cfg, B)
+    hot = topkrec.popular_items(i, ni)
+    assert 0 < hot.size <= topkrec.MAX_HOT
+    topkrec.bpr_set_hot_items(cfg, B, ws, hot)
+    loss = torch.empty(steps, dtype=torch.float32, device="cuda")
+    topkrec.bpr_step(cfg, dst["U"], dst["V"], dst["b"], dst["msU"], dst["msV"], dst["msb"],
+                     torch.from_numpy(u).cuda(), torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, ws, loss)
+    ref_loss = bpr_ref.bpr_train(st, u, i, j, B, ocfg)
+    for name in st:
+        assert _rel(dst[name].cpu().numpy(), st[name]) <= REL_TOL, (name, _rel(dst[name].cpu().numpy(), st[name]))
+    assert np.allclose(loss.cpu().numpy(), ref_loss, rtol=1e-4, atol=1e-5)
+    _assert_ws_clean(cfg, B, ws)
+    topkrec.bpr_set_hot_items(cfg, B, ws, [])                    # clearing restores an all-zero map
+    lay = topkrec.bpr_workspace_layout(cfg, B)
+    assert int(ws[lay["hotV"]:lay["hotV"] + 4 * ni].count_nonzero().item()) == 0
+    with pytest.raises(topkrec.TkrError):
+        topkrec.bpr_set_hot_items(cfg, B, ws, [0, 0])
 
 
 def test_bpr_step_lazy_rows_and_single_update():
@@ -304,8 +340,8 @@ def test_full_size_properties_c2():
     assert torch.equal(a["U"][nu // 2:], U0[nu // 2:]) and bool((a["msU"][nu // 2:] == 1).all())
     cnt = torch.bincount(u.long(), minlength=nu)
     assert bool((a["msU"][cnt > 0] < 1).all()) and bool((a["msU"][cnt > 0] >= 0.9).all())
-    for n in a:
-        assert _rel(a[n].cpu().numpy(), b[n].cpu().numpy()) <= 1e-5, n
+    for n in a:   # (item 0 collects ~1e5 gradients of both signs per step: its squared sum carries ~1e-5 of order noise)
+        assert _rel(a[n].cpu().numpy(), b[n].cpu().numpy()) <= 5e-5, n
     _assert_ws_clean(cfg, B, ws)
 
 

@@ -17,6 +17,8 @@ struct StepWs {            // views into the caller's workspace
     int32_t* cntU; int32_t* cntV;
     int32_t* listU; int32_t* listV;
     int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
+    int32_t* hot_slot;     // [n_items] 0 = cold, s+1 = the row's gradients are privatised in slot s of every block
+    int32_t* hot_ids;      // [TKR_MAX_HOT] item id of slot s (-1 = unused)
 };
 
 // VBPR rides on the same kernels with concatenated rows U' = [ur|uc], V' = [ir | F.E]:
@@ -28,6 +30,7 @@ struct StepExtra {
     int item_cols;
     const float* b_reg;
     float* wq;
+    int hot_rows = 0;      // privatised item rows per block (0 = off): shared memory holds hot_rows * (d + 2) floats
 };
 
 // MODE_LIST / MODE_DENSE: every touched row goes through the gradient accumulators (touched rows listed / flagged).

@@ -91,6 +91,10 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void red_add(float* p) const { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory"); }
 };
 
+__device__ __forceinline__ void sh_red_add(float* shared_ptr, float v) {
+    asm volatile("red.shared.add.f32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(shared_ptr)), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float x) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
@@ -186,6 +190,16 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
     }
     float loss_acc = 0.f;          // per-lane partial; summed over the block at the end
     constexpr unsigned FULL = 0xffffffffu;
+    // Popular item rows named by the caller (tkr_bpr_workspace_set_hot_items) are summed here, per block, and added to
+    // the global accumulators once at the end: one L2 atomic per block instead of one per occurrence.
+    extern __shared__ float hot_smem[];                        // [hmax][d] rows, [hmax] biases, [hmax] dirty flags
+    const int hmax = ex.hot_rows;
+    float* hot_b = hot_smem + (size_t)hmax * d;
+    float* hot_dirty = hot_b + hmax;
+    if (hmax > 0) {
+        for (int t = threadIdx.x; t < hmax * (d + 2); t += blockDim.x) hot_smem[t] = 0.f;
+        __syncthreads();
+    }
 
     // tpw (<= 32) triples per warp per round: 32 for large batches, fewer when the batch is too small
     // to give every resident warp a full block
@@ -202,6 +216,12 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
         const float bi = valid ? __ldg(ex.b_reg + i) : 0.f, bj = valid ? __ldg(ex.b_reg + j) : 0.f;   // regularised bias
         float x_mine = 0.f, s_mine = 0.f;
         // MODE_COUNT: bit 0/1/2 = the u / i / j row of this triple occurs once in the batch -> updated in place
+        int hs_i = 0, hs_j = 0;        // privatised slot + 1 of the item rows (0 = cold)
+        if (hmax > 0 && valid) {
+            hs_i = ws.hot_slot[i]; hs_j = ws.hot_slot[j];
+            if (hs_i > hmax) hs_i = 0;
+            if (hs_j > hmax) hs_j = 0;
+        }
         int single = 0;
         if (INPLACE && valid) single = (int)(ws.cntU[u] == 1) | ((int)(ws.cntV[i] == 1) << 1) | ((int)(ws.cntV[j] == 1) << 2);
         const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
@@ -215,6 +235,7 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
         for (int t = 0; t < cnt; ++t) {
             const int ru = __shfl_sync(FULL, u, t), ri = __shfl_sync(FULL, i, t), rj = __shfl_sync(FULL, j, t);
             const int sg = INPLACE ? __shfl_sync(FULL, single, t) : 0;
+            const int hi = hmax > 0 ? __shfl_sync(FULL, hs_i, t) : 0, hj = hmax > 0 ? __shfl_sync(FULL, hs_j, t) : 0;
             if (t + 1 < cnt) {   // next triple's gathers go out before this one's reduction
                 const int nu_ = __shfl_sync(FULL, u, t + 1), ni_ = __shfl_sync(FULL, i, t + 1), nj_ = __shfl_sync(FULL, j, t + 1);
                 nxt.load(U, V, nu_, ni_, nj_, d, lane);
@@ -263,12 +284,18 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
                         for (int e = 0; e < VW; ++e) opt_update(cfg, p.v[e], cur.i[c].v[e], cur.mi[c].v[e]);
                         cur.i[c].store(const_cast<float*>(V) + (int64_t)ri * d + off);
                         if (rms) cur.mi[c].store(msV + (int64_t)ri * d + off);
+                    } else if (hi) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) sh_red_add(hot_smem + (size_t)(hi - 1) * d + off + e, p.v[e]);
                     } else p.red_add(gi + off);
                     if (INPLACE && (sg & 4)) {
 #pragma unroll
                         for (int e = 0; e < VW; ++e) opt_update(cfg, q.v[e], cur.j[c].v[e], cur.mj[c].v[e]);
                         cur.j[c].store(const_cast<float*>(V) + (int64_t)rj * d + off);
                         if (rms) cur.mj[c].store(msV + (int64_t)rj * d + off);
+                    } else if (hj) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) sh_red_add(hot_smem + (size_t)(hj - 1) * d + off + e, q.v[e]);
                     } else q.red_add(gj + off);
                 }
             }
@@ -285,11 +312,26 @@ __global__ void __launch_bounds__(256) bpr_grad_kernel(
                 if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
                 if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
             }
-            atomicAdd(ws.Gb + i, -s_mine + reg_grad<L1>(bi, cfg.lambda_b));
-            atomicAdd(ws.Gb + j, s_mine + reg_grad<L1>(bj, cfg.lambda_b));
+            const float gbi = -s_mine + reg_grad<L1>(bi, cfg.lambda_b), gbj = s_mine + reg_grad<L1>(bj, cfg.lambda_b);
+            if (hs_i) { sh_red_add(hot_b + hs_i - 1, gbi); hot_dirty[hs_i - 1] = 1.f; } else atomicAdd(ws.Gb + i, gbi);
+            if (hs_j) { sh_red_add(hot_b + hs_j - 1, gbj); hot_dirty[hs_j - 1] = 1.f; } else atomicAdd(ws.Gb + j, gbj);
             if (ex.wq != nullptr) { atomicAdd(ex.wq + i, -s_mine); atomicAdd(ex.wq + j, s_mine); }
             if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)
                 loss_acc += fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
+        }
+    }
+    if (hmax > 0) {    // flush the block's privatised sums: one vector red per chunk per dirty row
+        __syncthreads();
+        for (int sl = threadIdx.x >> 5; sl < hmax; sl += blockDim.x >> 5) {
+            if (hot_dirty[sl] == 0.f) continue;
+            const int id = ws.hot_ids[sl];
+            for (int off = lane * VW; off < d; off += 32 * VW) {
+                Vec<VW> a;
+#pragma unroll
+                for (int e = 0; e < VW; ++e) a.v[e] = hot_smem[(size_t)sl * d + off + e];
+                a.red_add(ws.GV + (int64_t)id * d + off);
+            }
+            if (lane == 0) atomicAdd(ws.Gb + id, hot_b[sl]);
         }
     }
     if (!want_loss) return;
@@ -408,7 +450,7 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
     }
 }
 
-struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, total; };
+struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, hotV, total; };
 
 WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     WsLayout L;
@@ -426,6 +468,7 @@ WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     o = align_up(o, 256);
     L.cntV = take(ni * 4);
     L.listV = take((size_t)(2 * B < (int64_t)ni ? 2 * B : (int64_t)ni) * 4);
+    L.hotV = take(ni * 4 + TKR_MAX_HOT * 4);
     L.total = o;
     return L;
 }
@@ -439,6 +482,7 @@ int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, Step
     out->cntU = (int32_t*)(p + L.cntU); out->cntV = (int32_t*)(p + L.cntV);
     out->n_touched = (int32_t*)(p + L.n_touched);
     out->listU = (int32_t*)(p + L.listU); out->listV = (int32_t*)(p + L.listV);
+    out->hot_slot = (int32_t*)(p + L.hotV); out->hot_ids = out->hot_slot + cfg->n_items;
     return TKR_OK;
 }
 
@@ -480,7 +524,8 @@ static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, 
     const int tpw = tpw64 > 32 ? 32 : (int)tpw64;
     int64_t blocks = ((B + tpw - 1) / tpw + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-#define TKR_K(L1_, S_, IP_) bpr_grad_kernel<VW, NCH, L1_, S_, IP_><<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss, msU, msV)
+    const size_t hot_bytes = (size_t)ex.hot_rows * (cfg->d + 2) * sizeof(float);
+#define TKR_K(L1_, S_, IP_) bpr_grad_kernel<VW, NCH, L1_, S_, IP_><<<(unsigned)blocks, 256, hot_bytes, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss, msU, msV)
     if (mode == MODE_COUNT) TKR_K(false, false, true);   // (bpr_pick_mode only returns it for l2 + explicit triples)
     else if (cfg->l1) { if (u == nullptr) TKR_K(true, true, false); else TKR_K(true, false, false); }
     else { if (u == nullptr) TKR_K(false, true, false); else TKR_K(false, false, false); }
@@ -535,7 +580,13 @@ size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B) { return ws_layout(cfg, B
 
 using namespace tkr;
 
-static inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) { return StepExtra{cfg->d, b, nullptr}; }
+// Plain BPR rows: every column is a parameter; up to 16 KB of shared memory per block for the privatised hot rows
+// (costs nothing when the caller named none: the per-triple slot lookups read zeros).
+static inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) {
+    int rows = (16 * 1024) / ((cfg->d + 2) * (int)sizeof(float));
+    if (rows > TKR_MAX_HOT) rows = TKR_MAX_HOT;
+    return StepExtra{cfg->d, b, nullptr, rows};
+}
 
 extern "C" void tkr_debug_set_count_mode(int32_t m) { g_count_mode = m < -1 || m > 1 ? -1 : m; }
 
@@ -548,7 +599,7 @@ extern "C" int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t B, int64
     if (int rc = bpr_check_cfg(cfg, B)) return rc;
     TKR_CHECK_ARG(offsets != nullptr, "offsets is NULL");
     const WsLayout L = ws_layout(cfg, B);
-    const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.total};
+    const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.hotV, L.total};
     for (int t = 0; t < TKR_WS_NFIELDS; ++t) offsets[t] = (int64_t)v[t];
     return TKR_OK;
 }
@@ -558,6 +609,42 @@ extern "C" int tkr_bpr_workspace_init(const tkr_bpr_cfg* cfg, int64_t B, void* w
     StepWs v;
     if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &v)) return rc;
     TKR_CUDA(cudaMemsetAsync(ws, 0, ws_layout(cfg, B).total, (cudaStream_t)stream));
+    TKR_CUDA(cudaMemsetAsync(v.hot_ids, 0xff, TKR_MAX_HOT * 4, (cudaStream_t)stream));    // no privatised rows
+    return TKR_OK;
+}
+
+namespace tkr {
+__global__ void set_hot_kernel(int32_t* __restrict__ hot_slot, int32_t* __restrict__ hot_ids, int n_items, const int32_t* __restrict__ ids, int n) {
+    // one block: clear the previous set, then install the new one
+    for (int s = threadIdx.x; s < TKR_MAX_HOT; s += blockDim.x) {
+        const int old = hot_ids[s];
+        if (old >= 0 && old < n_items) hot_slot[old] = 0;
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < TKR_MAX_HOT; s += blockDim.x) {
+        const int id = s < n ? ids[s] : -1;
+        hot_ids[s] = id;
+        if (id >= 0) hot_slot[id] = s + 1;
+    }
+}
+}  // namespace tkr
+
+extern "C" int tkr_bpr_workspace_set_hot_items(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes,
+                                               const int32_t* item_ids_host, int32_t n, void* stream) {
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
+    StepWs v;
+    if (int rc = bpr_carve(cfg, B, ws, ws_bytes, &v)) return rc;
+    TKR_CHECK_ARG(n >= 0 && n <= TKR_MAX_HOT && (n == 0 || item_ids_host != nullptr), "n must be in [0, %d]", TKR_MAX_HOT);
+    for (int a = 0; a < n; ++a) {
+        TKR_CHECK_ARG(item_ids_host[a] >= 0 && item_ids_host[a] < cfg->n_items, "hot item id %d out of range", item_ids_host[a]);
+        for (int c = 0; c < a; ++c) TKR_CHECK_ARG(item_ids_host[c] != item_ids_host[a], "hot item ids must be distinct");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // the ids ride in the (unused while idle) head of listV; the kernel copies them into place
+    if (n > 0) TKR_CUDA(cudaMemcpyAsync(v.listV, item_ids_host, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    TKR_CUDA(cudaStreamSynchronize(st));            // the host array may be a temporary
+    set_hot_kernel<<<1, 64, 0, st>>>(v.hot_slot, v.hot_ids, cfg->n_items, v.listV, n);
+    TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
 

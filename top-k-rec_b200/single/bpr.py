@@ -174,6 +174,9 @@ class BPR(REC):
         if self._ws is None or self._ws_batch != batch_size:
             self._ws = topkrec.bpr_workspace(self._cfg, batch_size, self.device)
             self._ws_batch = batch_size
+            if self.tr_data:      # the most liked items: their gradient sums are privatised per thread block
+                pos = np.fromiter((i for items in self.tr_data.values() for i in items), np.int64)
+                topkrec.bpr_set_hot_items(self._cfg, batch_size, self._ws, topkrec.popular_items(pos, self.n_items))
         return self._ws
 
     def _run_steps(self, n_steps, batch_size, eid=0):

@@ -51,6 +51,7 @@ def lib():
     L.tkr_bpr_workspace_bytes.restype = sz; L.tkr_bpr_workspace_bytes.argtypes = [cfgp, i64]
     L.tkr_bpr_workspace_init.argtypes = [cfgp, i64, vp, sz, vp]
     L.tkr_bpr_workspace_layout.argtypes = [cfgp, i64, C.POINTER(C.c_int64)]
+    L.tkr_bpr_workspace_set_hot_items.argtypes = [cfgp, i64, vp, sz, vp, i32, vp]
     L.tkr_bpr_grad.argtypes = [cfgp] + [vp] * 3 + [vp] * 3 + [i64, smpp, u64, vp, vp, sz, i32, vp]
     L.tkr_bpr_apply.argtypes = [cfgp] + [vp] * 6 + [i64, vp, sz, i32, vp]
     L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
@@ -74,7 +75,7 @@ def lib():
     L.tkr_dat_read.argtypes = [C.c_char_p, vp, i64, i64]
     L.tkr_dat_write.argtypes = [C.c_char_p, vp, i64, i64]
     L.tkr_ratings_parse.argtypes = [C.c_char_p] * 3 + [C.POINTER(C.c_int64)] * 2 + [vp] * 4
-    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
@@ -177,7 +178,25 @@ def bpr_workspace(cfg: BprCfg, batch, device="cuda"):
     return ws
 
 
-WS_FIELDS = ("GU", "cntU", "listU", "n_touched", "GV", "Gb", "tchV", "cntV", "listV", "total")
+WS_FIELDS = ("GU", "cntU", "listU", "n_touched", "GV", "Gb", "tchV", "cntV", "listV", "hotV", "total")
+MAX_HOT = 32
+
+
+def bpr_set_hot_items(cfg: BprCfg, batch, ws, item_ids):
+    """Name up to MAX_HOT popular item rows whose gradients the step sums per thread block in shared memory
+    (tkr_bpr_workspace_set_hot_items).  item_ids: host ints, distinct; [] clears the set."""
+    ids = np.ascontiguousarray(np.asarray(item_ids, np.int32)[:MAX_HOT])
+    with torch.cuda.device(ws.device):
+        _check(lib().tkr_bpr_workspace_set_hot_items(cfg.ptr, int(batch), ws.data_ptr(), ws.numel(),
+                                                     ids.ctypes.data if ids.size else None, int(ids.size), _stream()))
+
+
+def popular_items(pos_idx, n_items, n=MAX_HOT):
+    """The n items with the most positives (ties: smaller id), from the sampler's positives CSR column array."""
+    pos_idx = pos_idx.cpu().numpy() if isinstance(pos_idx, torch.Tensor) else np.asarray(pos_idx)
+    cnt = np.bincount(pos_idx, minlength=n_items)
+    order = np.lexsort((np.arange(n_items), -cnt))[:n]
+    return order[cnt[order] > 0].astype(np.int32)
 
 
 def bpr_workspace_layout(cfg: BprCfg, batch):
