@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(256) bpr_count_kernel(const int32_t* __restric
 // the 32 row gathers run through the whole warp one triple after the other, software-pipelined so the
 // 128-bit gathers of triple t+1 are in flight while triple t is reduced and scattered.
 template <int VW, int NCH, bool L1, bool SAMPLE, bool INPLACE>
-__global__ void __launch_bounds__(256) bpr_grad_kernel(
+__global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
     SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, StepExtra ex, float* __restrict__ loss_out,
