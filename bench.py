@@ -306,6 +306,7 @@ def run_ours(args, rank, local_rank, world):
     if world == 1 and not args.skip_sweep:
         line["sweep"] = bpr_sweep(cfg, st, smp, dev)
         line["sweep"].append(bpr_hbm_streaming(dev))
+        line["vbpr"] = vbpr_points(smp, dev)
     if rank == 0 and world == 1 and not args.skip_cpu:
         # bounded CPU sample: ~10-30 s of the OpenMP port on the same workload
         v1, ms1, threads = cpu_bpr_steps(min(B, 1 << 20), 1, 1)
@@ -386,6 +387,44 @@ def bpr_hbm_streaming(dev, n_users=6_000_000, n_items=1_000_000, B=1 << 20, reps
            "roofline_frac": algorithmic_bytes_per_triple(D) * B / (ms / 1e3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
     del st, ws, pool
     torch.cuda.empty_cache()
+    return out
+
+
+def vbpr_points(smp, dev, d_feat=4096, k=128):
+    """BASELINE configs[2]: VBPR with a dense 4096-d feature table resident in HBM (70k users x 10k items, k = 64 + 64),
+    fused sampler, device-timed: the reference's batch 256 (vbpr.py:76) and 2^16 / 2^20."""
+    import torch
+    import topkrec
+    g = torch.Generator(device=dev); g.manual_seed(2)
+    F = torch.randn(N_ITEMS, d_feat, device=dev, generator=g).abs_()
+    F /= F.norm(dim=1, keepdim=True)
+    h = k // 2
+    cfg = topkrec.VbprCfg(N_USERS, N_ITEMS, k, d_feat)
+    st = {"U": torch.randn(N_USERS, k, device=dev, generator=g) * 0.01, "V": torch.zeros(N_ITEMS, k, device=dev),
+          "rb": torch.zeros(N_ITEMS, device=dev), "bsum": torch.zeros(N_ITEMS, device=dev),
+          "E": torch.full((d_feat, h), 2.0 / (d_feat * k), device=dev), "c": torch.zeros(d_feat, device=dev)}
+    st["V"][:, :h] = torch.randn(N_ITEMS, h, device=dev, generator=g) * 0.01
+    for n, m in (("U", "msU"), ("V", "msV"), ("rb", "msrb"), ("E", "msE"), ("c", "msc")):
+        st[m] = torch.ones_like(st[n])
+    out = []
+    for B, n_steps, reps in ((256, 64, 3), (1 << 16, 4, 3), (1 << 20, 1, 5)):
+        ws = topkrec.vbpr_workspace(cfg, B, dev)
+        loss = torch.zeros(n_steps, dtype=torch.float32, device=dev)
+
+        def run(r):
+            topkrec.vbpr_step(cfg, st, F, None, None, None, B, n_steps, ws, loss, sampler=smp, first_draw=(11 << 32) + r * B * n_steps)
+        for r in range(2):
+            run(r)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for r in range(reps):
+            run(2 + r)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (reps * n_steps)
+        out.append({"batch_size": B, "us_per_step": 1e3 * ms, "triples_per_sec": B / (ms / 1e3),
+                    "config": "VBPR %d users x %d items, k=%d (%d + %d), %d-d dense features resident (%.0f MB)" % (N_USERS, N_ITEMS, k, h, h, d_feat, N_ITEMS * d_feat * 4 / 1e6)})
+        del ws
     return out
 
 

@@ -16,67 +16,143 @@
 
 namespace tkr {
 
-constexpr int GT = 64;   // GEMM tile edge
-constexpr int GK = 16;   // K chunk
+constexpr int GT = 64;   // GEMM tile edge (output tile GT x GT per block)
+constexpr int GK = 32;   // K chunk staged per iteration; the four 64-thread groups of a block take 8 k's each
+
+// fp32 SGEMM core shared by the two content GEMMs (both have a 64-wide N: the k/2 content dims).  A block of 256
+// threads owns a 64 x 64 output tile; thread (g, ty, tx) of k-group g accumulates an 8 x 8 register tile over
+// the k's [8g, 8g + 8) of every staged chunk (two LDS.128 per operand per k for 64 FMAs), plus the extra
+// 64 x 1 product with the vector `vs` (the F.c / F^T wq column).  The four groups' partials are then summed
+// through shared memory.  As[k][m], Bs[k][n]: the caller stages them.
+// RT = output rows per thread: the tile is (8 * RT) x 64, so the row count of a tile can be chosen to make the number
+// of tiles fit one wave of the 148 SMs (these kernels run one 256-thread block per SM: ~160 registers per thread).
+template <int RT>
+struct GemmSmem {
+    float As[GK][8 * RT + 4];
+    float Bs[GK][GT + 4];
+    float vs[GK];
+};
+
+template <int RT>
+__device__ __forceinline__ void gemm_chunk(const GemmSmem<RT>& sm, int g, int ty, int tx, float (&acc)[RT][8], float (&accq)[RT]) {
+#pragma unroll
+    for (int k8 = 0; k8 < 8; ++k8) {
+        const int kk = g * 8 + k8;
+        float a[RT], bv[8];
+        if (RT == 8) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sm.As[kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&sm.As[kk][ty * 8 + 4]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        } else {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) a[r] = sm.As[kk][ty * RT + r];
+        }
+        const float4 b0 = *reinterpret_cast<const float4*>(&sm.Bs[kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&sm.Bs[kk][tx * 8 + 4]);
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        const float v = sm.vs[kk];
+#pragma unroll
+        for (int r = 0; r < RT; ++r) {
+#pragma unroll
+            for (int n = 0; n < 8; ++n) acc[r][n] = fmaf(a[r], bv[n], acc[r][n]);
+            if (tx == 0) accq[r] = fmaf(a[r], v, accq[r]);
+        }
+    }
+}
+
+// Sum the four k-groups' register tiles: afterwards red[m][n] (and redq[m]) hold the block's (8 RT) x 64 (+ x 1) result.
+template <int RT>
+__device__ __forceinline__ void gemm_reduce(float (*red)[GT + 1], float* redq, int g, int ty, int tx, const float (&acc)[RT][8], const float (&accq)[RT]) {
+    for (int turn = 0; turn < 4; ++turn) {
+        if (g == turn) {
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    float* dst = &red[ty * RT + r][tx * 8 + n];
+                    *dst = turn == 0 ? acc[r][n] : *dst + acc[r][n];
+                }
+                if (tx == 0) redq[ty * RT + r] = turn == 0 ? accq[r] : redq[ty * RT + r] + accq[r];
+            }
+        }
+        __syncthreads();
+    }
+}
 
 // C[m, n] = sum_k F[m, k] * E[k, n]  (m < M items, n < h), written to Vp[m * ldv + h_off + n];
-// q[m] = sum_k F[m, k] * c[k], bsum[m] = rb[m] + q[m].
+// q[m] = sum_k F[m, k] * c[k], bsum[m] = rb[m] + q[m].  One block per (8 RT)-row tile.
+template <int RT>
 __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restrict__ F, const float* __restrict__ E,
                                                            const float* __restrict__ c, const float* __restrict__ rb, int M,
                                                            int h, int K, float* __restrict__ Vp, int ldv, int h_off,
                                                            float* __restrict__ bsum) {
-    __shared__ float As[GK][GT + 4];
-    __shared__ float Bs[GK][GT + 4];
-    __shared__ float cs[GK];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int m0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
-    float acc[4][4] = {};
-    float accq[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int TM = 8 * RT, NA = TM * (GK / 4);          // rows per tile; float4 of an A chunk
+    constexpr int AIT = (NA + 255) / 256;
+    __shared__ GemmSmem<RT> sm;
+    __shared__ float red[TM][GT + 1];
+    __shared__ float redq[TM];
+    const int tid = threadIdx.x, g = tid >> 6, ty = (tid & 63) >> 3, tx = tid & 7;
+    const int m0 = blockIdx.x * TM, n0 = blockIdx.y * GT;
+    const bool vec = (K & 3) == 0 && (h & 3) == 0;
+    float acc[RT][8] = {};
+    float accq[RT] = {};
+    // A chunk: TM rows x 32 k of F (row-major), transposed into As[k][row]; B chunk: 32 k x 64 n of E.  The next chunk's
+    // global loads are issued before the current chunk is multiplied (register double buffer).
+    float4 pa[AIT], pb[2];
+    float pc = 0.f;
+    auto fetch = [&](int k0) {
+#pragma unroll
+        for (int it = 0; it < AIT; ++it) {
+            const int idx = tid + it * 256;
+            const int row = idx >> 3, k4 = (idx & 7) * 4;
+            const int m = m0 + row, k = k0 + k4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < NA && m < M) {
+                const float* src = F + (int64_t)m * K + k;
+                if (vec && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
+                else { if (k < K) v.x = __ldg(src); if (k + 1 < K) v.y = __ldg(src + 1); if (k + 2 < K) v.z = __ldg(src + 2); if (k + 3 < K) v.w = __ldg(src + 3); }
+            }
+            pa[it] = v;
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int idx = tid + it * 256;
+            const int kb = idx >> 4, n4 = (idx & 15) * 4;
+            const int kk = k0 + kb, n = n0 + n4;
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kk < K) {
+                const float* src = E + (int64_t)kk * h + n;
+                if (vec && n + 3 < h) w = __ldg(reinterpret_cast<const float4*>(src));
+                else { if (n < h) w.x = __ldg(src); if (n + 1 < h) w.y = __ldg(src + 1); if (n + 2 < h) w.z = __ldg(src + 2); if (n + 3 < h) w.w = __ldg(src + 3); }
+            }
+            pb[it] = w;
+        }
+        pc = (tid < GK && k0 + tid < K) ? __ldg(c + k0 + tid) : 0.f;
+    };
+    fetch(0);
     for (int k0 = 0; k0 < K; k0 += GK) {
-        {   // A chunk: 64 rows x 16 k, transposed into As[k][row]
-            const int row = tid >> 2, kq = (tid & 3) * 4;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int m = m0 + row, k = k0 + kq + e;
-                As[kq + e][row] = (m < M && k < K) ? __ldg(F + (int64_t)m * K + k) : 0.f;
-            }
-            // B chunk: 16 k x 64 n
-            const int kk = tid >> 4, nq = (tid & 15) * 4;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int k = k0 + kk, n = n0 + nq + e;
-                Bs[kk][nq + e] = (k < K && n < h) ? __ldg(E + (int64_t)k * h + n) : 0.f;
-            }
-            if (tid < GK) cs[tid] = (k0 + tid < K) ? __ldg(c + k0 + tid) : 0.f;
+        for (int it = 0; it < AIT; ++it) {
+            const int idx = tid + it * 256;
+            const int row = idx >> 3, k4 = (idx & 7) * 4;
+            if (idx < NA) { sm.As[k4][row] = pa[it].x; sm.As[k4 + 1][row] = pa[it].y; sm.As[k4 + 2][row] = pa[it].z; sm.As[k4 + 3][row] = pa[it].w; }
         }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int idx = tid + it * 256;
+            *reinterpret_cast<float4*>(&sm.Bs[idx >> 4][(idx & 15) * 4]) = pb[it];
+        }
+        if (tid < GK) sm.vs[tid] = pc;
         __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < GK; ++kk) {
-            float a[4], bv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
-#pragma unroll
-            for (int n = 0; n < 4; ++n) bv[n] = Bs[kk][tx * 4 + n];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int n = 0; n < 4; ++n) acc[r][n] = fmaf(a[r], bv[n], acc[r][n]);
-                if (tx == 0) accq[r] = fmaf(a[r], cs[kk], accq[r]);
-            }
-        }
+        if (k0 + GK < K) fetch(k0 + GK);
+        gemm_chunk<RT>(sm, g, ty, tx, acc, accq);
         __syncthreads();
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int m = m0 + ty * 4 + r;
-        if (m >= M) continue;
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            const int col = n0 + tx * 4 + n;
-            if (col < h) Vp[(int64_t)m * ldv + h_off + col] = acc[r][n];
-        }
-        if (tx == 0 && blockIdx.y == 0) bsum[m] = rb[m] + accq[r];
+    gemm_reduce<RT>(red, redq, g, ty, tx, acc, accq);
+    for (int e = tid; e < TM * GT; e += 256) {
+        const int r = e >> 6, n = e & 63;
+        const int m = m0 + r, col = n0 + n;
+        if (m < M && col < h) Vp[(int64_t)m * ldv + h_off + col] = red[r][n];
     }
+    if (blockIdx.y == 0 && tid < TM && m0 + tid < M) bsum[m0 + tid] = rb[m0 + tid] + redq[tid];
 }
 
 // GE[f, n] += sum_r F[row_r, f] * W[row_r, n],  Gc[f] += sum_r F[row_r, f] * wq[row_r]
@@ -85,63 +161,67 @@ __global__ void __launch_bounds__(256) vbpr_grad_dense_kernel(const float* __res
                                                               int ldv, int h_off, int h, const float* __restrict__ wq,
                                                               const int32_t* __restrict__ rows, const int32_t* __restrict__ n_rows_dev,
                                                               int n_rows_all, float* __restrict__ GE, float* __restrict__ Gc) {
-    __shared__ float As[GK][GT + 4];   // F[row, f0..f0+64)
-    __shared__ float Bs[GK][GT + 4];   // W[row, n0..n0+64)
-    __shared__ float ws_[GK];
-    __shared__ int rs[GK];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ GemmSmem<8> sm;         // As[r][f0..f0+64) = F rows, Bs[r][n0..n0+64) = W rows, vs[r] = wq
+    __shared__ float red[GT][GT + 1];
+    __shared__ float redq[GT];
+    const int tid = threadIdx.x, g = tid >> 6, ty = (tid & 63) >> 3, tx = tid & 7;
     const int f0 = blockIdx.x * GT, n0 = blockIdx.y * GT;
     const int n_rows = rows ? *n_rows_dev : n_rows_all;
     const int chunks = (n_rows + GK - 1) / GK;
     const int per = (chunks + gridDim.z - 1) / gridDim.z;
     const int c_beg = blockIdx.z * per, c_end = min(chunks, c_beg + per);
-    float acc[4][4] = {};
-    float accq[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ch = c_beg; ch < c_end; ++ch) {
+    if (c_beg >= c_end) return;
+    const bool vecF = (dF & 3) == 0, vecW = (ldv & 3) == 0 && (h_off & 3) == 0 && (h & 3) == 0;
+    float acc[8][8] = {};
+    float accq[8] = {};
+    float4 pa[2], pb[2];
+    float pq = 0.f;
+    auto fetch = [&](int ch) {     // next chunk's rows straight into registers (row ids read from global)
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int idx = tid + it * 256;
+            const int kk = idx >> 4, q4 = (idx & 15) * 4;
+            const int rr = ch * GK + kk;
+            const int r = rr < n_rows ? (rows ? __ldg(rows + rr) : rr) : -1;
+            const int f = f0 + q4, n = n0 + q4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f), w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r >= 0) {
+                const float* sf = F + (int64_t)r * dF + f;
+                if (vecF && f + 3 < dF) v = __ldg(reinterpret_cast<const float4*>(sf));
+                else { if (f < dF) v.x = __ldg(sf); if (f + 1 < dF) v.y = __ldg(sf + 1); if (f + 2 < dF) v.z = __ldg(sf + 2); if (f + 3 < dF) v.w = __ldg(sf + 3); }
+                const float* sw = GV + (int64_t)r * ldv + h_off + n;
+                if (vecW && n + 3 < h) w = *reinterpret_cast<const float4*>(sw);
+                else { if (n < h) w.x = sw[0]; if (n + 1 < h) w.y = sw[1]; if (n + 2 < h) w.z = sw[2]; if (n + 3 < h) w.w = sw[3]; }
+            }
+            pa[it] = v; pb[it] = w;
+        }
         if (tid < GK) {
-            const int r = ch * GK + tid;
-            rs[tid] = r < n_rows ? (rows ? rows[r] : r) : -1;
+            const int rr = ch * GK + tid;
+            const int r = rr < n_rows ? (rows ? __ldg(rows + rr) : rr) : -1;
+            pq = r >= 0 ? wq[r] : 0.f;
         }
+    };
+    fetch(c_beg);
+    for (int ch = c_beg; ch < c_end; ++ch) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int idx = tid + it * 256;
+            *reinterpret_cast<float4*>(&sm.As[idx >> 4][(idx & 15) * 4]) = pa[it];
+            *reinterpret_cast<float4*>(&sm.Bs[idx >> 4][(idx & 15) * 4]) = pb[it];
+        }
+        if (tid < GK) sm.vs[tid] = pq;
         __syncthreads();
-        {
-            const int kk = tid >> 4, q4 = (tid & 15) * 4;
-            const int r = rs[kk];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int f = f0 + q4 + e, n = n0 + q4 + e;
-                As[kk][q4 + e] = (r >= 0 && f < dF) ? __ldg(F + (int64_t)r * dF + f) : 0.f;
-                Bs[kk][q4 + e] = (r >= 0 && n < h) ? GV[(int64_t)r * ldv + h_off + n] : 0.f;
-            }
-            if (tid < GK) ws_[tid] = rs[tid] >= 0 ? wq[rs[tid]] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int kk = 0; kk < GK; ++kk) {
-            float a[4], bv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) a[r] = As[kk][ty * 4 + r];
-#pragma unroll
-            for (int n = 0; n < 4; ++n) bv[n] = Bs[kk][tx * 4 + n];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                for (int n = 0; n < 4; ++n) acc[r][n] = fmaf(a[r], bv[n], acc[r][n]);
-                if (tx == 0) accq[r] = fmaf(a[r], ws_[kk], accq[r]);
-            }
-        }
+        if (ch + 1 < c_end) fetch(ch + 1);
+        gemm_chunk<8>(sm, g, ty, tx, acc, accq);
         __syncthreads();
     }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int f = f0 + ty * 4 + r;
-        if (f >= dF) continue;
-#pragma unroll
-        for (int n = 0; n < 4; ++n) {
-            const int col = n0 + tx * 4 + n;
-            if (col < h && acc[r][n] != 0.f) atomicAdd(GE + (int64_t)f * h + col, acc[r][n]);
-        }
-        if (tx == 0 && blockIdx.y == 0 && accq[r] != 0.f) atomicAdd(Gc + f, accq[r]);
+    gemm_reduce<8>(red, redq, g, ty, tx, acc, accq);
+    for (int e = tid; e < GT * GT; e += 256) {
+        const int r = e >> 6, n = e & 63;
+        const int f = f0 + r, col = n0 + n;
+        if (f < dF && col < h && red[r][n] != 0.f) atomicAdd(GE + (int64_t)f * h + col, red[r][n]);
     }
+    if (blockIdx.y == 0 && tid < GT && f0 + tid < dF && redq[tid] != 0.f) atomicAdd(Gc + f0 + tid, redq[tid]);
 }
 
 // Dense optimiser step on E[dF*h] and c[dF] (vbpr.py:63-73: the E and c regularisers are NOT per occurrence);
@@ -208,9 +288,20 @@ static int vbpr_check(const tkr_vbpr_cfg* cfg, int64_t B) {
 
 static void launch_project(const tkr_vbpr_cfg* cfg, const float* F, const float* E, const float* c, const float* rb, float* V,
                            float* bsum, cudaStream_t st) {
-    const int h = cfg->base.d / 2;
-    dim3 grid((cfg->base.n_items + GT - 1) / GT, (h + GT - 1) / GT);
-    vbpr_project_kernel<<<grid, 256, 0, st>>>(F, E, c, rb, cfg->base.n_items, h, cfg->d_feat, V, cfg->base.d, h, bsum);
+    const int h = cfg->base.d / 2, M = cfg->base.n_items;
+    // rows per tile: the smallest multiple of 8 in [64, 96] that fits the item table into one wave of blocks
+    int rt = ((M + kNumSMs - 1) / kNumSMs + 7) / 8;
+    if (rt < 8 || rt > 12) rt = 8;
+    const unsigned gy = (unsigned)((h + GT - 1) / GT);
+#define TKR_PROJ(RT) vbpr_project_kernel<RT><<<dim3((unsigned)((M + 8 * RT - 1) / (8 * RT)), gy), 256, 0, st>>>(F, E, c, rb, M, h, cfg->d_feat, V, cfg->base.d, h, bsum)
+    switch (rt) {
+        case 9: TKR_PROJ(9); break;
+        case 10: TKR_PROJ(10); break;
+        case 11: TKR_PROJ(11); break;
+        case 12: TKR_PROJ(12); break;
+        default: TKR_PROJ(8); break;
+    }
+#undef TKR_PROJ
 }
 
 }  // namespace tkr
