@@ -29,7 +29,7 @@ for mode in (1, 2, 3, 4, 5):
     print('mode %d (%s): call ms %.3f; MMA-warp cycles per tile %.0f (ideal %d)' % (
         mode, {1: 'normal+counters', 2: 'no TMEM reads', 3: 'TMEM drain, no scan', 4: 'no TMEM reads, no V loads', 5: 'full scan, thresholds at +inf (no hand-offs)'}[mode], e0.elapsed_time(e1), x[0::2, 21, 0].mean() / tiles, 128 * ((d + 63) // 64) * 4))
     for w in (0, 4, 8, 12, 16, 20, 21):
-        role = 'sel(busy,idle,events,compact)' if w < 4 else ('epi(scan,wait_tfull,drain+handback)' if w < 20 else ('tma(total,wait_empty)' if w == 20 else 'mma(total,-,wait_full,ns)'))
+        role = 'sel(busy,idle,events,compact)' if w < 4 else ('epi(scan,wait_tfull,drain+handback,tmem_ld)' if w < 20 else ('tma(total,wait_empty)' if w == 20 else 'mma(total,-,wait_full,ns)'))
         print('   warp %2d %-36s %7.0f %7.0f %7.0f %7.0f' % (w, role, x[:, w, 0].mean() / tiles, x[:, w, 1].mean() / tiles, x[:, w, 2].mean() / tiles, x[:, w, 3].mean() / tiles))
     lead = x[0::2, 21]
     print('   MMA loop: %.3f ms, SM clock %.0f MHz, %.0f TFLOP/s over the loop' % (lead[:, 3].mean() * 1e-6, lead[:, 0].mean() / lead[:, 3].mean() * 1e3, 2.0 * nu * 256 * tiles * d / (lead[:, 3].mean() * 1e-9) / 1e12))

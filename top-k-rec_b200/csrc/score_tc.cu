@@ -547,7 +547,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             mbar_arrive_cluster(full_leader);
             mbar_arrive_cluster(full_leader + 8u * ((uint32_t)spt & smask));
         }
-        long long dbg_w = 0, dbg_c = 0, dbg_s = 0;
+        long long dbg_w = 0, dbg_c = 0, dbg_s = 0, dbg_l = 0;
         float s1 = -INFINITY, s2 = -INFINITY, s3 = -INFINITY, s4 = -INFINITY;
         // loop-carried addresses instead of per-tile recomputation (the kernel runs at its register cap)
         const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cq * 64;
@@ -585,6 +585,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
                 tmem_ld32(taddr + 32, vb);
                 tmem_ld_wait();
             }
+            dbg_l += tick<DBG>() - w1;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(full_leader + 8u * hb_stage);
@@ -606,7 +607,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
         }
         __syncwarp();
         if (lane == 0) { __threadfence_block(); sh_atomic_inc(ring + (uint32_t)offsetof(SelShared, done)); }
-        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)cta_lin * F_WARPS + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; }
+        if (p.dbg && lane == 0) { long long* o = p.dbg + ((size_t)cta_lin * F_WARPS + warp) * 4; o[0] = dbg_s; o[1] = dbg_w; o[2] = dbg_c; o[3] = dbg_l; }
         } else {
         // ===================== selection: one warp per lane quarter owns the candidate lists of its 32 rows =====================
         // (explicit shared-space accesses: through generic volatile pointers every poll is an LD.E.STRONG.SYS)
