@@ -244,6 +244,53 @@ int tkr_dat_write(const char* path, const float* mat, int64_t rows, int64_t cols
 int tkr_ratings_parse(const char* ratings_path, const char* uid_path, const char* iid_path, int64_t* n_lines,
                       int64_t* n_pairs, int32_t* line_user, int64_t* line_indptr, int32_t* pair_item, int8_t* pair_like);
 
+/* ------------------------------------------------------------------ ALS (WMF / CER), SURVEY 8(f) NEXT-1 */
+
+/* One half-step of the alternating least squares of single/cer.py:36-63 (and the intended single/wmf.py:67-96):
+ * for every row r of the solved side X[n_rows, d]
+ *     X_r = solve( base + (a-b) * sum_{p in pos(r)} Y_p Y_p^T + ridge*I ,  a * sum_p Y_p + ridge * prior_r )
+ * replacing the reference's Python loop of np.dot + np.linalg.solve.  fp32 throughout (the reference forms the
+ * matrices in fp32 and solves them in fp64 LAPACK; see DESIGN.md for the measured difference).  d <= 256.
+ *   base   [d,d]   b * Yr^T Yr (+ lambda_u I on the user side, cer.py:38) from tkr_als_gram
+ *   prior  [n_rows,d] or NULL: the content prior F_j E of CER (cer.py:35,55,62)
+ *   cfg.solve_empty  rows without positives are solved too (CER items, cer.py:61-62) or keep their value
+ *   cfg.item_loss    loss_rows[r] = the row's terms of the reference's loss: 0 -> 1/2 lreg |x|^2 (cer.py:46),
+ *                    1 -> cer.py:58-63 / wmf.py:91-96 (with x^T B x evaluated as x^T rhs - ridge |x|^2)
+ * The work list (`plan`, DEVICE arrays built by the caller once per data set) cuts rows into segments of
+ * positives: seg_slot < 0 = the row's only segment, solved by the block that accumulates it; otherwise the segment's
+ * partial matrix is written to partial slot seg_slot and the row is finished by the second kernel from its
+ * multi_nslots consecutive slots starting at multi_slot0 (fixed summation order: results are deterministic).
+ * Segments should be listed longest first. */
+typedef struct tkr_als_cfg {
+    int32_t d;
+    float a, b;          /* confidence of positives / of everything else (wmf.py:11) */
+    float ridge;         /* added to the diagonal per row: 0 on the user side (lambda_u is in base), lambda_v for items */
+    float lreg;          /* coefficient of the row's quadratic loss term (lambda_u / lambda_v) */
+    int32_t solve_empty;
+    int32_t item_loss;
+} tkr_als_cfg;
+typedef struct tkr_als_plan {
+    int64_t n_segs;
+    const int32_t* seg_row;     /* [n_segs] row of X */
+    const int64_t* seg_off;     /* [n_segs] first position in idx */
+    const int32_t* seg_len;     /* [n_segs] positives in the segment */
+    const int32_t* seg_slot;    /* [n_segs] -1 or partial slot */
+    int64_t n_multi;
+    const int32_t* multi_row;   /* [n_multi] rows that were split */
+    const int32_t* multi_slot0; /* [n_multi] */
+    const int32_t* multi_nslots;/* [n_multi] */
+    const int64_t* multi_total; /* [n_multi] positives of the row */
+    int64_t n_slots;
+} tkr_als_plan;
+size_t tkr_als_partial_bytes(int32_t d, int64_t n_slots);
+int tkr_als_solve_rows(const tkr_als_cfg* cfg, const tkr_als_plan* plan, const float* Y, float* X, const int32_t* idx,
+                       const float* base, const float* prior, double* loss_rows, void* partial, size_t partial_bytes,
+                       void* stream);
+/* out[d,d] = scale * sum_{r in rows} Y_r Y_r^T + ridge * I   (XX of cer.py:37-38 / :47-48); rows = DEVICE int32[n_rows]. */
+size_t tkr_als_gram_workspace_bytes(int32_t d);
+int tkr_als_gram(const float* Y, int32_t d, const int32_t* rows, int64_t n_rows, float scale, float ridge, float* out,
+                 void* ws, size_t ws_bytes, void* stream);
+
 /* Merge n_lists candidate lists idx/score[n_lists][nu][k] (each in the order
  * above, padded with idx -1) into out[nu][k] in the same order. */
 int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,

@@ -254,3 +254,60 @@ def test_load_content_data(tmp_path, mini):
         assert np.array_equal(m.feat[m.iids[iid]], dense[pos])
     missing = [i for i in m.iids if i not in set(order)]
     assert all((m.feat[m.iids[i]] == 0).all() for i in missing)
+
+
+def test_als_plan_tiles_every_row():
+    """topkrec.als_build_plan: segments of a row are consecutive, cover its positives exactly once, split rows own
+    consecutive partial slots, longest rows come first."""
+    import topkrec
+    rng = np.random.default_rng(0)
+    cnt = rng.integers(0, 50, 200); cnt[5] = 1000; cnt[9] = 64; cnt[11] = 0
+    indptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    for seg in (16, 64, 4096):
+        plan, n_slots = topkrec.als_build_plan(indptr, seg)
+        seen = np.zeros(int(indptr[-1]), np.int32)
+        for r, off, ln in zip(plan["seg_row"], plan["seg_off"], plan["seg_len"]):
+            assert indptr[r] <= off and off + ln <= indptr[r + 1] and 0 <= ln <= seg
+            seen[off:off + ln] += 1
+        assert np.all(seen == 1)
+        assert sorted(set(plan["seg_row"].tolist())) == list(range(200))              # empty rows keep one (empty) segment
+        first_len = cnt[plan["seg_row"]]
+        assert np.all(np.diff(first_len) <= 0)                                        # longest first
+        multi = set(np.flatnonzero(cnt > seg).tolist())
+        assert set(plan["multi_row"].tolist()) == multi and n_slots == int((plan["seg_slot"] >= 0).sum())
+        for r, s0, ns, tot in zip(plan["multi_row"], plan["multi_slot0"], plan["multi_nslots"], plan["multi_total"]):
+            slots = plan["seg_slot"][plan["seg_row"] == r]
+            assert slots.tolist() == list(range(s0, s0 + ns)) and tot == cnt[r] and ns == -(-cnt[r] // seg)
+        single = plan["seg_slot"][~np.isin(plan["seg_row"], plan["multi_row"])]
+        assert np.all(single == -1)
+    with pytest.raises(ValueError):
+        topkrec.als_build_plan(np.array([0, 3, 2]), 16)
+
+
+def test_als_abi_argument_errors_without_gpu():
+    import ctypes as C
+    import topkrec
+    from topkrec._lib import tkr_als_cfg, tkr_als_plan
+    L = topkrec.lib()
+    assert L.tkr_als_partial_bytes(300, 1) == 0 and L.tkr_als_gram_workspace_bytes(0) == 0
+    assert L.tkr_als_partial_bytes(256, 2) >= 2 * (10 * 4096 + 256) * 4
+    assert L.tkr_als_gram(None, 8, None, 0, 1.0, 0.0, None, None, 0, None) == -1 and b"null pointer" in L.tkr_last_error()
+    cfg, plan = tkr_als_cfg(512, 1, 0.01, 0, 0.01, 0, 0), tkr_als_plan()
+    assert L.tkr_als_solve_rows(C.byref(cfg), C.byref(plan), 1, 1, None, 1, None, None, None, 0, None) == -1
+    assert b"outside [1,256]" in L.tkr_last_error()
+
+
+def test_wmf_cer_class_surface():
+    """constructor defaults and attributes of single/wmf.py:11-31, single/cer.py:17-22"""
+    import inspect
+    from single import WMF, CER, REC
+    w, c = WMF(8), CER(8, 5)
+    assert (w.k, w.lu, w.lv, w.a, w.b) == (8, 0.01, 0.01, 1, 0.01)
+    assert (c.k, c.d, c.lu, c.lv, c.le, c.a, c.b) == (8, 5, 0.01, 10, 10e3, 1, 0.01) and c.E is None
+    assert issubclass(CER, WMF) and issubclass(WMF, REC)
+    for cls in (WMF, CER):
+        sig = inspect.signature(cls.train)
+        assert list(sig.parameters)[1:] == ["max_iter", "tol", "model_path"]
+        assert sig.parameters["max_iter"].default == 200 and sig.parameters["tol"].default == 1e-4
+    for attr in ("uids", "n_users", "usm", "iids", "n_items", "ism", "n_ratings", "u_rated", "i_rated", "fue", "fie"):
+        assert hasattr(w, attr)

@@ -250,3 +250,39 @@ def test_philox_sampler_is_valid_and_uniform(mini):
     # order independence: a later window of draws is the same as slicing a longer one
     u2, i2, j2 = philox_ref.sample(tr_users, indptr, idx, len(iids), 99, 1000, 50)
     assert np.array_equal(u2, u[1000:1050]) and np.array_equal(i2, i[1000:1050]) and np.array_equal(j2, j[1000:1050])
+
+
+def _als_golden(golden):
+    g = np.load(os.path.join(golden, "als_cer.npz"))
+    u_ptr = np.concatenate([[0], np.cumsum(g["u_cnt"])]).astype(np.int64)
+    i_ptr = np.concatenate([[0], np.cumsum(g["i_cnt"])]).astype(np.int64)
+    return g, u_ptr, i_ptr
+
+
+@pytest.mark.parametrize("iters", [1, 4])
+def test_als_oracle_matches_reference_cer(golden, iters):
+    """oracle/als_ref.py against factors produced by the UNMODIFIED reference CER.train (make_golden_als.py):
+    bit-identical U / V / E (same numpy calls in the same order), losses to print precision (the reference's running
+    sum is fp32 until a fp64 term joins it, cer.py:46-65)."""
+    from oracle import als_ref
+    g, u_ptr, i_ptr = _als_golden(golden)
+    U, V, E, losses = als_ref.cer_train(g["fue0"], g["fie0"], g["E0"], g["feat"], u_ptr, g["u_idx"], i_ptr, g["i_idx"],
+                                        float(g["a"]), float(g["b"]), float(g["lu"]), float(g["lv"]), float(g["le"]),
+                                        max_iter=iters, tol=0.0)
+    assert np.array_equal(U, g["fue%d" % iters]) and np.array_equal(V, g["fie%d" % iters]) and np.array_equal(E, g["E%d" % iters])
+    assert np.allclose(losses, g["losses"][:iters], rtol=1e-6)
+    assert (g["u_cnt"] == 0).any() and (g["i_cnt"] == 0).any()
+
+
+def test_als_oracle_row_solution_satisfies_normal_equations(golden):
+    """independent check of the restated algebra (cer.py:39-45): fp64 residual of one user's system."""
+    from oracle import als_ref
+    g, u_ptr, i_ptr = _als_golden(golden)
+    fue, fie = g["fue0"].copy(), g["fie0"].copy()
+    i_rated = np.flatnonzero(g["i_cnt"] > 0)
+    als_ref.user_step(fue, fie, u_ptr, g["u_idx"], i_rated, 1.0, 0.01, 0.01)
+    u = int(np.argmax(g["u_cnt"]))
+    Vi = fie[g["u_idx"][u_ptr[u]:u_ptr[u + 1]]].astype(np.float64)
+    Vr = fie[i_rated].astype(np.float64)
+    A = 0.01 * Vr.T @ Vr + 0.01 * np.eye(fie.shape[1]) + 0.99 * Vi.T @ Vi
+    assert np.linalg.norm(A @ fue[u] - Vi.sum(0)) <= 1e-5 * np.linalg.norm(Vi.sum(0))

@@ -3,5 +3,7 @@ on the B200 engine.  ``from single import *`` + ``train.py:3-16`` run unchanged.
 from .rec import REC
 from .bpr import BPR
 from .vbpr import VBPR
+from .wmf import WMF
+from .cer import CER
 
-__all__ = ['REC', 'BPR', 'VBPR']
+__all__ = ['REC', 'BPR', 'VBPR', 'WMF', 'CER']

@@ -30,6 +30,17 @@ class tkr_sampler(C.Structure):
                 ("pos_idx", C.c_void_p), ("n_items", C.c_int32), ("seed", C.c_uint64)]
 
 
+class tkr_als_cfg(C.Structure):
+    _fields_ = [("d", C.c_int32), ("a", C.c_float), ("b", C.c_float), ("ridge", C.c_float), ("lreg", C.c_float),
+                ("solve_empty", C.c_int32), ("item_loss", C.c_int32)]
+
+
+class tkr_als_plan(C.Structure):
+    _fields_ = [("n_segs", C.c_int64), ("seg_row", C.c_void_p), ("seg_off", C.c_void_p), ("seg_len", C.c_void_p),
+                ("seg_slot", C.c_void_p), ("n_multi", C.c_int64), ("multi_row", C.c_void_p), ("multi_slot0", C.c_void_p),
+                ("multi_nslots", C.c_void_p), ("multi_total", C.c_void_p), ("n_slots", C.c_int64)]
+
+
 _lib = None
 
 
@@ -75,7 +86,11 @@ def lib():
     L.tkr_dat_read.argtypes = [C.c_char_p, vp, i64, i64]
     L.tkr_dat_write.argtypes = [C.c_char_p, vp, i64, i64]
     L.tkr_ratings_parse.argtypes = [C.c_char_p] * 3 + [C.POINTER(C.c_int64)] * 2 + [vp] * 4
-    for name in ("tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    L.tkr_als_partial_bytes.restype = sz; L.tkr_als_partial_bytes.argtypes = [i32, i64]
+    L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
+    L.tkr_als_gram.argtypes = [vp, i32, vp, i64, C.c_float, C.c_float, vp, vp, sz, vp]
+    L.tkr_als_solve_rows.argtypes = [C.POINTER(tkr_als_cfg), C.POINTER(tkr_als_plan), vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    for name in ("tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
