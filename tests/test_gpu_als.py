@@ -106,7 +106,7 @@ def test_user_and_item_steps_match_oracle(d, seg, init):
     torch.cuda.synchronize()
     tol = bound(ref_u, exact64_step(fue, fie, u_ptr, u_idx, i_rated, a, b, lu, 0.0)) if init == "uniform" or d >= 100 else TOL
     assert rel(U.cpu().numpy(), ref_u.astype(np.float64)) <= tol
-    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * (abs(loss_ref) + a * u_idx.size)      # terms of size a*nnz cancel in the item loss
     empty = np.flatnonzero(np.diff(u_ptr) == 0)
     assert np.array_equal(U.cpu().numpy()[empty], fue[empty])                # users without positives keep their row
 
@@ -119,7 +119,7 @@ def test_user_and_item_steps_match_oracle(d, seg, init):
     lr = topkrec.als_solve_rows(its, U0, Vc, XXv, a, b, lv, lv, prior=torch.from_numpy(Fe).cuda(), solve_empty=True, item_loss=True)
     tol = bound(ref_v, exact64_step(fie, ref_u, i_ptr, i_idx, u_rated, a, b, 0.0, lv, Fe, True)) if init == "uniform" or d >= 100 else TOL
     assert rel(Vc.cpu().numpy(), ref_v.astype(np.float64)) <= tol
-    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * (abs(loss_ref) + a * u_idx.size)      # terms of size a*nnz cancel in the item loss
 
     # item half-step, WMF flavour (wmf.py:78-96): ridge only, unrated items untouched
     ref_v = fie.copy()
@@ -128,7 +128,7 @@ def test_user_and_item_steps_match_oracle(d, seg, init):
     lr = topkrec.als_solve_rows(its, U0, Vw, XXv, a, b, 0.01, 0.01, item_loss=True)
     tol = bound(ref_v, exact64_step(fie, ref_u, i_ptr, i_idx, u_rated, a, b, 0.0, 0.01)) if init == "uniform" or d >= 100 else TOL
     assert rel(Vw.cpu().numpy(), ref_v.astype(np.float64)) <= tol
-    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * abs(loss_ref)
+    assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * (abs(loss_ref) + a * u_idx.size)      # terms of size a*nnz cancel in the item loss
 
 
 def test_split_rows_are_deterministic_and_agree_with_fused():
@@ -143,7 +143,7 @@ def test_split_rows_are_deterministic_and_agree_with_fused():
         topkrec.als_solve_rows(topkrec.AlsSide(ptr, idx, seg), Y, X, base, 1.0, 0.01, 0.0, 0.01)
         outs.append(X.cpu().numpy())
     assert np.array_equal(outs[1], outs[2])
-    assert rel(outs[1], outs[0].astype(np.float64)) <= 2e-5 and rel(outs[3], outs[0].astype(np.float64)) <= 2e-5
+    assert rel(outs[1], outs[0].astype(np.float64)) <= TOL and rel(outs[3], outs[0].astype(np.float64)) <= TOL   # summation order only
 
 
 def _golden_model(golden, iters):

@@ -29,10 +29,18 @@ constexpr int STAGES = 3;
 template <int NB> struct Geo {
     static constexpr int DP = 64 * NB;                 // padded width
     static constexpr int NBLK = NB * (NB + 1) / 2;     // lower-triangular 64x64 blocks
-    static constexpr int NT = NBLK * 64;               // threads per block
-    static constexpr int PACKED = DP * (DP + 1) / 2;   // packed lower triangle (column-major)
+    // rows of a thread's register tile (columns: always 8).  16 x 8 tiles on 320 threads would halve the shared-memory
+    // reads per FMA at NB = 4, but 10 warps put 3 on one scheduler partition (16 K registers): 168 registers per thread
+    // at most, not enough next to 128 accumulators (measured: 1.2 KB of spills).  So 8 x 8 everywhere.
+    static constexpr int TR = 8;
+    static constexpr int RS = 32;                      // row register i sits at r0 + (i & 3) + (i >> 2) * RS
+    static constexpr int TPB = 512 / TR;               // threads per 64x64 block
+    static constexpr int NT = NBLK * TPB;              // threads per thread block
+    static constexpr int MAXREG = NB == 4 ? 96 : 168;  // register budget: 6 / 2 / 1 / 1 resident blocks per SM
+    static constexpr int NP = DP / 4;                  // 4-column panels of the factor
+    static constexpr int PACKED = DP * DP / 2 + 2 * DP;// floats of the factor: panel p keeps a float4 per row 4p..DP-1
     static constexpr int PART = NBLK * 4096 + DP;      // floats per partial slot
-    static constexpr size_t SMEM = (size_t)(PACKED + STAGES * KC * DP + 2 * DP + 64) * sizeof(float);
+    static constexpr size_t SMEM = (size_t)(PACKED + STAGES * KC * DP + 4 * DP + 2 * DP + 16 + 64 + 3 * DP) * sizeof(float);
 };
 
 struct RowArgs {
@@ -61,12 +69,12 @@ __device__ __forceinline__ void named_barrier(int id, int nthreads) {
 // thread -> tile geometry
 struct Tile {
     int I, J;        // block coordinates (I >= J)
-    int r0, c0;      // first row / column of the tile; register index q maps to x0 + (q & 3) + (q >> 2) * 32
+    int r0, c0;      // first row / column of the tile (see row_pos / reg_pos)
     int tx;
 };
-__device__ __forceinline__ Tile tile_of(int tid) {
+template <int NB> __device__ __forceinline__ Tile tile_of(int tid) {
     Tile t;
-    const int blk = tid >> 6, u = tid & 63;
+    const int blk = tid / Geo<NB>::TPB, u = tid % Geo<NB>::TPB;
     int I = 0;
     while ((I + 1) * (I + 2) / 2 <= blk) ++I;
     t.I = I; t.J = blk - I * (I + 1) / 2;
@@ -75,27 +83,46 @@ __device__ __forceinline__ Tile tile_of(int tid) {
     t.c0 = t.J * 64 + t.tx * 4;
     return t;
 }
-__device__ __forceinline__ int reg_pos(int x0, int q) { return x0 + (q & 3) + (q >> 2) * 32; }
+__device__ __forceinline__ int reg_pos(int x0, int q) { return x0 + (q & 3) + (q >> 2) * 32; }           // column register q
+template <int NB> __device__ __forceinline__ int row_pos(int r0, int i) { return r0 + (i & 3) + (i >> 2) * Geo<NB>::RS; }   // row register i
 
 // acc += sum over rows list[0..n) of y y^T (this thread's tile); ssum += column tid of the same rows.
 template <int NB>
-__device__ __forceinline__ void gram_accumulate(float (&acc)[8][8], float& ssum, const Tile& t, const float* __restrict__ Y,
+__device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], float& ssum, const Tile& t, const float* __restrict__ Y,
                                                 int d, const int32_t* __restrict__ list, int64_t n, float* stage) {
     using G = Geo<NB>;
+    constexpr int EPT = (KC * (G::DP / 4) + G::NT - 1) / G::NT;   // 16-byte pieces of a stage per thread (upper bound)
     const int tid = threadIdx.x;
     const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const int64_t nchunks = (n + KC - 1) / KC;
+    // vector path: piece e = tid + i*NT of every stage is (row e / q, floats 4*(e % q)..+3); the row's index is fetched
+    // one stage ahead of its cp.async so the gather never waits on the index load
+    int prow[EPT], pcol[EPT], pidx[EPT];
+    const int q = d >> 2;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+        const int e = tid + i * G::NT;
+        prow[i] = (vec && e < KC * q) ? e / q : KC;
+        pcol[i] = (e - prow[i] * q) * 4;
+        pidx[i] = 0;
+    }
+    auto fetch_idx = [&](int64_t c) {
+        if (vec && c < nchunks) {
+            const int rows = (int)min((int64_t)KC, n - c * KC);
+#pragma unroll
+            for (int i = 0; i < EPT; ++i)
+                if (prow[i] < rows) pidx[i] = list[c * KC + prow[i]];
+        }
+    };
     auto issue = [&](int64_t c) {
         if (c < nchunks) {
             const int rows = (int)min((int64_t)KC, n - c * KC);
             const uint32_t buf = stage_s + (uint32_t)((c % STAGES) * KC * G::DP) * 4u;
             if (vec) {
-                const int q = d >> 2;
-                for (int e = tid; e < rows * q; e += G::NT) {
-                    const int r = e / q, c4 = e - r * q;
-                    cp_async16(buf + (uint32_t)(r * G::DP + c4 * 4) * 4u, Y + (size_t)list[c * KC + r] * d + c4 * 4);
-                }
+#pragma unroll
+                for (int i = 0; i < EPT; ++i)
+                    if (prow[i] < rows) cp_async16(buf + (uint32_t)(prow[i] * G::DP + pcol[i]) * 4u, Y + (size_t)pidx[i] * d + pcol[i]);
             } else {
                 for (int e = tid; e < rows * d; e += G::NT) {
                     const int r = e / d, cc = e - r * d;
@@ -105,25 +132,30 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[8][8], float& ssum,
         }
         cp_async_commit();
     };
+    fetch_idx(0);
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    for (int s = 0; s < STAGES - 1; ++s) { issue(s); fetch_idx(s + 1); }
     for (int64_t c = 0; c < nchunks; ++c) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         issue(c + STAGES - 1);
+        fetch_idx(c + STAGES);
         const float* buf = stage + (c % STAGES) * KC * G::DP;
         const int rows = (int)min((int64_t)KC, n - c * KC);
 #pragma unroll 2
         for (int k = 0; k < rows; ++k) {
             const float* y = buf + k * G::DP;
-            const float4 a0 = *reinterpret_cast<const float4*>(y + t.r0), a1 = *reinterpret_cast<const float4*>(y + t.r0 + 32);
             const float4 b0 = *reinterpret_cast<const float4*>(y + t.c0), b1 = *reinterpret_cast<const float4*>(y + t.c0 + 32);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int gi = 0; gi < G::TR / 4; ++gi) {
+                const float4 a4 = *reinterpret_cast<const float4*>(y + t.r0 + gi * G::RS);
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[gi * 4 + i][j] = fmaf(av[i], bv[j], acc[gi * 4 + i][j]);
+            }
             if (tid < G::DP) ssum += y[tid];
         }
     }
@@ -132,24 +164,24 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[8][8], float& ssum,
 }
 
 template <int NB>
-__device__ __forceinline__ void store_partial(const float (&acc)[8][8], float ssum, float* slot) {
+__device__ __forceinline__ void store_partial(const float (&acc)[Geo<NB>::TR][8], float ssum, float* slot) {
     using G = Geo<NB>;
-    const int tid = threadIdx.x, blk = tid >> 6, u = tid & 63;
+    const int tid = threadIdx.x, blk = tid / G::TPB, u = tid % G::TPB;
     float4* p = reinterpret_cast<float4*>(slot) + (size_t)blk * 1024 + u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        p[(i * 2) * 64] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        p[(i * 2 + 1) * 64] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    for (int i = 0; i < G::TR; ++i) {
+        p[(i * 2) * G::TPB] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        p[(i * 2 + 1) * G::TPB] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
     if (tid < G::DP) slot[G::NBLK * 4096 + tid] = ssum;
 }
 template <int NB>
-__device__ __forceinline__ void add_partial(float (&acc)[8][8], float& ssum, const float* slot, int blk, int u, bool with_sum) {
+__device__ __forceinline__ void add_partial(float (&acc)[Geo<NB>::TR][8], float& ssum, const float* slot, int blk, int u, bool with_sum) {
     using G = Geo<NB>;
     const float4* p = reinterpret_cast<const float4*>(slot) + (size_t)blk * 1024 + u;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float4 lo = p[(i * 2) * 64], hi = p[(i * 2 + 1) * 64];
+    for (int i = 0; i < G::TR; ++i) {
+        const float4 lo = p[(i * 2) * G::TPB], hi = p[(i * 2 + 1) * G::TPB];
         acc[i][0] += lo.x; acc[i][1] += lo.y; acc[i][2] += lo.z; acc[i][3] += lo.w;
         acc[i][4] += hi.x; acc[i][5] += hi.y; acc[i][6] += hi.z; acc[i][7] += hi.w;
     }
@@ -187,35 +219,173 @@ __device__ __forceinline__ void row_loss(const RowArgs& p, int row, int64_t n, b
     }
 }
 
-// Build A from the accumulated Gram, factor it (L D L^T in registers), solve, write the row and its loss.
-template <int NB>
-__device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n, float (&acc)[8][8], float ssum, const Tile& t,
-                                           float* M, float* zs, float* xs, float* red) {
+template <int NB> struct Smem {
     using G = Geo<NB>;
-    const int tid = threadIdx.x, d = p.d;
+    float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep;
+    __device__ explicit Smem(float* base) {
+        M = base; stage = M + G::PACKED;     // PACKED * 4 bytes is a multiple of 16 for every DP
+        raw = stage + STAGES * KC * G::DP; zs = raw + 4 * G::DP; xs = zs + G::DP; d44 = xs + G::DP; red = d44 + 16; keep = red + 64;
+    }
+};
+
+// A = L D L^T four columns per round (see finish_row), then back substitution; z = right-hand side entry of thread
+// tid < DP on entry, x = solution entry on exit.
+template <int NB>
+__device__ __forceinline__ void factor_solve_panels(float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, float z, float& x) {
+    using G = Geo<NB>;
+    const int tid = threadIdx.x;
+    float4* const L4 = reinterpret_cast<float4*>(sm.M);
+    float4* const R4 = reinterpret_cast<float4*>(sm.raw);
+    const int rmax = row_pos<NB>(t.r0, G::TR - 1), cmax = t.c0 + 35;
+    const bool on_diag_block = t.I == t.J;
+    const int ty4 = t.r0 - t.I * 64;            // 4 * ty
+    float pinv_mine = 1.f;                      // 1 / D[tid]
+    int poff = 0;                               // float4 offset of the round's panel in the factor
+    int j0 = 0;
+    for (int Jb = 0; Jb < NB; ++Jb) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = reg_pos(t.r0, i);
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll 1
+            for (int tq = 0; tq < 8; ++tq) {
+                const bool owner = t.J == Jb && t.tx == tq;
+                // ---- A
+                if (owner && on_diag_block && ty4 == (G::TR == 8 ? tq : (tq & 3)) * 4) {
+                    const bool th = G::TR == 16 && (tq >> 2);     // which of the two candidate row groups holds rows j0..j0+3
+                    auto dg = [&](int qr, int qc) -> float {
+                        if (G::TR == 8) return acc[g * 4 + qr][g * 4 + qc];
+                        return th ? acc[((2 * g + 1) * 4 + qr) % G::TR][g * 4 + qc] : acc[((2 * g) * 4 + qr) % G::TR][g * 4 + qc];
+                    };
+                    float a00 = dg(0, 0);
+                    float a10 = dg(1, 0), a11 = dg(1, 1);
+                    float a20 = dg(2, 0), a21 = dg(2, 1), a22 = dg(2, 2);
+                    float a30 = dg(3, 0), a31 = dg(3, 1), a32 = dg(3, 2), a33 = dg(3, 3);
+                    const float i0 = __frcp_rn(a00);
+                    const float l10 = a10 * i0, l20 = a20 * i0, l30 = a30 * i0;
+                    a11 = fmaf(-l10, a10, a11); a21 = fmaf(-l20, a10, a21); a31 = fmaf(-l30, a10, a31);
+                    a22 = fmaf(-l20, a20, a22); a32 = fmaf(-l30, a20, a32); a33 = fmaf(-l30, a30, a33);
+                    const float i1 = __frcp_rn(a11);
+                    const float l21 = a21 * i1, l31 = a31 * i1;
+                    a22 = fmaf(-l21, a21, a22); a32 = fmaf(-l31, a21, a32); a33 = fmaf(-l31, a31, a33);
+                    const float i2 = __frcp_rn(a22);
+                    const float l32 = a32 * i2;
+                    a33 = fmaf(-l32, a32, a33);
+                    const float i3 = __frcp_rn(a33);
+                    float4* o = reinterpret_cast<float4*>(sm.d44);
+                    o[0] = make_float4(i0, i1, i2, i3);
+                    o[1] = make_float4(l10, l20, l30, l21);
+                    o[2] = make_float4(l31, l32, 0.f, 0.f);
+                    L4[poff + 0] = make_float4(0.f, 0.f, 0.f, 0.f);      // rows of the diagonal block: L entries left of the diagonal
+                    L4[poff + 1] = make_float4(l10, 0.f, 0.f, 0.f);
+                    L4[poff + 2] = make_float4(l20, l21, 0.f, 0.f);
+                    L4[poff + 3] = make_float4(l30, l31, l32, 0.f);
+                }
+                if (tid >= j0 && tid < j0 + 4) sm.zs[tid] = z;
+                __syncthreads();
+                // ---- B
+                const float4 di = reinterpret_cast<const float4*>(sm.d44)[0];
+                const float4 la = reinterpret_cast<const float4*>(sm.d44)[1];
+                const float4 lb = reinterpret_cast<const float4*>(sm.d44)[2];
+                const float l10 = la.x, l20 = la.y, l30 = la.z, l21 = la.w, l31 = lb.x, l32 = lb.y;
+                if (owner) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = reg_pos(t.c0, j);
-            float v;
-            if (r < d && c < d) v = fmaf(p.amb, acc[i][j], __ldg(p.base + (size_t)r * d + c)) + (r == c ? p.ridge : 0.f);
-            else v = (r == c) ? 1.f : 0.f;
-            acc[i][j] = v;
+                    for (int i = 0; i < G::TR; ++i) {
+                        const int r = row_pos<NB>(t.r0, i);
+                        if (r > j0 + 3) {
+                            const float m0 = acc[i][g * 4 + 0];
+                            const float m1 = fmaf(-m0, l10, acc[i][g * 4 + 1]);
+                            const float m2 = fmaf(-m1, l21, fmaf(-m0, l20, acc[i][g * 4 + 2]));
+                            const float m3 = fmaf(-m2, l32, fmaf(-m1, l31, fmaf(-m0, l30, acc[i][g * 4 + 3])));
+                            R4[r] = make_float4(m0, m1, m2, m3);
+                            L4[poff + r - j0] = make_float4(m0 * di.x, m1 * di.y, m2 * di.z, m3 * di.w);
+                        }
+                    }
+                }
+                float zq0 = 0.f, zq1 = 0.f, zq2 = 0.f, zq3 = 0.f;
+                if (tid < G::DP) {
+                    const float4 zz = *reinterpret_cast<const float4*>(sm.zs + j0);
+                    zq0 = zz.x;
+                    zq1 = fmaf(-l10, zq0, zz.y);
+                    zq2 = fmaf(-l21, zq1, fmaf(-l20, zq0, zz.z));
+                    zq3 = fmaf(-l32, zq2, fmaf(-l31, zq1, fmaf(-l30, zq0, zz.w)));
+                    if (tid >= j0 && tid < j0 + 4) {
+                        const int qq = tid - j0;
+                        z = qq == 0 ? zq0 : qq == 1 ? zq1 : qq == 2 ? zq2 : zq3;
+                        pinv_mine = qq == 0 ? di.x : qq == 1 ? di.y : qq == 2 ? di.z : di.w;
+                    }
+                }
+                __syncthreads();
+                // ---- C
+                if (tid > j0 + 3 && tid < G::DP) {
+                    const float4 lz = L4[poff + tid - j0];
+                    z = fmaf(-lz.w, zq3, fmaf(-lz.z, zq2, fmaf(-lz.y, zq1, fmaf(-lz.x, zq0, z))));
+                }
+                if (rmax > j0 + 3 && cmax > j0 + 3) {
+                    const float4* lrow = L4 + poff - j0 + t.r0;     // rows <= j0+3 read earlier panels (valid memory) and are zeroed
+                    const bool edge = t.r0 <= j0 + 3 || t.c0 <= j0 + 3;
+                    constexpr int CW = 4;                           // columns per pass
+#pragma unroll
+                    for (int h = 0; h < 8 / CW; ++h) {              // column registers CW*h .. CW*h + CW-1
+                        float4 mc[CW];
+#pragma unroll
+                        for (int jj = 0; jj < CW; ++jj) {
+                            const int cq = h * CW + jj, c = t.c0 + (cq & 3) + (cq >> 2) * 32;
+                            mc[jj] = R4[c];
+                            if (edge && c <= j0 + 3) mc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < G::TR; ++i) {
+                            float4 lr = lrow[(i & 3) + (i >> 2) * G::RS];
+                            if (edge && t.r0 + (i & 3) + (i >> 2) * G::RS <= j0 + 3) lr = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int jj = 0; jj < CW; ++jj) {
+                                float v = acc[i][h * CW + jj];
+                                v = fmaf(-lr.x, mc[jj].x, v); v = fmaf(-lr.y, mc[jj].y, v);
+                                v = fmaf(-lr.z, mc[jj].z, v); v = fmaf(-lr.w, mc[jj].w, v);
+                                acc[i][h * CW + jj] = v;
+                            }
+                        }
+                    }
+                }
+                poff += G::DP - j0;
+                j0 += 4;
+            }
         }
     }
-    float pr = 0.f, z = 0.f;
-    if (tid < d) {
-        if (p.prior) pr = p.prior[(size_t)row * d + tid];
-        z = fmaf(p.a, ssum, p.ridge * pr);      // a * sum_p y_p + ridge * prior  (cer.py:43,55)
+    // back substitution, four rows per round from the bottom: x_j = z_j / D_j - sum_{r > j} L[r][j] x_r
+    if (tid < G::DP) {
+        float w = z * pinv_mine;
+        const int myp = tid >> 2, myq = tid & 3;
+        const float* mycol = sm.M + (size_t)(myp * G::DP - 2 * myp * (myp - 1) - 4 * myp) * 4 + myq;   // + 4*r: L[r][tid]
+        for (int pp = G::NP - 1; pp >= 0; --pp) {
+            const int b0 = pp * 4;
+            if (myp == pp) sm.xs[tid] = w;
+            named_barrier(1, G::DP);
+            const int po = pp * G::DP - 2 * pp * (pp - 1);
+            const float4 ww = *reinterpret_cast<const float4*>(sm.xs + b0);
+            const float4 r1 = L4[po + 1], r2 = L4[po + 2], r3 = L4[po + 3];
+            const float x3 = ww.w;
+            const float x2 = fmaf(-r3.z, x3, ww.z);
+            const float x1 = fmaf(-r3.y, x3, fmaf(-r2.y, x2, ww.y));
+            const float x0 = fmaf(-r3.x, x3, fmaf(-r2.x, x2, fmaf(-r1.x, x1, ww.x)));
+            if (myp == pp) x = myq == 0 ? x0 : myq == 1 ? x1 : myq == 2 ? x2 : x3;
+            if (myp < pp) {
+                const float* c = mycol + 4 * b0;
+                w = fmaf(-c[12], x3, fmaf(-c[8], x2, fmaf(-c[4], x1, fmaf(-c[0], x0, w))));
+            }
+        }
     }
-    const float rhs0 = z;
-    // Column j of the factor is published at M + j*DP - j(j-1)/2 (packed, column-major); `col - j` is the column's
-    // virtual row 0, so a tile addresses its rows / columns with compile-time offsets.  Reads at rows < j land in
-    // earlier columns (valid shared memory) and are discarded by the select.
+}
+
+// The same factorisation one column per barrier (the variant for NB = 4, whose 96-register budget has no room for the
+// rank-4 update's operands): the owners of column j publish it raw (M, packed column-major: column j at
+// M + j*DP - j(j-1)/2, `col - j` = the column's virtual row 0), one barrier, every tile below/right applies the rank-1
+// update M_r M_c / D_j; the right-hand side rides along; back substitution walks the packed columns.
+template <int NB>
+__device__ __forceinline__ void factor_solve_columns(float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, float z, float& x) {
+    using G = Geo<NB>;
+    const int tid = threadIdx.x;
     const int rmax = t.r0 + 35, cmax = t.c0 + 35;
-    float* col = M;
+    float* col = sm.M;
     int j = 0;
     for (int Jb = 0; Jb < NB; ++Jb) {
 #pragma unroll
@@ -236,11 +406,11 @@ __device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n,
                                 if (t.r0 + (i & 3) + (i >> 2) * 32 >= j) pw[(i & 3) + (i >> 2) * 32] = acc[i][cj];
                         }
                     }
-                    if (tid == j) zs[j] = z;
+                    if (tid == j) sm.zs[j] = z;
                     __syncthreads();
                     const float inv = 1.0f / col[0];
                     if (rmax > j && cmax > j) {
-                        const float* pr = col - j + t.r0;
+                        const float* pr = col - j + t.r0;     // rows <= j read earlier columns (valid memory) and are zeroed
                         const float* pc = col - j + t.c0;
                         float cr[8], cc[8];
 #pragma unroll
@@ -260,27 +430,66 @@ __device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n,
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(-cr[i], cc[jj], acc[i][jj]);
                     }
-                    if (tid > j && tid < G::DP) z = fmaf(-col[tid - j] * inv, zs[j], z);
+                    if (tid > j && tid < G::DP) z = fmaf(-col[tid - j] * inv, sm.zs[j], z);
                     col += G::DP - j;
                     ++j;
                 }
             }
         }
     }
-    // back substitution: x_r = (z_r - sum_{q > r} M[q][r] x_q) / p_r, walking r downwards; thread c keeps z_c - (partial sum)
-    float x = 0.f;
+    // x_r = (z_r - sum_{q > r} M[q][r] x_q) / D_r, walking r downwards; thread c keeps z_c - (partial sum)
     if (tid < G::DP) {
-        const float* mycol = M + ((size_t)tid * G::DP - (size_t)tid * (tid - 1) / 2);
+        const float* mycol = sm.M + ((size_t)tid * G::DP - (size_t)tid * (tid - 1) / 2);
         const float pinv = 1.0f / mycol[0];
         for (int r = G::DP - 1; r >= 0; --r) {
-            if (tid == r) { x = z * pinv; xs[r] = x; }
+            if (tid == r) { x = z * pinv; sm.xs[r] = x; }
             named_barrier(1, G::DP);
-            if (tid < r) z = fmaf(-mycol[r - tid], xs[r], z);
+            if (tid < r) z = fmaf(-mycol[r - tid], sm.xs[r], z);
         }
+    }
+}
+
+// Build A from the accumulated Gram, factor it (A = L D L^T, in registers, four columns per round), solve, write the
+// row and its loss.  One round for columns j0..j0+3:
+//   A  the thread holding the 4x4 diagonal block factors it and publishes 1/D and the six L entries; threads j0..j0+3
+//      publish their right-hand-side entries                                                            -- barrier --
+//   B  the threads holding those columns eliminate the block from their rows (raw M and scaled L = M/D, a float4 per
+//      row each: M into a transient buffer, L into the factor, which back substitution reads later)      -- barrier --
+//   C  every tile to the right/below applies the rank-4 update from L (its rows) and M (its columns); the right-hand
+//      side does the same (forward substitution rides along).
+template <int NB>
+__device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n, float (&acc)[Geo<NB>::TR][8], float ssum, const Tile& t,
+                                           const Smem<NB>& sm) {
+    using G = Geo<NB>;
+    const int tid = threadIdx.x, d = p.d;
+#pragma unroll
+    for (int i = 0; i < G::TR; ++i) {
+        const int r = row_pos<NB>(t.r0, i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = reg_pos(t.c0, j);
+            float v;
+            if (r < d && c < d) v = fmaf(p.amb, acc[i][j], __ldg(p.base + (size_t)r * d + c)) + (r == c ? p.ridge : 0.f);
+            else v = (r == c) ? 1.f : 0.f;
+            acc[i][j] = v;
+        }
+    }
+    float pr = 0.f, z = 0.f;
+    if (tid < d) {
+        if (p.prior) pr = p.prior[(size_t)row * d + tid];
+        z = fmaf(p.a, ssum, p.ridge * pr);      // a * sum_p y_p + ridge * prior  (cer.py:43,55)
+    }
+    if (tid < G::DP) { sm.keep[tid] = z; sm.keep[G::DP + tid] = pr; sm.keep[2 * G::DP + tid] = ssum; }   // read back for the loss
+    float x = 0.f;
+    if constexpr (NB == 4) factor_solve_columns<NB>(acc, t, sm, z, x);
+    else factor_solve_panels<NB>(acc, t, sm, z, x);
+    if (tid < G::DP) {
         if (tid < d) p.X[(size_t)row * d + tid] = x;
     }
     __syncthreads();
-    row_loss<NB>(p, row, n, true, x, rhs0, ssum, pr, red);
+    float rhs0 = 0.f;
+    if (tid < G::DP) { rhs0 = sm.keep[tid]; pr = sm.keep[G::DP + tid]; ssum = sm.keep[2 * G::DP + tid]; }
+    row_loss<NB>(p, row, n, true, x, rhs0, ssum, pr, sm.red);
 }
 
 template <int NB>
@@ -294,18 +503,9 @@ __device__ __forceinline__ void loss_only_row(const RowArgs& p, int row, float* 
     row_loss<NB>(p, row, 0, false, x, 0.f, 0.f, pr, red);
 }
 
-template <int NB> struct Smem {
-    using G = Geo<NB>;
-    float* M; float* stage; float* zs; float* xs; float* red;
-    __device__ explicit Smem(float* base) {
-        M = base; stage = M + G::PACKED; stage = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(stage) + 15) & ~(uintptr_t)15);
-        zs = stage + STAGES * KC * G::DP; xs = zs + G::DP; red = xs + G::DP;
-    }
-};
-
 // kernel 1: one block per segment
 template <int NB>
-__global__ void __launch_bounds__(Geo<NB>::NT, 1) als_segment_kernel(const RowArgs p) {
+__global__ void __launch_bounds__(Geo<NB>::NT) __maxnreg__(Geo<NB>::MAXREG) als_segment_kernel(const RowArgs p) {
     using G = Geo<NB>;
     extern __shared__ __align__(16) float smem_raw[];
     Smem<NB> sm(smem_raw);
@@ -317,10 +517,10 @@ __global__ void __launch_bounds__(Geo<NB>::NT, 1) als_segment_kernel(const RowAr
     }
     for (int e = tid; e < STAGES * KC * G::DP; e += G::NT) sm.stage[e] = 0.f;   // pad columns stay zero
     __syncthreads();
-    const Tile t = tile_of(tid);
-    float acc[8][8];
+    const Tile t = tile_of<NB>(tid);
+    float acc[G::TR][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < G::TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float ssum = 0.f;
@@ -329,45 +529,45 @@ __global__ void __launch_bounds__(Geo<NB>::NT, 1) als_segment_kernel(const RowAr
         store_partial<NB>(acc, ssum, p.partial + (size_t)slot * G::PART);
         return;
     }
-    finish_row<NB>(p, row, len, acc, ssum, t, sm.M, sm.zs, sm.xs, sm.red);
+    finish_row<NB>(p, row, len, acc, ssum, t, sm);
 }
 
 // kernel 2: one block per split row: ordered sum of its partial slots, then the same finish
 template <int NB>
-__global__ void __launch_bounds__(Geo<NB>::NT, 1) als_multi_kernel(const RowArgs p) {
+__global__ void __launch_bounds__(Geo<NB>::NT) __maxnreg__(Geo<NB>::MAXREG) als_multi_kernel(const RowArgs p) {
     using G = Geo<NB>;
     extern __shared__ __align__(16) float smem_raw[];
     Smem<NB> sm(smem_raw);
     const int m = blockIdx.x, tid = threadIdx.x;
     const int row = p.multi_row[m], slot0 = p.multi_slot0[m], ns = p.multi_nslots[m];
-    const Tile t = tile_of(tid);
-    float acc[8][8];
+    const Tile t = tile_of<NB>(tid);
+    float acc[G::TR][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < G::TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float ssum = 0.f;
-    for (int s = 0; s < ns; ++s) add_partial<NB>(acc, ssum, p.partial + (size_t)(slot0 + s) * G::PART, tid >> 6, tid & 63, true);
-    finish_row<NB>(p, row, p.multi_total[m], acc, ssum, t, sm.M, sm.zs, sm.xs, sm.red);
+    for (int s = 0; s < ns; ++s) add_partial<NB>(acc, ssum, p.partial + (size_t)(slot0 + s) * G::PART, tid / G::TPB, tid % G::TPB, true);
+    finish_row<NB>(p, row, p.multi_total[m], acc, ssum, t, sm);
 }
 
 // shared Gram: out[d,d] = scale * sum of n_slots partial matrices + ridge * I  (one 64-thread block per 64x64 block)
 template <int NB>
-__global__ void __launch_bounds__(64) als_gram_reduce_kernel(const float* partial, int n_slots, int d, float scale, float ridge,
+__global__ void __launch_bounds__(Geo<NB>::TPB) als_gram_reduce_kernel(const float* partial, int n_slots, int d, float scale, float ridge,
                                                             float* out) {
     using G = Geo<NB>;
     const int blk = blockIdx.x, u = threadIdx.x;
-    const Tile t = tile_of(blk * 64 + u);
-    float acc[8][8];
+    const Tile t = tile_of<NB>(blk * G::TPB + u);
+    float acc[G::TR][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < G::TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float dummy = 0.f;
     for (int s = 0; s < n_slots; ++s) add_partial<NB>(acc, dummy, partial + (size_t)s * G::PART, blk, u, false);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int r = reg_pos(t.r0, i);
+    for (int i = 0; i < G::TR; ++i) {
+        const int r = row_pos<NB>(t.r0, i);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = reg_pos(t.c0, j);
@@ -413,7 +613,7 @@ template <int NB> static int launch_gram(const RowArgs& p, int64_t n_segs, int d
     if (rc) return rc;
     als_segment_kernel<NB><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);
     TKR_LAUNCH_CHECK();
-    als_gram_reduce_kernel<NB><<<G::NBLK, 64, 0, st>>>(p.partial, (int)n_segs, d, scale, ridge, out);
+    als_gram_reduce_kernel<NB><<<G::NBLK, G::TPB, 0, st>>>(p.partial, (int)n_segs, d, scale, ridge, out);
     TKR_LAUNCH_CHECK();
     return TKR_OK;
 }
