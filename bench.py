@@ -307,6 +307,7 @@ def run_ours(args, rank, local_rank, world):
         line["sweep"] = bpr_sweep(cfg, st, smp, dev)
         line["sweep"].append(bpr_hbm_streaming(dev))
         line["vbpr"] = vbpr_points(smp, dev)
+        line["als"] = als_points(dev, cpu=not args.skip_cpu)
     if rank == 0 and world == 1 and not args.skip_cpu:
         # bounded CPU sample: ~10-30 s of the OpenMP port on the same workload
         v1, ms1, threads = cpu_bpr_steps(min(B, 1 << 20), 1, 1)
@@ -425,6 +426,77 @@ def vbpr_points(smp, dev, d_feat=4096, k=128):
         out.append({"batch_size": B, "us_per_step": 1e3 * ms, "triples_per_sec": B / (ms / 1e3),
                     "config": "VBPR %d users x %d items, k=%d (%d + %d), %d-d dense features resident (%.0f MB)" % (N_USERS, N_ITEMS, k, h, h, d_feat, N_ITEMS * d_feat * 4 / 1e6)})
         del ws
+    return out
+
+
+def als_points(dev, d=256, n_users=480189 // 8, n_items=17770, mean_pos=208, reps=3, cpu_rows=96, cpu=True):
+    """BASELINE configs[3] (CER/WMF, Netflix shape 480 189 users x 17 770 items, d=256): one ALS iteration
+    (single/cer.py:36-63 without the content terms = the intended single/wmf.py:67-96) on ONE GPU's share of the
+    8-GPU run -- 1/8 of the users, all items -- with Zipf item popularity and ~208 positives per user (100 M / 480 k).
+    Device-timed per half-step; FLOP are the reference algorithm's (np.dot(Vi.T, Vi) = 2 n d^2 per row, solve = 2/3 d^3);
+    the kernel itself computes the lower triangle only.  Bound: the fp32 FMA pipe (nominal 148 SMs x 128 lanes x 2 x
+    1.965 GHz = 74.4 TFLOP/s); cpu_baseline = oracle/als_ref.py user half-step on a bounded sample of rows."""
+    import torch
+    import topkrec
+    rng = np.random.default_rng(0)
+    cnt = np.maximum(1, rng.poisson(mean_pos, n_users))
+    pop = 1.0 / np.arange(1, n_items + 1); cdf = np.cumsum(pop / pop.sum())
+    items = np.searchsorted(cdf, rng.random(int(cnt.sum()))).clip(0, n_items - 1).astype(np.int64)
+    users = np.repeat(np.arange(n_users, dtype=np.int64), cnt)
+    key = np.sort(users * n_items + items); key = key[np.r_[True, key[1:] != key[:-1]]]      # dedup per user
+    users, items = key // n_items, key % n_items
+    nnz = int(users.size)
+    u_ptr = np.zeros(n_users + 1, np.int64); np.cumsum(np.bincount(users, minlength=n_users), out=u_ptr[1:])
+    by_i = np.argsort(items, kind="stable")
+    i_ptr = np.zeros(n_items + 1, np.int64); np.cumsum(np.bincount(items, minlength=n_items), out=i_ptr[1:])
+    u_idx, i_idx = items.astype(np.int32), users[by_i].astype(np.int32)
+    us, its = topkrec.AlsSide(u_ptr, u_idx, 4096, dev), topkrec.AlsSide(i_ptr, i_idx, 4096, dev)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    U = torch.rand(n_users, d, device=dev, generator=g)            # the reference's start (wmf.py:55-56)
+    V = torch.rand(n_items, d, device=dev, generator=g)
+    a, b, lu, lv = 1.0, 0.01, 0.01, 0.01
+    U0, V0 = U.cpu().numpy(), V.cpu().numpy()
+
+    def iteration():
+        XX = topkrec.als_gram(V, its.rated_dev, b, lu)
+        l_u = topkrec.als_solve_rows(us, V, U, XX, a, b, 0.0, lu)
+        ev[1].record()
+        XXv = topkrec.als_gram(U, us.rated_dev, b, 0.0)
+        l_i = topkrec.als_solve_rows(its, U, V, XXv, a, b, lv, lv, item_loss=True)
+        return l_u, l_i
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tu = ti = 0.0
+    topkrec.reset_launch_count()
+    for r in range(reps + 1):
+        ev[0].record()
+        l_u, l_i = iteration()
+        ev[2].record(); torch.cuda.synchronize()
+        if r:                                                       # first iteration = warm-up
+            tu += ev[0].elapsed_time(ev[1]) / reps; ti += ev[1].elapsed_time(ev[2]) / reps
+    launches = topkrec.launch_count() // (reps + 1)
+    fl_gram = 2.0 * nnz * d * d
+    fl_u, fl_i = fl_gram + n_users * (2.0 / 3.0) * d ** 3, fl_gram + n_items * (2.0 / 3.0) * d ** 3
+    peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    out = {"config": "WMF/CER ALS, %d users (1/8 of 480 189: one GPU's share of the 8-GPU run) x %d items, d=%d, %d positives (Zipf items), a=1 b=0.01" % (n_users, n_items, d, nnz),
+           "user_step_ms": tu, "item_step_ms": ti, "iteration_ms": tu + ti, "user_rows_per_sec": n_users / (tu / 1e3),
+           "item_rows_per_sec": n_items / (ti / 1e3), "positives_per_sec": 2 * nnz / ((tu + ti) / 1e3),
+           "loss": float(l_u.sum()) + float(l_i.sum()), "gpu_launches_per_iteration": launches, "dtype": "f32",
+           "roofline": {"bound": "fp32 fma pipe", "achieved": (fl_u + fl_i) / ((tu + ti) / 1e3) / 1e12, "peak": peak,
+                        "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x 1.965 GHz", "unit": "TFLOP/s",
+                        "frac": (fl_u + fl_i) / ((tu + ti) / 1e3) / 1e12 / peak,
+                        "flop_definition": "reference algorithm: 2*nnz*d^2 + 2/3*d^3 per row, per half-step"}}
+    if not cpu:
+        return out
+    # CPU baseline: the oracle user half-step (np.dot + np.linalg.solve per row, cer.py:39-45) on the first rows
+    from oracle import als_ref
+    i_rated = np.flatnonzero(np.diff(i_ptr) > 0)
+    sub_ptr = u_ptr[:cpu_rows + 1].copy()
+    fue = U0[:cpu_rows].copy()
+    t0 = time.perf_counter()
+    als_ref.user_step(fue, V0, sub_ptr, u_idx, i_rated, a, b, lu)
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": cpu_rows / dt, "unit": "user rows/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": "%d users of the same workload (incl. one shared Gram of %d item rows), numpy restatement oracle/als_ref.py of single/cer.py:36-46" % (cpu_rows, i_rated.size)}
     return out
 
 

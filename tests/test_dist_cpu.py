@@ -12,7 +12,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from topkrec import dist as tdist
-from oracle import bpr_ref, topk_ref
+from oracle import als_ref, bpr_ref, topk_ref
 
 
 def _free_port():
@@ -85,7 +85,61 @@ def _worker_dp(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp])
+class _CpuSide:
+    def __init__(self, indptr, idx):
+        self.indptr, self.idx = indptr, idx
+
+
+def _oracle_gram(Y, rows, scale, ridge):
+    return torch.from_numpy(als_ref.shared_gram(Y.numpy(), rows.numpy(), scale, ridge))
+
+
+def _oracle_solve(side, Y, X, base, a, b, ridge, lreg, prior=None, solve_empty=False, item_loss=False):
+    """per-row restatement with the matrix handed in (cer.py:39-45 / :49-62) on a CPU slice, in place"""
+    Yn, Xn, Bn = Y.numpy(), X.numpy(), base.numpy()
+    k = Yn.shape[1]
+    loss = np.zeros(Xn.shape[0])
+    for r in range(Xn.shape[0]):
+        pos = side.idx[side.indptr[r]:side.indptr[r + 1]]
+        if len(pos) or solve_empty:
+            Yi = Yn[pos]
+            rhs = np.sum(Yi, axis=0) * a + (prior[r].numpy() * ridge if prior is not None else 0)
+            Xn[r] = np.linalg.solve(np.dot(Yi.T, Yi) * (a - b) + Bn + np.eye(k, dtype=np.float32) * ridge, rhs)
+        loss[r] = 0.5 * lreg * np.sum(Xn[r] ** 2)
+    return torch.from_numpy(loss)
+
+
+def _worker_als(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(4)
+    nu, ni, d = 37, 21, 6
+    cnt = rng.integers(0, 9, nu); cnt[3] = 40
+    u_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    u_idx = rng.integers(0, ni - 2, int(u_ptr[-1])).astype(np.int32)
+    users = np.repeat(np.arange(nu), cnt)
+    by_i = np.argsort(u_idx, kind="stable")
+    i_ptr = np.zeros(ni + 1, np.int64); np.cumsum(np.bincount(u_idx, minlength=ni), out=i_ptr[1:])
+    i_idx = users[by_i].astype(np.int32)
+    U0, V0 = rng.random((nu, d)).astype(np.float32), rng.random((ni, d)).astype(np.float32)
+    eng = tdist.ShardedAls(u_ptr, u_idx, i_ptr, i_idx, side_fn=_CpuSide, gram_fn=_oracle_gram, solve_fn=_oracle_solve)
+    bounds = eng.bounds[0]
+    ok = bounds[0][0] == 0 and bounds[-1][1] == nu and all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+    U, V = torch.from_numpy(U0.copy()), torch.from_numpy(V0.copy())
+    for _ in range(2):
+        eng.iteration(U, V, 1.0, 0.01, 0.01, 0.01, wmf=True)
+    # unsharded: the oracle's own half-steps
+    ru, rv = U0.copy(), V0.copy()
+    u_rated = np.flatnonzero(np.diff(u_ptr) > 0); i_rated = np.flatnonzero(np.diff(i_ptr) > 0)
+    for _ in range(2):
+        als_ref.user_step(ru, rv, u_ptr, u_idx, i_rated, 1.0, 0.01, 0.01)
+        als_ref.item_step(ru, rv, i_ptr, i_idx, u_rated, 1.0, 0.01, 0.01, None)
+    ok = ok and np.array_equal(U.numpy(), ru) and np.array_equal(V.numpy(), rv)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp, _worker_als])
 def test_world2_gloo(worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -104,3 +158,12 @@ def test_shard_bounds():
     assert tdist.shard_bounds(1 << 20, 8)[-1] == (7 << 17, 1 << 20)
     b = tdist.shard_bounds(5, 8)
     assert b[0] == (0, 1) and b[-1] == (5, 5) and sum(e - s for s, e in b) == 5
+
+
+def test_balanced_row_bounds():
+    indptr = np.concatenate([[0], np.cumsum([1000] + [10] * 99)])
+    b = tdist.balanced_row_bounds(indptr, 4, row_cost=0)
+    assert b[0][0] == 0 and b[-1][1] == 100 and all(b[r][1] == b[r + 1][0] for r in range(3))
+    work = [indptr[e] - indptr[s] for s, e in b]
+    assert max(work) <= 1000 + 10 and sum(work) == indptr[-1]            # the heavy row sits alone
+    assert tdist.balanced_row_bounds(np.array([0, 0, 0]), 4) [-1][1] == 2

@@ -218,3 +218,25 @@ def test_argument_errors():
     side = topkrec.AlsSide(np.array([0, 1]), np.array([9], np.int32))
     with pytest.raises(ValueError):
         topkrec.als_solve_rows(side, torch.zeros(4, 8, device="cuda"), torch.zeros(1, 8, device="cuda"), torch.zeros(8, 8, device="cuda"), 1, 0.01, 0, 0)
+
+
+def test_sharded_engine_world1_equals_direct_calls():
+    """topkrec.dist.ShardedAls on one rank = the plain calls (bit-identical); the exchange itself is covered by the
+    gloo world-2 test in tests/test_dist_cpu.py."""
+    from topkrec import dist as tdist
+    rng = np.random.default_rng(12)
+    nu, ni, d = 300, 90, 40
+    u_ptr, u_idx = random_csr(rng, nu, ni, 30)
+    users = np.repeat(np.arange(nu), np.diff(u_ptr))
+    by_i = np.argsort(u_idx, kind="stable")
+    i_ptr = np.zeros(ni + 1, np.int64); np.cumsum(np.bincount(u_idx, minlength=ni), out=i_ptr[1:])
+    i_idx = users[by_i].astype(np.int32)
+    U0 = torch.from_numpy(rng.random((nu, d)).astype(np.float32)).cuda(); V0 = torch.from_numpy(rng.random((ni, d)).astype(np.float32)).cuda()
+    U, V = U0.clone(), V0.clone()
+    lu_, li_ = tdist.ShardedAls(u_ptr, u_idx, i_ptr, i_idx, seg=16).iteration(U, V, 1.0, 0.01, 0.01, 0.01, wmf=True)
+    us, its = topkrec.AlsSide(u_ptr, u_idx, 16), topkrec.AlsSide(i_ptr, i_idx, 16)
+    U2, V2 = U0.clone(), V0.clone()
+    l1 = topkrec.als_solve_rows(us, V2, U2, topkrec.als_gram(V2, its.rated_dev, 0.01, 0.01), 1.0, 0.01, 0.0, 0.01)
+    l2 = topkrec.als_solve_rows(its, U2, V2, topkrec.als_gram(U2, us.rated_dev, 0.01, 0.0), 1.0, 0.01, 0.01, 0.01, item_loss=True)
+    assert torch.equal(U, U2) and torch.equal(V, V2)
+    assert abs(lu_ - float(l1.sum())) <= 1e-9 * abs(lu_) and abs(li_ - float(l2.sum())) <= 1e-9 * abs(li_)
