@@ -15,6 +15,9 @@ Pinning status
 * sampler / loaders / ``.dat`` codec: PINNED against the reference's own
   functions imported through ``oracle/tf_stub`` (a 20-line fake of
   ``tensorflow.compat.v1``, import-time only).
+* ALS for WMF/CER (``single/cer.py:24-73``): PINNED.  ``CER.train`` is numpy-only once imported through
+  ``oracle/tf_stub``; ``tests/golden/make_golden_als.py`` ran it unmodified and ``oracle.als_ref`` reproduces its
+  factors bit for bit.
 * path 1 step arithmetic (``single/bpr.py:71-101`` executed by TensorFlow 1.15,
   pinned ``tensorflow-gpu == 1.15.*`` in ``requirements.txt:3``, not vendored,
   not installable offline): **PARITY UNPINNED**.  ``oracle.bpr_ref`` restates

@@ -15,3 +15,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:bpr_
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:score_filter -s 2 -c 1 -f -o gpurun_out/prof_score_$TAG \
     python bench.py --steps 4 --warmup 3 --skip-cpu --skip-sweep > /dev/null 2> gpurun_out/ncu_score_$TAG.err
 ls -la gpurun_out | tail -12
+SKIP=5 timeout 300 bash profiles/ncu_als.sh $TAG > /dev/null 2>&1
+ls -la gpurun_out | tail -5

@@ -376,8 +376,8 @@ __device__ __forceinline__ void factor_solve_panels(float (&acc)[Geo<NB>::TR][8]
     }
 }
 
-// The same factorisation one column per barrier (the variant for NB = 4, whose 96-register budget has no room for the
-// rank-4 update's operands): the owners of column j publish it raw (M, packed column-major: column j at
+// The same factorisation one column per barrier: the variant for NB = 4.  At its 96-register budget the 4-column rounds
+// (and a 2-column version of them) spill and measured slower: 46.5 / 39.7 ms against 32.1 ms for 24 009 rows of d=256: the owners of column j publish it raw (M, packed column-major: column j at
 // M + j*DP - j(j-1)/2, `col - j` = the column's virtual row 0), one barrier, every tile below/right applies the rank-1
 // update M_r M_c / D_j; the right-hand side rides along; back substitution walks the packed columns.
 template <int NB>
