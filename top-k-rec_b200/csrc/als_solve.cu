@@ -377,7 +377,11 @@ __device__ __forceinline__ void factor_solve_panels(float (&acc)[Geo<NB>::TR][8]
 }
 
 // The same factorisation one column per barrier: the variant for NB = 4.  At its 96-register budget the 4-column rounds
-// (and a 2-column version of them) spill and measured slower: 46.5 / 39.7 ms against 32.1 ms for 24 009 rows of d=256: the owners of column j publish it raw (M, packed column-major: column j at
+// (and a 2-column version of them) spill and measured slower: 46.5 / 39.7 ms against 32.1 ms for 24 009 rows of d=256.
+// Also tried and slower (37.3 ms): a blocked right-looking variant (64-column panels factored by the panel's own warps
+// behind a named barrier, trailing blocks updated 64 columns at a time at Gram-loop density, next column published
+// early) -- it executes 2.6x fewer instructions, but a column's critical path is the in-order latency of ONE warp's
+// ~100-150 dependent instructions (~6 cycles each with 5 warps per scheduler), not the instruction total: the owners of column j publish it raw (M, packed column-major: column j at
 // M + j*DP - j(j-1)/2, `col - j` = the column's virtual row 0), one barrier, every tile below/right applies the rank-1
 // update M_r M_c / D_j; the right-hand side rides along; back substitution walks the packed columns.
 template <int NB>

@@ -52,6 +52,7 @@ class AlsSide:
             raise ValueError("indptr[-1] != len(idx)")
         self.n_rows = indptr.size - 1
         self.nnz = int(idx.size)
+        self.max_idx = int(idx.max()) if idx.size else -1
         self.seg = int(seg)
         self.rated = np.flatnonzero(np.diff(indptr) > 0).astype(np.int32)       # u_rated / i_rated (wmf.py:53-54), ascending
         _need_cuda()
@@ -102,7 +103,7 @@ def als_solve_rows(side: AlsSide, Y, X, base, a, b, ridge, lreg, prior=None, sol
     d = X.shape[1]
     if Y.shape[1] != d or tuple(base.shape) != (d, d) or X.shape[0] != side.n_rows:
         raise ValueError("shape mismatch: X %s, Y %s, base %s, rows %d" % (tuple(X.shape), tuple(Y.shape), tuple(base.shape), side.n_rows))
-    if side.nnz and int(side.idx.max()) >= Y.shape[0]:
+    if side.max_idx >= Y.shape[0]:
         raise ValueError("idx refers to a row beyond Y")
     if loss_rows is None:
         loss_rows = torch.empty(side.n_rows, dtype=torch.float64, device=X.device)
