@@ -638,6 +638,8 @@ def main():
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG set in the environment) go to a file
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(os.environ.get("TMPDIR", "/tmp"), "nccl_debug.%h.%p.log"))
     if args.impl == "reference":
         run_reference(args, rank)
         return
