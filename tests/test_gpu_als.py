@@ -240,3 +240,31 @@ def test_sharded_engine_world1_equals_direct_calls():
     l2 = topkrec.als_solve_rows(its, U2, V2, topkrec.als_gram(U2, us.rated_dev, 0.01, 0.0), 1.0, 0.01, 0.01, 0.01, item_loss=True)
     assert torch.equal(U, U2) and torch.equal(V, V2)
     assert abs(lu_ - float(l1.sum())) <= 1e-9 * abs(lu_) and abs(li_ - float(l2.sum())) <= 1e-9 * abs(li_)
+
+
+def test_degenerate_shapes():
+    """no positives at all, a single row, d = 1, one-positive segments: the edge cases of wmf.py:35-56 inputs"""
+    rng = np.random.default_rng(21)
+    # (a) every row empty: users keep their rows (cer.py:40), CER items are solved from the prior alone (cer.py:61-62)
+    d, n = 24, 7
+    Y = torch.from_numpy(rng.random((5, d)).astype(np.float32)).cuda()
+    X0 = rng.random((n, d)).astype(np.float32)
+    side = topkrec.AlsSide(np.zeros(n + 1, np.int64), np.zeros(0, np.int32), 8)
+    base = topkrec.als_gram(Y, torch.zeros(0, dtype=torch.int32, device="cuda"), 0.01, 0.5)
+    assert np.array_equal(base.cpu().numpy(), 0.5 * np.eye(d, dtype=np.float32))
+    X = torch.from_numpy(X0.copy()).cuda()
+    loss = topkrec.als_solve_rows(side, Y, X, base, 1.0, 0.01, 0.0, 0.5)
+    assert np.array_equal(X.cpu().numpy(), X0)
+    assert np.allclose(loss.cpu().numpy(), 0.25 * (X0.astype(np.float64) ** 2).sum(1), rtol=1e-6)
+    prior = rng.standard_normal((n, d)).astype(np.float32)
+    topkrec.als_solve_rows(side, Y, X, base, 1.0, 0.01, 10.0, 10.0, prior=torch.from_numpy(prior).cuda(), solve_empty=True, item_loss=True)
+    assert rel(X.cpu().numpy(), (10.0 / 10.5) * prior.astype(np.float64)) <= 1e-6       # (0.5 I + 10 I) x = 10 prior
+    # (b) one row, d = 1, segments of one positive each
+    Y1 = torch.from_numpy(np.array([[2.0], [3.0], [0.5]], np.float32)).cuda()
+    side1 = topkrec.AlsSide(np.array([0, 3]), np.array([0, 1, 1], np.int32), 1)
+    assert side1.n_slots == 3
+    X1 = torch.zeros(1, 1, device="cuda")
+    b1 = topkrec.als_gram(Y1, torch.tensor([0, 1, 2], dtype=torch.int32, device="cuda"), 0.01, 0.01)
+    topkrec.als_solve_rows(side1, Y1, X1, b1, 1.0, 0.01, 0.0, 0.01)
+    A = 0.01 * (4 + 9 + 0.25) + 0.01 + 0.99 * (4 + 9 + 9)
+    assert abs(float(X1[0, 0]) - (2 + 3 + 3) / A) <= 1e-6

@@ -36,7 +36,8 @@ template <int NB> struct Geo {
     static constexpr int RS = 32;                      // row register i sits at r0 + (i & 3) + (i >> 2) * RS
     static constexpr int TPB = 512 / TR;               // threads per 64x64 block
     static constexpr int NT = NBLK * TPB;              // threads per thread block
-    static constexpr int MAXREG = NB == 4 ? 96 : 168;  // register budget: 6 / 2 / 1 / 1 resident blocks per SM
+    static constexpr int MAXREG = NB == 4 ? 96 : 168;  // register budget: 6 / 2 / 1 / 1 resident blocks per SM (the 4-column rounds
+                                                       // spill below ~130 registers: 112 -> 584 bytes at NB = 2)
     static constexpr int NP = DP / 4;                  // 4-column panels of the factor
     static constexpr int PACKED = DP * DP / 2 + 2 * DP;// floats of the factor: panel p keeps a float4 per row 4p..DP-1
     static constexpr int PART = NBLK * 4096 + DP;      // floats per partial slot
@@ -689,7 +690,6 @@ extern "C" int tkr_als_solve_rows(const tkr_als_cfg* cfg, const tkr_als_plan* pl
     TKR_CHECK_ARG(plan->n_segs == 0 || (plan->seg_row && plan->seg_off && plan->seg_len && plan->seg_slot), "tkr_als_solve_rows: plan segment arrays missing");
     TKR_CHECK_ARG(plan->n_multi == 0 || (plan->multi_row && plan->multi_slot0 && plan->multi_nslots && plan->multi_total),
                   "tkr_als_solve_rows: plan split-row arrays missing");
-    TKR_CHECK_ARG(idx || plan->n_segs == 0, "tkr_als_solve_rows: idx is null");
     if (plan->n_slots > 0 && (!partial || partial_bytes < tkr_als_partial_bytes(cfg->d, plan->n_slots) || (reinterpret_cast<uintptr_t>(partial) & 15))) {
         set_error("tkr_als_solve_rows: partial workspace of %zu bytes needed, got %zu", tkr_als_partial_bytes(cfg->d, plan->n_slots), partial_bytes);
         return TKR_ERR_WORKSPACE;
