@@ -311,3 +311,45 @@ def test_wmf_cer_class_surface():
         assert sig.parameters["max_iter"].default == 200 and sig.parameters["tol"].default == 1e-4
     for attr in ("uids", "n_users", "usm", "iids", "n_items", "ism", "n_ratings", "u_rated", "i_rated", "fue", "fie"):
         assert hasattr(w, attr)
+
+
+def _mini_without_unknown_user(mini, tmp_path):
+    tr = tmp_path / "tr.txt"
+    tr.write_text("".join(ln for ln in open(os.path.join(mini, "f0tr.txt")) if not ln.startswith("99999,")))
+    return str(tr)
+
+
+def test_wmf_loader_matches_reference(golden, mini, tmp_path):
+    """WMF.load_training_data (host only) against the reference's own loader (wmf.py:33-56), whose usm / ism lists and
+    seeded uniform(0,1) start are stored in tests/golden/als_cer.npz by make_golden_als.py."""
+    from single import CER
+    g = np.load(os.path.join(golden, "als_cer.npz"))
+    m = CER(k=int(g["k"]), d=int(g["d_feat"]))
+    with pytest.raises(KeyError):                                           # wmf.py:51: unknown uid inside a positive pair
+        m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    np.random.seed(77)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), _mini_without_unknown_user(mini, tmp_path))
+    u_ptr, u_idx, i_ptr, i_idx = m._csr
+    assert np.array_equal(np.diff(u_ptr), g["u_cnt"]) and np.array_equal(u_idx, g["u_idx"])      # usm, file order kept
+    assert np.array_equal(np.diff(i_ptr), g["i_cnt"]) and np.array_equal(i_idx, g["i_idx"])      # ism
+    assert m.usm[5] == g["u_idx"][u_ptr[5]:u_ptr[6]].tolist() and m.ism[7] == g["i_idx"][i_ptr[7]:i_ptr[8]].tolist()
+    assert m.u_rated == np.flatnonzero(g["u_cnt"] > 0).tolist() and m.i_rated == np.flatnonzero(g["i_cnt"] > 0).tolist()
+    assert m.n_ratings == m.n_users * m.n_items
+    assert np.array_equal(m.fue, g["fue0"]) and np.array_equal(m.fie, g["fie0"])                 # same RNG draws, same order
+
+
+def test_cer_model_files_roundtrip(tmp_path, mini):
+    """export_embeddings writes final-U/V.dat + final-E.dat (cer.py:81-85), import_embeddings reads them back (cer.py:75-79)."""
+    from single import CER
+    m = CER(k=6, d=4)
+    np.random.seed(1)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), _mini_without_unknown_user(mini, tmp_path))
+    m.E = np.random.randn(4, 6)
+    path = str(tmp_path / "cer")
+    m.export_embeddings(path)
+    assert sorted(os.listdir(path)) == ["final-E.dat", "final-U.dat", "final-V.dat"]
+    r = CER(k=6, d=4)
+    r.uids, r.iids = m.uids, m.iids
+    r.import_embeddings(path)
+    assert np.allclose(r.fue, m.fue, atol=5e-7) and np.allclose(r.fie, m.fie, atol=5e-7) and np.allclose(r.E, m.E, atol=5e-7)
+    assert r.E.shape == (4, 6)
