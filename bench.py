@@ -429,7 +429,7 @@ def vbpr_points(smp, dev, d_feat=4096, k=128):
     return out
 
 
-def als_points(dev, d=256, n_users=480189 // 8, n_items=17770, mean_pos=208, reps=3, cpu_rows=96, cpu=True):
+def als_points(dev, d=256, n_users=480189 // 8, n_items=17770, mean_pos=208, reps=3, cpu_rows=8192, cpu=True):
     """BASELINE configs[3] (CER/WMF, Netflix shape 480 189 users x 17 770 items, d=256): one ALS iteration
     (single/cer.py:36-63 without the content terms = the intended single/wmf.py:67-96) on ONE GPU's share of the
     8-GPU run -- 1/8 of the users, all items -- with Zipf item popularity and ~208 positives per user (100 M / 480 k).
