@@ -353,3 +353,16 @@ def test_cer_model_files_roundtrip(tmp_path, mini):
     r.import_embeddings(path)
     assert np.allclose(r.fue, m.fue, atol=5e-7) and np.allclose(r.fie, m.fie, atol=5e-7) and np.allclose(r.E, m.E, atol=5e-7)
     assert r.E.shape == (4, 6)
+
+
+def test_single_exports_the_reference_names():
+    """single/__init__.py:1-9 exports REC, BPR, VBPR, WMF, DPM, CER, ENCODER, MLP; DPM/MLP fail where the reference's do."""
+    import single
+    for name in ("REC", "BPR", "VBPR", "WMF", "DPM", "CER", "ENCODER", "MLP"):
+        assert hasattr(single, name) and name in single.__all__
+    with pytest.raises(TypeError):
+        single.MLP(8, 4)
+    m = single.DPM(k=8, d=4)
+    assert (m.k, m.d, m.lv, m.le) == (8, 4, 10, 10e3)
+    with pytest.raises(TypeError):
+        m.train(single.MLP, max_iter=1)

@@ -5,5 +5,6 @@ from .bpr import BPR
 from .vbpr import VBPR
 from .wmf import WMF
 from .cer import CER
+from .dpm import DPM, ENCODER, MLP
 
-__all__ = ['REC', 'BPR', 'VBPR', 'WMF', 'CER']
+__all__ = ['REC', 'BPR', 'VBPR', 'WMF', 'DPM', 'CER', 'ENCODER', 'MLP']
