@@ -8,10 +8,12 @@
 //     64x64 blocks, two warps per block, an 8x8 register tile per thread (symmetry halves the FMA work).
 //   * the positives' factor rows are gathered HBM/L2 -> shared memory with cp.async, 16 rows per stage,
 //     3 stages in flight; each staged row is a rank-1 update read with conflict-free 128-bit shared loads.
-//   * the matrix is then factored where it is, A = L D L^T, column by column: the owners of column j publish it
-//     to shared memory (packed column-major, which also keeps the factor for the back substitution), one
-//     barrier, every thread applies the rank-1 update to its register tile.  The right-hand side rides along as
-//     an extra row, so forward substitution costs nothing; back substitution walks the packed columns.
+//   * the matrix is then factored where it is, A = L D L^T (no square roots).  d <= 192: in rounds of four columns -- the
+//     thread holding the 4x4 diagonal block factors it, the column owners eliminate it from their rows and publish raw M
+//     and scaled L = M/D (a float4 per row), every tile applies the rank-4 update: two barriers per four columns.
+//     d <= 256 (96 registers per thread at 640 threads, no room for the rank-4 operands): one column per barrier.
+//     Either way the published columns ARE the stored factor (packed, in shared memory) that back substitution walks,
+//     and the right-hand side rides along as an extra row, so forward substitution costs nothing.
 //   * rows with more positives than one segment (popular items: up to every user) are split: the segments'
 //     partial matrices go to a caller workspace in the threads' own register order and a second kernel sums
 //     them in a fixed order (deterministic) and solves.  The shared Gram b*Yr^T Yr uses the same two kernels.
@@ -377,14 +379,14 @@ __device__ __forceinline__ void factor_solve_panels(float (&acc)[Geo<NB>::TR][8]
     }
 }
 
-// The same factorisation one column per barrier: the variant for NB = 4.  At its 96-register budget the 4-column rounds
-// (and a 2-column version of them) spill and measured slower: 46.5 / 39.7 ms against 32.1 ms for 24 009 rows of d=256.
-// Also tried and slower (37.3 ms): a blocked right-looking variant (64-column panels factored by the panel's own warps
-// behind a named barrier, trailing blocks updated 64 columns at a time at Gram-loop density, next column published
-// early) -- it executes 2.6x fewer instructions, but a column's critical path is the in-order latency of ONE warp's
-// ~100-150 dependent instructions (~6 cycles each with 5 warps per scheduler), not the instruction total: the owners of column j publish it raw (M, packed column-major: column j at
-// M + j*DP - j(j-1)/2, `col - j` = the column's virtual row 0), one barrier, every tile below/right applies the rank-1
-// update M_r M_c / D_j; the right-hand side rides along; back substitution walks the packed columns.
+// The same factorisation one column per barrier: the variant for NB = 4.  The owners of column j publish it raw (M, packed
+// column-major: column j at M + j*DP - j(j-1)/2, `col - j` = the column's virtual row 0), one barrier, every tile below /
+// right applies the rank-1 update M_r M_c / D_j; the right-hand side rides along; back substitution walks the packed columns.
+// Measured alternatives at this register budget, 24 009 rows of d=256 (this loop: 32.1 ms): the 4-column rounds 46.5 ms and a
+// 2-column version 39.7 ms (both spill ~0.6 KB per thread); a blocked right-looking variant -- 64-column panels factored by
+// the panel's own warps behind a named barrier, trailing blocks updated 64 columns at a time at the gather loop's density,
+// next column published early -- 37.3 ms although it executes 2.6x fewer instructions: a column's critical path is the
+// in-order latency of ONE warp's ~100-150 dependent instructions, not the instruction total.
 template <int NB>
 __device__ __forceinline__ void factor_solve_columns(float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, float z, float& x) {
     using G = Geo<NB>;
