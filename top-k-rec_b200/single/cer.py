@@ -17,7 +17,7 @@ from .wmf import WMF
 
 class CER(WMF):
     def __init__(self, k: int, d: int, lu: float = 0.01, lv: float = 10, le: float = 10e3, a: float = 1, b: float = 0.01,
-                 device: str = 'cuda', seg: int = 4096) -> None:
+                 device: str = 'cuda', seg: int = 1024) -> None:
         super().__init__(k, lu, lv, a, b, device, seg)
         self.__sn = 'cer'
         self.d = d

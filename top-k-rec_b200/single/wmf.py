@@ -27,7 +27,7 @@ def _lists(indptr, idx, n):
 
 class WMF(REC):
     def __init__(self, k: int, lu: float = 0.01, lv: float = 0.01, a: float = 1, b: float = 0.01, device: str = 'cuda',
-                 seg: int = 4096) -> None:
+                 seg: int = 1024) -> None:
         self.__sn = 'wmf'
         self.k = k
         self.lu, self.lv, self.a, self.b = lu, lv, a, b

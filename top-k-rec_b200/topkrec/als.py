@@ -42,9 +42,12 @@ class AlsSide:
 
     indptr int64[n_rows+1], idx int32[nnz] (host): positives of each solved row, as rows of the fixed side
     (``usm`` / ``ism`` of wmf.py:35-52, duplicates kept).  ``seg`` = most positives one thread block accumulates;
-    longer rows are split into partial sums (deterministic: summed in segment order)."""
+    longer rows are split into partial sums (deterministic: summed in segment order).  The default also bounds the length of
+    one sequential fp32 accumulation: on the reference's uniform(0,1) start a 5000-positive row solved from one 4096-long
+    chain sits 6.8e-5 from the fp64-exact solution, from 1024-long chains 1.5e-5 (BLAS order: 0.8e-5;
+    profiles/tf32_gram_model.py)."""
 
-    def __init__(self, indptr, idx, seg=4096, device="cuda"):
+    def __init__(self, indptr, idx, seg=1024, device="cuda"):
         indptr = np.ascontiguousarray(indptr, np.int64)
         idx = np.ascontiguousarray(idx, np.int32)
         self.host, self.n_slots = build_plan(indptr, seg)

@@ -114,7 +114,7 @@ class ShardedAls:
 
     ``side_fn(indptr, idx)`` / ``gram_fn`` / ``solve_fn`` default to the CUDA engine; the gloo tests inject the oracle."""
 
-    def __init__(self, u_ptr, u_idx, i_ptr, i_idx, group=None, seg=4096, device="cuda", side_fn=None, gram_fn=None, solve_fn=None):
+    def __init__(self, u_ptr, u_idx, i_ptr, i_idx, group=None, seg=1024, device="cuda", side_fn=None, gram_fn=None, solve_fn=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
