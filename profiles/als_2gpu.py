@@ -31,7 +31,7 @@ def main():
     u_idx, i_idx = items.astype(np.int32), users[by_i].astype(np.int32)
     g = torch.Generator(device="cuda"); g.manual_seed(1)
     U0 = torch.rand(n_users, d, device="cuda", generator=g); V0 = torch.rand(n_items, d, device="cuda", generator=g)
-    eng = tdist.ShardedAls(u_ptr, u_idx, i_ptr, i_idx)
+    eng = tdist.ShardedAls(u_ptr, u_idx, i_ptr, i_idx, seg=4096)
     U, V = U0.clone(), V0.clone()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     times, losses = [], None
