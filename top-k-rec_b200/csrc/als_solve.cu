@@ -39,7 +39,8 @@ template <int NB> struct Geo {
     static constexpr int TPB = 512 / TR;               // threads per 64x64 block
     static constexpr int NT = NBLK * TPB;              // threads per thread block
     static constexpr int MAXREG = NB == 4 ? 96 : 168;  // register budget: 6 / 2 / 1 / 1 resident blocks per SM (the 4-column rounds
-                                                       // spill below ~130 registers: 112 -> 584 bytes at NB = 2)
+                                                       // spill below ~130 registers: 112 -> 584 bytes at NB = 2).  Same budgets as
+                                                       // __launch_bounds__(NT, 6 / 2 / 1 / 1), should a compiler reject the pair
     static constexpr int NP = DP / 4;                  // 4-column panels of the factor
     static constexpr int PACKED = DP * DP / 2 + 2 * DP;// floats of the factor: panel p keeps a float4 per row 4p..DP-1
     static constexpr int PART = NBLK * 4096 + DP;      // floats per partial slot
