@@ -59,14 +59,18 @@ class CER(WMF):
         V[unrated] = Fe[unrated]                                                                            # cer.py:70-73
         self.fue, self.fie, self.E = U.cpu().numpy(), V.cpu().numpy(), E.cpu().numpy()
 
+    _E_FILE = 'final-E.dat'          # the content projection next to final-U/V.dat (cer.py:75-85)
+
     def import_model(self, model_path: str) -> None:
-        file_path = os.path.join(model_path, 'final-E.dat')
-        if os.path.exists(file_path):
-            tprint('Loading content projection matrix from %s' % file_path)
-            self.E = get_embed_from_file(file_path)
+        path = os.path.join(model_path, self._E_FILE)
+        if not os.path.exists(path):
+            return
+        tprint('Loading content projection matrix from %s' % path)
+        self.E = get_embed_from_file(path)
 
     def export_model(self, model_path: str) -> None:
-        if os.path.exists(model_path):
-            if hasattr(self, 'E'):
-                tprint('Saving content projection matrix to %s' % os.path.join(model_path, 'final-E.dat'))
-                export_embed_to_file(os.path.join(model_path, 'final-E.dat'), self.E)
+        if not os.path.exists(model_path) or getattr(self, 'E', None) is None:
+            return
+        path = os.path.join(model_path, self._E_FILE)
+        tprint('Saving content projection matrix to %s' % path)
+        export_embed_to_file(path, self.E)
