@@ -22,8 +22,11 @@
  *     before returning because they write host memory).
  *   - Return 0 on success, a negative TKR_ERR_* otherwise; the message is in
  *     thread-local storage, `tkr_last_error()`.  No C++ exception crosses.
- *   - Re-entrant across streams/devices; no global mutable state but the TLS
- *     error string.
+ *   - Re-entrant across streams/devices.  The compute entry points keep no global
+ *     mutable state but the TLS error string and launch counter.  The tkr_debug_*
+ *     setters (profiling / test aids: filter counters, filter mode, seed fraction,
+ *     count mode) write PROCESS-WIDE variables without synchronisation: set them
+ *     from one thread while no other thread is inside the library.
  */
 #ifndef TOPKREC_H
 #define TOPKREC_H
@@ -211,7 +214,7 @@ void tkr_debug_set_filter_counters(long long* dev_buf);
  * updates rows occurring once in a batch in place; both paths follow the same step semantics. */
 void tkr_debug_set_count_mode(int32_t mode);
 void tkr_debug_set_filter_mode(int32_t mode);
-void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 8); tuning aid */
+void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */
 
 /* Same with HOST inputs/outputs (the np.dot/np.argsort seam of evaluate.py):
@@ -237,6 +240,8 @@ int tkr_eval_hits(const int32_t* lists, int32_t total, const int32_t* line_rows,
 int tkr_dat_shape(const char* path, int64_t* rows, int64_t* cols);
 int tkr_dat_read(const char* path, float* out, int64_t rows, int64_t cols);
 int tkr_dat_write(const char* path, const float* mat, int64_t rows, int64_t cols);
+/* same for a float64 matrix (CER's final-E.dat, single/cer.py:81-85): the doubles are formatted directly, like "'%f ' % x" */
+int tkr_dat_write_f64(const char* path, const double* mat, int64_t rows, int64_t cols);
 /* Rating file "uid,iid:like,..." (utils.py:58-89, evaluate.py:30-45) -> flat arrays in file order.  Call once with
  * line_user == NULL to get *n_lines / *n_pairs, allocate, call again.  line_user[l] / pair_item[p] = row of the id in
  * uid_path / iid_path (one id per line), -1 when unknown; pair_like[p] = 1 iff the label text is exactly "1";

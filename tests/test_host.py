@@ -125,6 +125,11 @@ def test_native_codec_edge_cases(tmp_path):
         topkrec.dat_read(q)
     topkrec.dat_write(q, np.zeros((0, 4), np.float32))
     assert open(q).read() == "" and topkrec.dat_read(q).shape[0] == 0
+    # float64 input (CER's E, single/cer.py:81-85) is formatted from the doubles, exactly like the reference's "'%f ' % x"
+    x64 = rng.standard_normal((300, 23)) * rng.choice([1e-6, 1.0, 1e5], (300, 23))
+    topkrec.dat_write(q, x64)
+    assert open(q).read() == "".join("".join("%f " % v for v in row) + "\n" for row in x64)
+    assert open(q).read() != "".join("".join("%f " % v for v in row) + "\n" for row in x64.astype(np.float32).astype(np.float64))
     with pytest.raises(topkrec.TkrError):
         topkrec.dat_read(str(tmp_path / "missing.dat"))
 

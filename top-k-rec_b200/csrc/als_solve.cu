@@ -219,7 +219,7 @@ __device__ __forceinline__ void row_loss(const RowArgs& p, int row, int64_t n, b
             loss = 0.5 * (double)p.lreg * dd;
             if (n > 0 && solved) loss += 0.5 * (xr - (double)p.ridge * xx) + 0.5 * (double)n * (double)p.a - (double)p.a * sx;
         }
-        p.loss_rows[row] = loss;
+        if (p.loss_rows) p.loss_rows[row] = loss;   // optional output (C callers may pass NULL)
     }
 }
 

@@ -153,7 +153,8 @@ extern "C" int tkr_dat_read(const char* path, float* out, int64_t rows, int64_t 
     return TKR_OK;
 }
 
-extern "C" int tkr_dat_write(const char* path, const float* mat, int64_t rows, int64_t cols) {
+template <typename T>
+static int dat_write_impl(const char* path, const T* mat, int64_t rows, int64_t cols) {
     TKR_CHECK_ARG(path && (mat || rows * cols == 0) && rows >= 0 && cols >= 0, "bad arguments");
     FILE* fp = fopen(path, "wb");
     if (fp == nullptr) { set_error("cannot create %s: %s", path, strerror(errno)); return TKR_ERR_INVALID; }
@@ -186,6 +187,11 @@ extern "C" int tkr_dat_write(const char* path, const float* mat, int64_t rows, i
     if (fclose(fp) != 0 && rc == TKR_OK) { set_error("closing %s failed: %s", path, strerror(errno)); rc = TKR_ERR_INVALID; }
     return rc;
 }
+
+extern "C" int tkr_dat_write(const char* path, const float* mat, int64_t rows, int64_t cols) { return dat_write_impl(path, mat, rows, cols); }
+// float64 input is formatted from the doubles themselves, as the reference's "'%f ' % x" does for a float64 matrix
+// (CER keeps E in float64, single/cer.py:27,64,81-85): rounding to float32 first changes the last printed digit of ~2 % of the values.
+extern "C" int tkr_dat_write_f64(const char* path, const double* mat, int64_t rows, int64_t cols) { return dat_write_impl(path, mat, rows, cols); }
 
 // Rating file -> flat arrays.  Pass 1 (pairs == NULL): counts only.  line_user[l] = row of the line's user id in
 // uid_path (-1 unknown); pair_item[p] = row of the item id in iid_path (-1 unknown); pair_like[p] = 1 iff the label

@@ -23,6 +23,9 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from utils import get_id_dict_from_file, get_embed_from_file, rated_csr_from_files, test_lines_from_files  # noqa: E402
 
 
+MAX_TOTAL = 64     # tkr_score_topk: k <= 64
+
+
 def filtered_topk(umat, temat, total, bias, rated_indptr, rated_idx, user_batch=65536):
     """Per-user filtered top-``total`` test columns via the device engine (device tensor [n_users, total]); user
     batches are uploaded on a side stream while the previous batch is scored (``topkrec.score_topk_batches``)."""
@@ -56,6 +59,12 @@ def main(argv=None):
     parser.add_argument('-t', '--total', type=int, default=30, help='The number of total predictions')
     parser.add_argument('-sl', '--scenarios', nargs='+', default=None, help='The test scenario list')
     args = parser.parse_args(argv)
+    # the device engine keeps the filtered top-`total` of a user in registers / shared memory: total <= 64
+    # (the reference accepts any total up to the number of test items; its own recipe uses 30)
+    if not 1 <= args.total <= MAX_TOTAL:
+        parser.error('--total must be in [1, %d] on the device engine (got %d)' % (MAX_TOTAL, args.total))
+    if args.step < 1:
+        parser.error('--step must be positive')
 
     uid_file, tr_file = os.path.join(args.data, 'uid'), os.path.join(args.data, 'f%dtr.txt' % args.fold)
     uids = get_id_dict_from_file(uid_file)

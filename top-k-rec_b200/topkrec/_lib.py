@@ -85,6 +85,7 @@ def lib():
     L.tkr_dat_shape.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.tkr_dat_read.argtypes = [C.c_char_p, vp, i64, i64]
     L.tkr_dat_write.argtypes = [C.c_char_p, vp, i64, i64]
+    L.tkr_dat_write_f64.argtypes = [C.c_char_p, vp, i64, i64]; L.tkr_dat_write_f64.restype = C.c_int
     L.tkr_ratings_parse.argtypes = [C.c_char_p] * 3 + [C.POINTER(C.c_int64)] * 2 + [vp] * 4
     L.tkr_als_partial_bytes.restype = sz; L.tkr_als_partial_bytes.argtypes = [i32, i64]
     L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
@@ -499,10 +500,16 @@ def dat_read(path):
 
 
 def dat_write(path, mat):
-    """float32 matrix -> ``.dat`` text, byte-identical to the reference writer (utils.py:47-55)."""
-    mat = np.ascontiguousarray(mat, np.float32)
+    """matrix -> ``.dat`` text, byte-identical to the reference writer (utils.py:47-55): float64 input is formatted from
+    the doubles (what ``'%f ' % x`` does for CER's float64 ``E``), anything else as float32."""
+    mat = np.asarray(mat)
     if mat.ndim != 2:
         raise ValueError("embed must be a matrix, got shape %s" % (mat.shape,))
+    if mat.dtype == np.float64:
+        mat = np.ascontiguousarray(mat)
+        _check(lib().tkr_dat_write_f64(os.fsencode(path), mat.ctypes.data, mat.shape[0], mat.shape[1]))
+        return
+    mat = np.ascontiguousarray(mat, np.float32)
     _check(lib().tkr_dat_write(os.fsencode(path), mat.ctypes.data, mat.shape[0], mat.shape[1]))
 
 

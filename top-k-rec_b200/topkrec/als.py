@@ -55,6 +55,8 @@ class AlsSide:
             raise ValueError("indptr[-1] != len(idx)")
         self.n_rows = indptr.size - 1
         self.nnz = int(idx.size)
+        if idx.size and int(idx.min()) < 0:
+            raise ValueError("idx holds a negative row index (%d)" % int(idx.min()))
         self.max_idx = int(idx.max()) if idx.size else -1
         self.seg = int(seg)
         self.rated = np.flatnonzero(np.diff(indptr) > 0).astype(np.int32)       # u_rated / i_rated (wmf.py:53-54), ascending

@@ -59,7 +59,8 @@ def get_embed_from_file(file_path: str, ids: dict = None):
 
 def export_embed_to_file(file_path: str, embed) -> None:
     """Write a ``.dat`` matrix, byte-identical to the reference writer
-    (``utils.py:47-55``): ``'%f '`` per element, newline per row (``tkr_dat_write``)."""
+    (``utils.py:47-55``): ``'%f '`` per element, newline per row (``tkr_dat_write``;
+    a float64 matrix -- CER's ``E`` -- is formatted from its doubles, ``tkr_dat_write_f64``)."""
     parent = os.path.dirname(file_path)
     if parent and not os.path.isdir(parent):
         os.mkdir(parent)
