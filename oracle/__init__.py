@@ -21,6 +21,11 @@ Pinning status
 * path 1 step arithmetic (``single/bpr.py:71-101`` executed by TensorFlow 1.15,
   pinned ``tensorflow-gpu == 1.15.*`` in ``requirements.txt:3``, not vendored,
   not installable offline): **PARITY UNPINNED**.  ``oracle.bpr_ref`` restates
-  the published TF-1.15 semantics and is cross-checked only
-  by fp64 finite differences of the objective and by hand-computed cases.
+  the published TF-1.15 semantics and is cross-checked by
+  fp64 finite differences of the objective, by hand-computed cases, and by
+  ``oracle.tf_literal`` -- an independent derivation: the reference's graph
+  lines under torch autograd + a statement-by-statement transcription of
+  TF-1.15's duplicate-index plumbing and RMSProp kernels (momentum slot and
+  all).  Transcribing ``vbpr.py:61`` literally exposed defect D-14 (the
+  ``[n,1]`` bias variables broadcast x to ``[B,B]``); both readings are kept.
 """

@@ -2,7 +2,11 @@
 
 TEST INFRASTRUCTURE -- see ``oracle/__init__.py``.  PARITY UNPINNED: the step
 arithmetic of the reference runs inside TensorFlow 1.15 (``requirements.txt:3``),
-which is not vendored and cannot be installed here.  This file restates
+which is not vendored and cannot be installed here.  Cross-checked (tests/test_oracle.py)
+by fp64 finite differences, a hand-computed duplicate case, and -- independently of the
+hand-derived gradients below -- by ``oracle/tf_literal.py`` (the reference's graph lines in
+torch autograd + a statement-by-statement transcription of TF's RMSProp kernels and
+duplicate-index plumbing).  This file restates
 
 * the objective and its per-occurrence gradients   ``single/bpr.py:81-99``
 * ``RMSPropOptimizer(lr).minimize(obj)``           ``single/bpr.py:100``
@@ -168,31 +172,44 @@ def new_vbpr_state(n_users, n_items, k, d, rng, dtype=np.float32):
     return st
 
 
-def vbpr_forward(st, F, u, i, j, cfg: BprCfg):
-    l2 = cfg.mode == "l2"
+def _vbpr_parts(st, F, u, i, j):
+    """r_n = rb[i]-rb[j] + (F[i]-F[j]).c  (the [B,1] terms of ``vbpr.py:61``) and y_n = x_ui - x_uj (the [B] terms)."""
     ur, uc = st["UR"][u], st["UC"][u]
-    iri, irj = st["IR"][i], st["IR"][j]
-    bi, bj = st["rb"][i], st["rb"][j]
     Fi, Fj = F[i], F[j]
     ice, jce = Fi @ st["E"], Fj @ st["E"]
-    x_ui = np.sum(ur * iri + uc * ice, axis=1)
-    x_uj = np.sum(ur * irj + uc * jce, axis=1)
-    x = bi - bj + x_ui - x_uj + (Fi - Fj) @ st["c"]
-    loss = np.sum(np.log1p(np.exp(-x)))
-    loss += _reg_value(st["E"], cfg.lambda_e, l2)
-    loss += _reg_value(ur, cfg.lambda_u, l2) + _reg_value(uc, cfg.lambda_u, l2)
-    loss += _reg_value(iri, cfg.lambda_i, l2) + _reg_value(irj, cfg.lambda_j, l2)
-    loss += _reg_value(bi, cfg.lambda_b, l2) + _reg_value(bj, cfg.lambda_b, l2) + _reg_value(st["c"], cfg.lambda_b, l2)
-    return x, loss
+    y = np.sum(ur * st["IR"][i] + uc * ice, axis=1) - np.sum(ur * st["IR"][j] + uc * jce, axis=1)
+    r = st["rb"][i] - st["rb"][j] + (Fi - Fj) @ st["c"]
+    return r, y
 
 
-def vbpr_step(st, F, u, i, j, cfg: BprCfg):
-    """One VBPR step: sparse RMSProp on UR/UC/IR/rb, dense on E/c."""
+def _vbpr_reg(st, u, i, j, cfg: BprCfg):
+    l2 = cfg.mode == "l2"
+    reg = _reg_value(st["E"], cfg.lambda_e, l2)
+    reg += _reg_value(st["UR"][u], cfg.lambda_u, l2) + _reg_value(st["UC"][u], cfg.lambda_u, l2)
+    reg += _reg_value(st["IR"][i], cfg.lambda_i, l2) + _reg_value(st["IR"][j], cfg.lambda_j, l2)
+    reg += _reg_value(st["rb"][i], cfg.lambda_b, l2) + _reg_value(st["rb"][j], cfg.lambda_b, l2) + _reg_value(st["c"], cfg.lambda_b, l2)
+    return reg
+
+
+def vbpr_forward(st, F, u, i, j, cfg: BprCfg, pairwise=False):
+    """x and the batch objective of ``single/vbpr.py:59-72``.  ``pairwise=False``: the per-triple x_n = r_n + y_n the
+    code evidently means.  ``pairwise=True``: the graph as written -- the bias variables are ``[n,1]`` (``vbpr.py:43,47``)
+    so ``vbpr.py:61`` broadcasts to x[a,b] = r_a + y_b and the loss sums over all B*B entries (defect D-14)."""
+    r, y = _vbpr_parts(st, F, u, i, j)
+    x = r[:, None] + y[None, :] if pairwise else r + y
+    return x, np.sum(np.log1p(np.exp(-x))) + _vbpr_reg(st, u, i, j, cfg)
+
+
+def vbpr_step(st, F, u, i, j, cfg: BprCfg, pairwise=False):
+    """One VBPR step: sparse RMSProp on UR/UC/IR/rb, dense on E/c.  With ``pairwise`` the weight of triple n is
+    sum_a sigma(-x[a,n]) on everything reached through y (embeddings, E) and sum_b sigma(-x[n,b]) on everything reached
+    through r (rb, c); per-triple they are both sigma(-x_n)."""
     l2 = cfg.mode == "l2"
     dt = st["UR"].dtype
     u = np.asarray(u, np.int64); i = np.asarray(i, np.int64); j = np.asarray(j, np.int64)
-    x, loss = vbpr_forward(st, F, u, i, j, cfg)
-    s = (1.0 / (1.0 + np.exp(x))).astype(dt)
+    x, loss = vbpr_forward(st, F, u, i, j, cfg, pairwise)
+    sig = (1.0 / (1.0 + np.exp(x))).astype(dt)
+    s, sb = (sig.sum(axis=0).astype(dt), sig.sum(axis=1).astype(dt)) if pairwise else (sig, sig)
     sc = s[:, None]
     ur, uc = st["UR"][u], st["UC"][u]
     iri, irj = st["IR"][i], st["IR"][j]
@@ -202,10 +219,10 @@ def vbpr_step(st, F, u, i, j, cfg: BprCfg):
     g_uc = -sc * (dF @ st["E"]) + _reg_grad(uc, dt.type(cfg.lambda_u), l2)
     g_iri = -sc * ur + _reg_grad(iri, dt.type(cfg.lambda_i), l2)
     g_irj = sc * ur + _reg_grad(irj, dt.type(cfg.lambda_j), l2)
-    g_bi = -s + _reg_grad(bi, dt.type(cfg.lambda_b), l2)
-    g_bj = s + _reg_grad(bj, dt.type(cfg.lambda_b), l2)
+    g_bi = -sb + _reg_grad(bi, dt.type(cfg.lambda_b), l2)
+    g_bj = sb + _reg_grad(bj, dt.type(cfg.lambda_b), l2)
     g_E = dF.T @ (-sc * uc) + _reg_grad(st["E"], dt.type(cfg.lambda_e), l2)
-    g_c = dF.T @ (-s) + _reg_grad(st["c"], dt.type(cfg.lambda_b), l2)
+    g_c = dF.T @ (-sb) + _reg_grad(st["c"], dt.type(cfg.lambda_b), l2)
     rU, G_ur = segment_sum(u, g_ur.astype(dt))
     _, G_uc = segment_sum(u, g_uc.astype(dt))
     ij = np.concatenate([i, j])

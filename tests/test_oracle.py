@@ -286,3 +286,145 @@ def test_als_oracle_row_solution_satisfies_normal_equations(golden):
     Vr = fie[i_rated].astype(np.float64)
     A = 0.01 * Vr.T @ Vr + 0.01 * np.eye(fie.shape[1]) + 0.99 * Vi.T @ Vi
     assert np.linalg.norm(A @ fue[u] - Vi.sum(0)) <= 1e-5 * np.linalg.norm(Vi.sum(0))
+
+
+# ------------------------------------------------------------------ path 1: a second, independent derivation
+# oracle/tf_literal.py = the reference's graph lines under torch autograd + a statement-by-statement transcription of
+# TF-1.15's duplicate-index plumbing and RMSProp kernels (momentum slot included).  Shares no code with bpr_ref.
+def _bpr_pair(rng, nu, ni, k, dtype, scale=30.0):
+    from oracle import tf_literal
+    st = bpr_ref.new_state(nu, ni, k, rng, dtype)
+    for n in ("U", "V"):
+        st[n] *= dtype(scale)
+    st["b"] = rng.standard_normal(ni).astype(dtype)
+    lit = {"ue": st["U"].copy(), "ie": st["V"].copy(), "ib": st["b"].copy()}
+    return st, lit, tf_literal.new_slots(lit)
+
+
+@pytest.mark.parametrize("mode", ["l2", "l1"])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_bpr_step_matches_autograd_plus_literal_tf_rmsprop(mode, dtype, tol):
+    """duplicates inside the i-gather, inside the j-gather, across both, rows hit by both signs, lambda_b != 0,
+    several consecutive steps (the rms slots carry over)"""
+    from oracle import tf_literal
+    rng = np.random.default_rng(21)
+    nu, ni, k, B, steps = 400, 7, 5, 24, 6
+    st, lit, slots = _bpr_pair(rng, nu, ni, k, dtype)
+    cfg = bpr_ref.BprCfg(lambda_u=0.03, lambda_i=0.02, lambda_j=0.01, lambda_b=0.05, lr=0.05, mode=mode)
+    for t in range(steps):
+        u = rng.integers(0, nu, B); i = rng.integers(0, ni, B); j = rng.integers(0, ni, B)
+        if t == 0:
+            i[:4] = 3; j[4:8] = 3; u[:6] = 2; u[6:12] = 5          # forced overlaps
+        l_ref = bpr_ref.bpr_step(st, u, i, j, cfg)
+        l_lit = tf_literal.bpr_minimize_step(lit, slots, u, i, j, cfg.lambda_u, cfg.lambda_i, cfg.lambda_j, cfg.lambda_b, cfg.lr, mode)
+        assert abs(l_ref - l_lit) <= max(tol, 1e-6 if dtype is np.float32 else 0) * abs(l_lit)
+        for a, b in (("U", "ue"), ("V", "ie"), ("b", "ib")):
+            assert np.abs(st[a] - lit[b]).max() <= tol * np.abs(lit[b]).max(), (t, a)
+            assert np.abs(st["ms" + a] - slots[b][0]).max() <= tol * np.abs(slots[b][0]).max(), (t, "ms" + a)
+    touched_once = slots["ue"][0] != 1
+    assert touched_once.any() and not touched_once.all()            # lazy rows stayed lazy in both
+
+
+def test_sparse_rmsprop_touches_zero_gradient_rows_like_tf():
+    """a looked-up row whose summed gradient is exactly zero still gets its rms slot decayed (TF updates every unique
+    index); rows never looked up keep rms == 1.  Both derivations agree on that."""
+    from oracle import tf_literal
+    st = {"U": np.zeros((3, 2)), "V": np.array([[1.0, 2.0], [1.0, 2.0], [5.0, 5.0]]), "b": np.zeros(3)}
+    for n in ("U", "V", "b"):
+        st["ms" + n] = np.ones_like(st[n])
+    lit = {"ue": st["U"].copy(), "ie": st["V"].copy(), "ib": st["b"].copy()}
+    slots = tf_literal.new_slots(lit)
+    cfg = bpr_ref.BprCfg(lambda_u=0.0, lambda_i=0.0, lambda_j=0.0, lambda_b=0.0, lr=0.1)
+    u, i, j = np.array([0]), np.array([0]), np.array([1])          # U_0 = 0 -> gV = 0; V_0 == V_1 -> gU = 0
+    bpr_ref.bpr_step(st, u, i, j, cfg)
+    tf_literal.bpr_minimize_step(lit, slots, u, i, j, 0.0, 0.0, 0.0, 0.0, 0.1)
+    assert np.allclose(st["msV"][:2], 0.9) and np.allclose(slots["ie"][0][:2], 0.9) and (st["msV"][2] == 1).all()
+    assert np.allclose(st["msU"][0], 0.9) and (st["msU"][1:] == 1).all() and np.allclose(slots["ue"][0], st["msU"])
+    assert np.array_equal(st["V"], lit["ie"]) and np.allclose(st["b"], lit["ib"], atol=1e-15)
+
+
+def _vbpr_pair(rng, nu, ni, k, d, dtype):
+    from oracle import tf_literal
+    st = bpr_ref.new_vbpr_state(nu, ni, k, d, rng, dtype)
+    for n in ("UR", "UC", "IR"):
+        st[n] *= dtype(30.0)
+    st["rb"] = (0.3 * rng.standard_normal(ni)).astype(dtype)
+    st["E"] = (0.2 * rng.standard_normal((d, k // 2))).astype(dtype)
+    st["c"] = (0.2 * rng.standard_normal(d)).astype(dtype)
+    lit = {"ure": st["UR"].copy(), "uce": st["UC"].copy(), "ire": st["IR"].copy(), "irb": st["rb"].reshape(-1, 1).copy(),
+           "cem": st["E"].copy(), "icb": st["c"].reshape(-1, 1).copy()}
+    return st, lit, tf_literal.new_slots(lit)
+
+
+@pytest.mark.parametrize("pairwise", [False, True])
+@pytest.mark.parametrize("mode", ["l2", "l1"])
+def test_vbpr_step_matches_autograd_plus_literal_tf_rmsprop(pairwise, mode):
+    """VBPR: sparse RMSProp on ur/uc/ir/rb, dense on E/c.  pairwise=True is vbpr.py:61 exactly as written: the [n,1]
+    bias variables make x a [B,B] matrix (defect D-14); pairwise=False the per-triple objective."""
+    from oracle import tf_literal
+    rng = np.random.default_rng(22)
+    nu, ni, k, d, B, steps = 8, 6, 6, 11, 12, 4
+    st, lit, slots = _vbpr_pair(rng, nu, ni, k, d, np.float64)
+    F = np.abs(rng.standard_normal((ni, d)))
+    cfg = bpr_ref.BprCfg(lambda_u=0.03, lambda_i=0.02, lambda_j=0.01, lambda_b=0.05, lambda_e=0.04, lr=0.05, mode=mode)
+    for t in range(steps):
+        u = rng.integers(0, nu, B); i = rng.integers(0, ni, B); j = rng.integers(0, ni, B)
+        l_ref = bpr_ref.vbpr_step(st, F, u, i, j, cfg, pairwise=pairwise)
+        l_lit = tf_literal.vbpr_minimize_step(lit, slots, F, u, i, j, cfg.lambda_u, cfg.lambda_i, cfg.lambda_j, cfg.lambda_b,
+                                              cfg.lambda_e, cfg.lr, mode, pairwise=pairwise)
+        assert abs(l_ref - l_lit) <= 1e-12 * abs(l_lit)
+        for a, b in (("UR", "ure"), ("UC", "uce"), ("IR", "ire"), ("rb", "irb"), ("E", "cem"), ("c", "icb")):
+            assert np.abs(st[a].ravel() - lit[b].ravel()).max() <= 1e-11 * np.abs(lit[b]).max(), (t, a)
+            assert np.abs(st["ms" + a].ravel() - slots[b][0].ravel()).max() <= 1e-11, (t, "ms" + a)
+
+
+def test_vbpr_graph_as_written_is_pairwise():
+    """D-14 pinned down: with B triples the literal graph of vbpr.py:59-72 has B*B loss terms; it equals the per-triple
+    objective only for B == 1, and with rb = c = 0 (the reference's initial state) it is B x the per-triple data term."""
+    from oracle import tf_literal
+    import torch
+    rng = np.random.default_rng(23)
+    nu, ni, k, d, B = 5, 4, 4, 7, 6
+    st, lit, _ = _vbpr_pair(rng, nu, ni, k, d, np.float64)
+    F = np.abs(rng.standard_normal((ni, d)))
+    u = rng.integers(0, nu, B); i = rng.integers(0, ni, B); j = rng.integers(0, ni, B)
+    t = {n: torch.tensor(v) for n, v in lit.items()}
+    args = (torch.as_tensor(F), torch.as_tensor(u), torch.as_tensor(i), torch.as_tensor(j), 0, 0, 0, 0, 0)
+    pw = float(tf_literal.vbpr_objective(*t.values(), *args, pairwise=True))
+    pt = float(tf_literal.vbpr_objective(*t.values(), *args, pairwise=False))
+    assert abs(pw - pt) > 1e-3 * pt
+    one = tuple(torch.as_tensor(a[:1]) for a in (u, i, j))
+    assert float(tf_literal.vbpr_objective(*t.values(), torch.as_tensor(F), *one, 0, 0, 0, 0, 0, pairwise=True)) == \
+        pytest.approx(float(tf_literal.vbpr_objective(*t.values(), torch.as_tensor(F), *one, 0, 0, 0, 0, 0, pairwise=False)), rel=1e-14)
+    t["irb"] = torch.zeros_like(t["irb"]); t["icb"] = torch.zeros_like(t["icb"])
+    pw0 = float(tf_literal.vbpr_objective(*t.values(), *args, pairwise=True))
+    pt0 = float(tf_literal.vbpr_objective(*t.values(), *args, pairwise=False))
+    assert pw0 == pytest.approx(B * pt0, rel=1e-13)
+
+
+def test_c_oracle_matches_literal_at_scale():
+    """the OpenMP C port (the checker of the full-size GPU tests and bench's CPU leg) against the literal transcription
+    on a batch with hundreds of duplicates per row"""
+    import ctypes
+    from oracle import clib, tf_literal
+
+    class Cfg(ctypes.Structure):
+        _fields_ = [("n_users", ctypes.c_int32), ("n_items", ctypes.c_int32), ("d", ctypes.c_int32),
+                    ("lu", ctypes.c_float), ("li", ctypes.c_float), ("lj", ctypes.c_float), ("lb", ctypes.c_float),
+                    ("lr", ctypes.c_float), ("l1", ctypes.c_int32), ("sgd", ctypes.c_int32)]
+    rng = np.random.default_rng(24)
+    nu, ni, d, B = 60, 12, 16, 2048
+    st = bpr_ref.new_state(nu, ni, d, rng); st["b"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    lit = {"ue": st["U"].astype(np.float64), "ie": st["V"].astype(np.float64), "ib": st["b"].astype(np.float64)}
+    slots = tf_literal.new_slots(lit)
+    u = rng.integers(0, nu, B).astype(np.int32); i = rng.integers(0, ni, B).astype(np.int32); j = rng.integers(0, ni, B).astype(np.int32)
+    c = Cfg(nu, ni, d, 2.5e-3, 2.5e-3, 2.5e-4, 0.01, 1e-4, 0, 0)
+    loss = ctypes.c_double()
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    assert clib.lib().tkr_ref_bpr_step(ctypes.byref(c), fp(st["U"]), fp(st["V"]), fp(st["b"]), fp(st["msU"]), fp(st["msV"]),
+                                       fp(st["msb"]), fp(u), fp(i), fp(j), ctypes.c_int64(B), ctypes.byref(loss)) == 0
+    l_lit = tf_literal.bpr_minimize_step(lit, slots, u, i, j, 2.5e-3, 2.5e-3, 2.5e-4, 0.01, 1e-4)
+    assert abs(loss.value - l_lit) / l_lit < 1e-6
+    for a, b in (("U", "ue"), ("V", "ie"), ("b", "ib")):
+        assert np.abs(st[a] - lit[b]).max() / np.abs(lit[b]).max() < 1e-5, a      # fp32 port vs fp64 literal
+        assert np.abs(st["ms" + a] - slots[b][0]).max() / np.abs(slots[b][0]).max() < 1e-5, a   # (ms_b ~ 20: +-s sums of ~340 occurrences, squared)
