@@ -243,3 +243,35 @@ def vbpr_export(st, F):
     fie = np.concatenate([st["IR"], F @ st["E"]], axis=1)
     fib = (st["rb"] + F @ st["c"]).reshape(-1, 1)
     return fue, fie, fib
+
+
+# --------------------------------------------------------------------------
+# ctypes face of oracle/bpr_ref.c (the same step in C + OpenMP, for full-size runs)
+# --------------------------------------------------------------------------
+
+def c_bpr_train(st, u, i, j, batch_size, cfg: BprCfg, n_users=None, n_items=None):
+    """``bpr_train`` through ``tkr_ref_bpr_step`` (fp32 state arrays updated in place); returns the per-step losses."""
+    import ctypes
+    from . import clib
+
+    class _Cfg(ctypes.Structure):
+        _fields_ = [("n_users", ctypes.c_int32), ("n_items", ctypes.c_int32), ("d", ctypes.c_int32),
+                    ("lu", ctypes.c_float), ("li", ctypes.c_float), ("lj", ctypes.c_float), ("lb", ctypes.c_float),
+                    ("lr", ctypes.c_float), ("l1", ctypes.c_int32), ("sgd", ctypes.c_int32)]
+    for n in ("U", "V", "b", "msU", "msV", "msb"):
+        assert st[n].dtype == np.float32 and st[n].flags.c_contiguous, n
+    u, i, j = (np.ascontiguousarray(a, np.int32) for a in (u, i, j))
+    nu, d = st["U"].shape
+    c = _Cfg(nu, st["V"].shape[0], d, cfg.lambda_u, cfg.lambda_i, cfg.lambda_j, cfg.lambda_b, cfg.lr,
+             int(cfg.mode != "l2"), int(cfg.optimizer == "sgd"))
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+    n_steps = len(u) // batch_size
+    losses, loss = np.zeros(n_steps), ctypes.c_double()
+    step = clib.lib().tkr_ref_bpr_step
+    for t in range(n_steps):
+        o = t * batch_size
+        rc = step(ctypes.byref(c), fp(st["U"]), fp(st["V"]), fp(st["b"]), fp(st["msU"]), fp(st["msV"]), fp(st["msb"]),
+                  fp(u[o:o + batch_size]), fp(i[o:o + batch_size]), fp(j[o:o + batch_size]), ctypes.c_int64(batch_size), ctypes.byref(loss))
+        assert rc == 0
+        losses[t] = loss.value
+    return losses

@@ -1,0 +1,161 @@
+"""GPU parity tests at the BASELINE.json configurations themselves: the CUDA path through the C ABI
+against the CPU oracle at FULL size -- C2 (70k x 10k, d=128: one step of 2^20 triples, and 1 000 steps of the
+reference's batch 256 on the replayed reference sampler stream, seed 123), C3 (VBPR, 4096-d dense features, k=128),
+C5 (18 944-user x 1 M-item slabs at d = 64 / 128 / 256, oracle lists for 256 sampled rows, with and without a
+rated mask).  Tolerances: 1e-4 relative max-norm on every state tensor (north_star), bit-exact lists and score bits."""
+import numpy as np
+import pytest
+import torch
+
+import topkrec
+from oracle import bpr_ref, sampler_ref, topk_ref
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+
+def _rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def c2():
+    """70 000 users x 10 000 items, 10 M (user, item) pairs, Zipf items, like w.p. 0.15 (bench.py's generator)."""
+    import bench
+    tr_users, indptr, pos_idx = bench.synth_interactions()
+    return tr_users, indptr, pos_idx, bench.init_state_np(bench.N_USERS, bench.N_ITEMS, bench.D)
+
+
+def _dev(st):
+    return {k: torch.from_numpy(v.copy()).cuda() for k, v in st.items()}
+
+
+def _compare(dst, st, tol=REL_TOL):
+    for name in st:
+        err = _rel(dst[name].cpu().numpy(), st[name])
+        assert err <= tol, (name, err)
+
+
+def test_c2_one_step_of_2_20_triples_matches_c_oracle(c2):
+    """configs[1] at the bench's operating point: B = 2^20 triples drawn by the device sampler (seed 123), hot items
+    privatised as in bench.py, against oracle/bpr_ref.c on the same triples."""
+    tr_users, indptr, pos_idx, st = c2
+    nu, ni, d, B = st["U"].shape[0], st["V"].shape[0], st["U"].shape[1], 1 << 20
+    smp = topkrec.Sampler(tr_users, indptr, pos_idx, ni, seed=123)
+    u, i, j = topkrec.bpr_sample(smp, 0, B)
+    cfg = topkrec.BprCfg(nu, ni, d)
+    ws = topkrec.bpr_workspace(cfg, B)
+    topkrec.bpr_set_hot_items(cfg, B, ws, topkrec.popular_items(pos_idx, ni))
+    dst = _dev(st)
+    loss = torch.empty(1, device="cuda")
+    topkrec.bpr_step(cfg, dst["U"], dst["V"], dst["b"], dst["msU"], dst["msV"], dst["msb"], u, i, j, B, 1, ws, loss)
+    ref = {k: v.copy() for k, v in st.items()}
+    ref_loss = bpr_ref.c_bpr_train(ref, u.cpu().numpy(), i.cpu().numpy(), j.cpu().numpy(), B, bpr_ref.BprCfg())
+    _compare(dst, ref)
+    assert abs(loss.item() - ref_loss[0]) <= 1e-4 * ref_loss[0]
+    # the same step with the sampler fused into the gradient kernel (u == NULL): same draws, same result
+    dst2 = _dev(st)
+    topkrec.bpr_step(cfg, dst2["U"], dst2["V"], dst2["b"], dst2["msU"], dst2["msV"], dst2["msb"], None, None, None, B, 1, ws, loss,
+                     sampler=smp, first_draw=0)
+    _compare(dst2, ref)
+
+
+def test_c2_1000_steps_of_256_on_the_replayed_reference_sampler(c2):
+    """SURVEY 8(d) C2 parity run: B = 256 (bpr.py:103), 1 000 steps, the reference's own sampler stream replayed with
+    np.random.seed(123) (bpr.py:155-165), identical initial U/V/b; all six state tensors within 1e-4 of the oracle."""
+    tr_users, indptr, pos_idx, st = c2
+    nu, ni, d, B, steps = st["U"].shape[0], st["V"].shape[0], st["U"].shape[1], 256, 1000
+    tr_data = {int(u): pos_idx[indptr[u]:indptr[u + 1]].tolist() for u in tr_users}
+    ub, ib, jb = sampler_ref.replay_sampler([int(u) for u in tr_users], tr_data, ni, B, steps, np.random.RandomState(123))
+    u, i, j = ub.ravel(), ib.ravel(), jb.ravel()
+    cfg = topkrec.BprCfg(nu, ni, d)
+    ws = topkrec.bpr_workspace(cfg, B)
+    dst = _dev(st)
+    loss = torch.empty(steps, device="cuda")
+    topkrec.bpr_step(cfg, dst["U"], dst["V"], dst["b"], dst["msU"], dst["msV"], dst["msb"],
+                     torch.from_numpy(u).cuda(), torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, ws, loss)
+    ref = {k: v.copy() for k, v in st.items()}
+    ref_loss = bpr_ref.c_bpr_train(ref, u, i, j, B, bpr_ref.BprCfg())
+    _compare(dst, ref)
+    assert np.allclose(loss.cpu().numpy(), ref_loss, rtol=1e-4)
+    moved = np.abs(ref["U"] - st["U"]).max()
+    assert moved > 1e-3, "1 000 steps must have moved the parameters (%.3g)" % moved
+
+
+# ------------------------------------------------------------------ C3
+def _vbpr_c3(B, steps, seed):
+    """C2 shape + F 10 000 x 4096 dense |N(0,1)| row-normalised (default_rng(2)), k = 128 -> 64 + 64,
+    E = 2/(d k), c = 0."""
+    from test_gpu_vbpr import _dev_state
+    nu, ni, k, dF = 70000, 10000, 128, 4096
+    rng = np.random.default_rng(2)
+    F = np.abs(rng.standard_normal((ni, dF), dtype=np.float32)); F /= np.linalg.norm(F, axis=1, keepdims=True)
+    rng = np.random.default_rng(seed)
+    st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
+    u = rng.integers(0, nu, B * steps).astype(np.int32)
+    p = 1.0 / np.arange(1, ni + 1); p /= p.sum()
+    i = rng.choice(ni, B * steps, p=p).astype(np.int32); j = rng.integers(0, ni, B * steps).astype(np.int32)
+    ocfg = bpr_ref.BprCfg()
+    cfg = topkrec.VbprCfg(nu, ni, k, dF)
+    dv = _dev_state(st, F, k)
+    Fd = torch.from_numpy(F).cuda()
+    ws = topkrec.vbpr_workspace(cfg, B)
+    loss = torch.empty(steps, dtype=torch.float32, device="cuda")
+    topkrec.vbpr_project(cfg, dv, Fd)
+    topkrec.vbpr_step(cfg, dv, Fd, torch.from_numpy(u).cuda(), torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, ws, loss)
+    ref_loss = np.array([bpr_ref.vbpr_step(st, F, u[t * B:(t + 1) * B], i[t * B:(t + 1) * B], j[t * B:(t + 1) * B], ocfg) for t in range(steps)])
+    h = k // 2
+    got = {n: v.cpu().numpy() for n, v in dv.items()}
+    pairs = {"UR": got["U"][:, :h], "UC": got["U"][:, h:], "IR": got["V"][:, :h], "rb": got["rb"], "E": got["E"], "c": got["c"],
+             "msUR": got["msU"][:, :h], "msUC": got["msU"][:, h:], "msIR": got["msV"][:, :h], "msrb": got["msrb"], "msE": got["msE"], "msc": got["msc"]}
+    for n, g in pairs.items():
+        assert _rel(g, st[n]) <= REL_TOL, (n, _rel(g, st[n]))
+    assert np.allclose(loss.cpu().numpy(), ref_loss, rtol=1e-4)
+    fue, fie, fib = bpr_ref.vbpr_export(st, F)
+    assert _rel(got["V"], fie) <= REL_TOL and _rel(got["bsum"], fib.ravel()) <= REL_TOL
+
+
+def test_c3_vbpr_4096d_k128_reference_batch():
+    """configs[2]: 20 steps of the reference's batch 256 (vbpr.py:76)"""
+    _vbpr_c3(256, 20, seed=31)
+
+
+def test_c3_vbpr_4096d_k128_large_batch():
+    """configs[2]: 2 steps of 2^14 triples (every popular item touched many times, dense dE GEMM over ~all items)"""
+    _vbpr_c3(1 << 14, 2, seed=32)
+
+
+# ------------------------------------------------------------------ C5
+@pytest.mark.parametrize("d", [64, 128, 256])
+def test_c5_slab_18944_users_x_1m_items_sampled_rows_match_oracle(d):
+    """configs[4]: one bench step (18 944 users x 2^20 items, k = 30) on the tensor-core engine; 256 sampled rows are
+    re-computed by oracle/topk_ref.c (exact fp32 FMA chains over all 2^20 items): lists and score bits identical,
+    without and with a 64-item rated mask per user (default_rng(5))."""
+    nu, ni, k, nsamp = 18944, 1 << 20, 30, 256
+    V = (0.1 * np.random.default_rng(4).standard_normal((ni, d), dtype=np.float32))
+    U = (0.1 * np.random.default_rng(3).standard_normal((nu, d), dtype=np.float32))
+    rng = np.random.default_rng(5)
+    rated = np.sort(rng.integers(0, ni, (nu, 64)), axis=1).astype(np.int32)
+    indptr = np.arange(0, (nu + 1) * 64, 64, dtype=np.int64)
+    rows = np.sort(rng.choice(nu, nsamp, replace=False))
+    Ud, Vd = torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda()
+    nfb = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(topkrec.lib().tkr_score_topk_tc_workspace_bytes(nu, ni, d, k, 0), dtype=torch.uint8, device="cuda")
+    for masked in (False, True):
+        rp = torch.from_numpy(indptr).cuda() if masked else None
+        ri = torch.from_numpy(rated.ravel()).cuda() if masked else None
+        gi, gs = topkrec.score_topk(Ud, Vd, k, None, rp, ri, engine="tc", ws=ws, n_fallback=nfb, items_prepared=masked)
+        gi, gs = gi.cpu().numpy(), gs.cpu().numpy()
+        if masked:      # duplicates inside a user's 64 draws: the oracle takes a strictly ascending, distinct list
+            sub = [np.unique(rated[r]) for r in rows]
+            sp = np.concatenate([[0], np.cumsum([len(s) for s in sub])]).astype(np.int64)
+            oi, osc = topk_ref.score_topk(U[rows], V, k, None, sp, np.concatenate(sub).astype(np.int32))
+            assert not any(np.isin(gi[r], rated[r]).any() for r in rows)
+        else:
+            oi, osc = topk_ref.score_topk(U[rows], V, k)
+        assert np.array_equal(gi[rows], oi), "d=%d masked=%s: lists differ at sampled rows %s" % (d, masked, rows[(gi[rows] != oi).any(1)][:5])
+        assert np.array_equal(gs[rows].view(np.uint32), osc.view(np.uint32))
+        assert int(nfb.item()) <= nu // 100
+        # size-independent properties on ALL rows: strictly ordered (score desc, column desc), columns in range, distinct
+        assert (gi >= 0).all() and (gi < ni).all()
+        assert ((gs[:, :-1] > gs[:, 1:]) | ((gs[:, :-1] == gs[:, 1:]) & (gi[:, :-1] > gi[:, 1:]))).all()

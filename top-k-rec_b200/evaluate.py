@@ -66,27 +66,35 @@ def main(argv=None):
     if args.step < 1:
         parser.error('--step must be positive')
 
-    uid_file, tr_file = os.path.join(args.data, 'uid'), os.path.join(args.data, 'f%dtr.txt' % args.fold)
+    lines, _ = run(args.data, args.model, args.fold, args.step, args.total, args.scenarios)
+    for line in lines:
+        print(line)
+    return lines
+
+
+def run(data, model, fold=0, step=5, total=30, scenarios=('im',), use_bias=True, keep_lists=False):
+    """The body of the reference's ``__main__`` (``evaluate.py:57-117``) on the device engine.  Returns the printed
+    lines and, with ``keep_lists``, {scenario: int32 [n_users, total] filtered top-``total`` test columns} (host)."""
+    uid_file, tr_file = os.path.join(data, 'uid'), os.path.join(data, 'f%dtr.txt' % fold)
     uids = get_id_dict_from_file(uid_file)
-    vids = get_id_dict_from_file(os.path.join(args.data, 'vid'))
-    umat = get_embed_from_file(os.path.join(args.model, 'final-U.dat'), uids)
-    vmat = get_embed_from_file(os.path.join(args.model, 'final-V.dat'), vids)
-    bmat = get_embed_from_file(os.path.join(args.model, 'final-B.dat'), vids)
-    lines = []
-    for sc in args.scenarios:
-        te_idl = os.path.join(args.data, 'f%dte.%s.idl' % (args.fold, sc))
+    vids = get_id_dict_from_file(os.path.join(data, 'vid'))
+    umat = get_embed_from_file(os.path.join(model, 'final-U.dat'), uids)
+    vmat = get_embed_from_file(os.path.join(model, 'final-V.dat'), vids)
+    bmat = get_embed_from_file(os.path.join(model, 'final-B.dat'), vids) if use_bias else None
+    lines, kept = [], {}
+    for sc in scenarios:
+        te_idl = os.path.join(data, 'f%dte.%s.idl' % (fold, sc))
         teids = get_id_dict_from_file(te_idl)
         cols = np.fromiter((vids[v] for v in teids), np.int64, count=len(teids))
         temat = np.ascontiguousarray(vmat[cols])
         bias = np.ascontiguousarray(bmat.ravel()[cols]) if bmat is not None else None
         indptr, idx = rated_csr_from_files(uid_file, tr_file, te_idl, len(uids))
-        lists = filtered_topk(umat, temat, args.total, bias, indptr, idx)
-        hits, tcount = count_hits(lists, uid_file, os.path.join(args.data, 'f%dte.%s.txt' % (args.fold, sc)), te_idl,
-                                  args.step, args.total)
+        lists = filtered_topk(umat, temat, total, bias, indptr, idx)
+        hits, tcount = count_hits(lists, uid_file, os.path.join(data, 'f%dte.%s.txt' % (fold, sc)), te_idl, step, total)
         lines.append(sc + ''.join(',%.6f' % (h / tcount) for h in hits))
-    for line in lines:
-        print(line)
-    return lines
+        if keep_lists:
+            kept[sc] = lists.cpu().numpy()
+    return lines, kept
 
 
 if __name__ == '__main__':
