@@ -123,6 +123,51 @@ int tkr_bpr_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, const f
 int tkr_bpr_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                   int64_t batch, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream);
 
+/* ---- multi-GPU plumbing: peer-mapped exchange buffers (one process per GPU, one box) ----
+ * Replaces nothing in the reference (it is single-process); this is how the sharded paths of SURVEY 8(e)
+ * move data: every rank allocates an exchange buffer with tkr_peer_alloc (the one place the library allocates device
+ * memory, explicitly and on request; zero-filled), exports its 64-byte CUDA-IPC handle, the handles travel over any
+ * host channel (topkrec/peer.py uses torch.distributed), every rank imports the others' and hands the table of mapped
+ * base addresses to the fused kernels, which then load from / store to peer HBM over NVLink.  All ranks use the same
+ * buffer layout.  tkr_peer_release unmaps an imported buffer, tkr_peer_free frees an own one. */
+#define TKR_MAX_PEERS 8
+#define TKR_PEER_HANDLE_BYTES 64
+typedef struct tkr_peers {
+    int32_t rank, world;
+    void* base[TKR_MAX_PEERS]; /* base[p] = rank p's exchange buffer as mapped here; base[rank] = the local allocation */
+} tkr_peers;
+int tkr_peer_alloc(size_t bytes, void** out);
+int tkr_peer_free(void* p);
+int tkr_peer_export(void* p, void* handle_out /* TKR_PEER_HANDLE_BYTES, host */);
+int tkr_peer_import(const void* handle /* host */, void** out);
+int tkr_peer_release(void* p);
+
+/* Data-parallel step with the exchange fused into the update (replaces grad + NCCL all-reduce +
+ * apply): users are partitioned over the ranks (U, msU rows never move), the item side lives in the exchange buffer:
+ *     [ V[n_items,d] | b[n_items] | G0 | G1 | flags ]   G* = [GV[n_items,d] | Gb[n_items] | tch[n_items]] (fp32)
+ * (byte offsets from tkr_bpr_dp_layout: TKR_DP_V, _B, _G0, _G1, _FLAGS, _TOTAL).  One call =
+ *   bpr_grad_kernel on this rank's triples (item gradients into G[epoch & 1], user gradients into the workspace), then
+ *   ONE kernel in which: a cross-GPU barrier waits for every rank's gradients; this rank, owner of the item rows
+ *   r % world == rank, LOADS those rows of every peer's G over NVLink, sums them in rank order, applies the optimiser
+ *   update once (slots msV/msb of owned rows are local) and STORES the new V row / bias into every rank's buffer;
+ *   meanwhile other thread blocks apply this rank's user rows and re-zero G[(epoch+1) & 1]; a second barrier closes the
+ *   step.  Every replica of V / b therefore holds identical bits, equal to one GPU stepping the union batch up to fp32
+ *   summation order.  `epoch` must be the same on every rank and grow by 1 per call, starting at 1.  msV / msb rows are
+ *   only meaningful on their owner.  A rank that never arrives trips a 20 s device-side timeout, reported by
+ *   tkr_bpr_dp_status (< 0) instead of hanging the GPU. */
+#define TKR_DP_V 0
+#define TKR_DP_B 1
+#define TKR_DP_G0 2
+#define TKR_DP_G1 3
+#define TKR_DP_FLAGS 4
+#define TKR_DP_TOTAL 5
+#define TKR_DP_NFIELDS 6
+int tkr_bpr_dp_layout(const tkr_bpr_cfg* cfg, int64_t* offsets);
+int tkr_bpr_dp_step(const tkr_bpr_cfg* cfg, float* U, float* msU, float* msV, float* msb, const int32_t* u,
+                    const int32_t* i, const int32_t* j, int64_t batch, const tkr_sampler* smp, uint64_t first_draw,
+                    float* loss_out, void* ws, size_t ws_bytes, const tkr_peers* peers, uint64_t epoch, void* stream);
+int tkr_bpr_dp_status(const tkr_bpr_cfg* cfg, const tkr_peers* peers, void* stream); /* synchronises; 0 = no timeout so far */
+
 /* n_steps consecutive synchronous mini-batch steps.  Step t uses triples
  * [t*batch, (t+1)*batch) of u/i/j and writes the batch objective evaluated
  * before the update to loss_out[t] (what sess.run returns for `obj`).

@@ -78,8 +78,14 @@ def test_c2_1000_steps_of_256_on_the_replayed_reference_sampler(c2):
     ref_loss = bpr_ref.c_bpr_train(ref, u, i, j, B, bpr_ref.BprCfg())
     _compare(dst, ref)
     assert np.allclose(loss.cpu().numpy(), ref_loss, rtol=1e-4)
-    moved = np.abs(ref["U"] - st["U"]).max()
-    assert moved > 1e-3, "1 000 steps must have moved the parameters (%.3g)" % moved
+    # the same bar on the MOVEMENT of every tensor (lr = 1e-4 with rms slots near 1 moves a user row by ~1e-5 in 1 000
+    # steps, far below 1e-4 of max|U|): |delta_gpu - delta_oracle| <= 1 % of max|delta_oracle|.  fp32 itself allows
+    # ~6e-4 here (the fp32 C port against an fp64 run of the same stream, measured in the build container).
+    for name in st:
+        got, want = dst[name].cpu().numpy() - st[name], ref[name] - st[name]
+        moved = np.abs(want).max()
+        assert moved > 0 and np.abs(got - want).max() <= 1e-2 * moved, (name, float(moved), float(np.abs(got - want).max()))
+    assert np.abs(ref["V"] - st["V"]).max() > 1e-3, "1 000 steps must have moved the item factors"
 
 
 # ------------------------------------------------------------------ C3

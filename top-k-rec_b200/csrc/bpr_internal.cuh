@@ -50,4 +50,13 @@ int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, co
 void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                       int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st);
 
+// Plain BPR rows: every column is a parameter; up to 16 KB of shared memory per block for the privatised hot rows
+// (costs nothing when the caller named none: the per-triple slot lookups read zeros).
+inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) {
+    int rows = (16 * 1024) / ((cfg->d + 2) * (int)sizeof(float));
+    if (rows > TKR_MAX_HOT) rows = TKR_MAX_HOT;
+    return StepExtra{cfg->d, b, nullptr, rows};
+}
+
+
 }  // namespace tkr
