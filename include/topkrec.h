@@ -346,6 +346,22 @@ int tkr_als_gram(const float* Y, int32_t d, const int32_t* rows, int64_t n_rows,
 int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,
                    int32_t* out_idx, float* out_score, void* stream);
 
+/* Item-sharded scoring on several GPUs: every rank holds the filtered top-k lists of all `nu`
+ * users of a batch against its own item shard (tkr_score_topk* with col_offset = the shard's first column).
+ * tkr_topk_exchange_push stores row u of this rank's lists into list `rank` of the merge buffer of the row's owner
+ * (owner = u / ceil(nu / world)) over NVLink and raises a flag; tkr_topk_exchange_merge waits for every rank's flag of
+ * the same epoch and merges the world lists of the owned rows into out[rows_owned, k] -- bit-identical to the unsharded
+ * call, each user's final list on exactly one rank.  The exchange buffer (tkr_peer_alloc'ed, tkr_topk_exchange_bytes,
+ * sized for nu_cap users per batch) is double-buffered by epoch parity: push(t+1) may run while merge(t) is pending
+ * (call them on different streams to overlap the exchange with the next batch's scoring).  `epoch` = 1, 2, 3, ... and
+ * the same on every rank.  Barriers time out after 20 s (tkr_topk_exchange_status < 0). */
+size_t tkr_topk_exchange_bytes(int64_t nu_cap, int32_t k, int32_t world);
+int tkr_topk_exchange_push(const int32_t* idx, const float* score, int64_t nu, int64_t nu_cap, int32_t k,
+                           const tkr_peers* peers, uint64_t epoch, void* stream);
+int tkr_topk_exchange_merge(int64_t nu, int64_t nu_cap, int32_t k, const tkr_peers* peers, uint64_t epoch,
+                            int32_t* out_idx, float* out_score, void* stream);
+int tkr_topk_exchange_status(int64_t nu_cap, int32_t k, const tkr_peers* peers, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -334,6 +334,12 @@ static int merge_lists(const int32_t* idx, const float* score, int32_t n_lists, 
     return TKR_OK;
 }
 
+namespace tkr {
+int merge_lists_public(const int32_t* idx, const float* score, int n_lists, int64_t nu, int k, int32_t* out_idx, float* out_score, void* stream) {
+    return merge_lists(idx, score, n_lists, nu, k, out_idx, out_score, nullptr, nullptr, stream);
+}
+}  // namespace tkr
+
 extern "C" int tkr_topk_merge(const int32_t* idx, const float* score, int32_t n_lists, int64_t nu, int32_t k,
                               int32_t* out_idx, float* out_score, void* stream) {
     return merge_lists(idx, score, n_lists, nu, k, out_idx, out_score, nullptr, nullptr, stream);

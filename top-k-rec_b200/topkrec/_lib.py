@@ -68,6 +68,9 @@ def lib():
     L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
     L.tkr_bpr_step_host.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, vp, vp, sz, vp, sz, vp]
     L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
+    L.tkr_bpr_dp_layout.argtypes = [cfgp, C.POINTER(C.c_int64)]
+    L.tkr_bpr_dp_step.argtypes = [cfgp] + [vp] * 4 + [vp] * 3 + [i64, smpp, u64, vp, vp, sz, vp, u64, vp]
+    L.tkr_bpr_dp_status.argtypes = [cfgp, vp, vp]
     vcfgp = C.POINTER(tkr_vbpr_cfg)
     L.tkr_vbpr_workspace_bytes.restype = sz; L.tkr_vbpr_workspace_bytes.argtypes = [vcfgp, i64]
     L.tkr_vbpr_workspace_init.argtypes = [vcfgp, i64, vp, sz, vp]
@@ -81,6 +84,10 @@ def lib():
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.tkr_topk_exchange_bytes.restype = sz; L.tkr_topk_exchange_bytes.argtypes = [i64, i32, i32]
+    L.tkr_topk_exchange_push.argtypes = [vp, vp, i64, i64, i32, vp, u64, vp]
+    L.tkr_topk_exchange_merge.argtypes = [i64, i64, i32, vp, u64, vp, vp, vp]
+    L.tkr_topk_exchange_status.argtypes = [i64, i32, vp, vp]
     L.tkr_eval_hits.argtypes = [vp, i32, vp, vp, vp, i64, vp, vp]
     L.tkr_dat_shape.argtypes = [C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.tkr_dat_read.argtypes = [C.c_char_p, vp, i64, i64]
@@ -91,7 +98,7 @@ def lib():
     L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
     L.tkr_als_gram.argtypes = [vp, i32, vp, i64, C.c_float, C.c_float, vp, vp, sz, vp]
     L.tkr_als_solve_rows.argtypes = [C.POINTER(tkr_als_cfg), C.POINTER(tkr_als_plan), vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    for name in ("tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    for name in ("tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
@@ -246,6 +253,34 @@ def bpr_apply(cfg: BprCfg, U, V, b, msU, msV, msb, batch, ws, data_parallel=Fals
         _check(lib().tkr_bpr_apply(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"),
                                    _dev(msU, f32, "msU"), _dev(msV, f32, "msV"), _dev(msb, f32, "msb"), int(batch),
                                    ws.data_ptr(), ws.numel(), int(bool(data_parallel)), _stream()))
+
+
+DP_FIELDS = ("V", "b", "G0", "G1", "flags", "total")
+
+
+def bpr_dp_layout(cfg: BprCfg):
+    """Byte offsets inside the data-parallel exchange buffer (include/topkrec.h, TKR_DP_*)."""
+    off = (C.c_int64 * len(DP_FIELDS))()
+    _check(lib().tkr_bpr_dp_layout(cfg.ptr, off))
+    return dict(zip(DP_FIELDS, (int(x) for x in off)))
+
+
+def bpr_dp_step(cfg: BprCfg, U, msU, msV, msb, u, i, j, batch, ws, peers, epoch, loss=None, sampler=None, first_draw=0):
+    """tkr_bpr_dp_step: gradient kernel + the fused exchange/update kernel over peer memory.  V and b live in the
+    exchange buffer (``peers``: a topkrec.peer.PeerBuffer)."""
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(U, ws)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_dp_step(cfg.ptr, _dev(U, f32, "U"), _dev(msU, f32, "msU"), _dev(msV, f32, "msV"), _dev(msb, f32, "msb"),
+                                     _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"), int(batch),
+                                     sampler.ptr if sampler is not None else None, int(first_draw), _dev(loss, f32, "loss"),
+                                     ws.data_ptr(), ws.numel(), peers.peers_ptr, int(epoch), _stream()))
+
+
+def bpr_dp_status(cfg: BprCfg, peers):
+    """synchronises the stream; raises if a device-side cross-GPU barrier timed out"""
+    with torch.cuda.device(peers.device):
+        _check(lib().tkr_bpr_dp_status(cfg.ptr, peers.peers_ptr, _stream()))
 
 
 def bpr_step(cfg: BprCfg, U, V, b, msU, msV, msb, u, i, j, batch, n_steps, ws, loss=None, sampler=None, first_draw=0):

@@ -5,8 +5,9 @@
   per-shard candidate lists are exchanged with ONE all-gather and merged with the
   (score desc, column desc) order, so the result is bit-identical to one GPU.
 * BPR: users are partitioned ``u % world == rank`` (U rows and their slots never
-  move); V/b are replicated; per step the contiguous fp32 region [GV | Gb | tchV]
-  of the workspace is all-reduced between ``tkr_bpr_grad`` and ``tkr_bpr_apply``.
+  move); V/b are replicated; per step the item gradients are exchanged and applied by
+  ONE kernel over peer memory (``tkr_bpr_dp_step``: NVLink loads of the owned rows of
+  every rank's accumulator, one update, NVLink stores of the new rows into every replica).
   Equivalent to a single-GPU batch of world*B triples up to fp32 summation order.
 
 The reference is single-process; these semantics are defined by
@@ -65,24 +66,159 @@ def sharded_score_topk(U, V_shard, k, col_offset, bias_shard=None, rated_indptr=
     return merge_fn(allp[:, 0].contiguous(), allp[:, 1].contiguous().view(torch.float32))
 
 
-class DataParallelBpr:
-    """Synchronous data-parallel BPR step over the ranks of ``group``."""
+class ShardedScorer:
+    """Item-sharded filtered top-k with the candidate exchange on peer memory (``tkr_topk_exchange_*``).
 
-    def __init__(self, cfg, state, batch, group=None):
+    Every rank scores the whole user batch against its item shard on the main stream, pushes each user's local list
+    into the merge buffer of the user's owner (rank = row // ceil(n / world)) with NVLink stores, and merges the lists
+    of its own slice on a side stream -- so the exchange + merge of batch t overlap the scoring of batch t+1.  The
+    final list of a user lives on exactly one rank (``submit`` returns this rank's slice) and equals the unsharded
+    result bit for bit.  All ranks must call ``submit`` with batches of the same number of rows, in the same order."""
+
+    def __init__(self, n_items_shard, d, k, user_batch, col_offset, group=None, engine="tc", has_bias=False, device=None):
+        import topkrec
+        from .peer import PeerBuffer
+        self.t, self.group = topkrec, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        self.ni, self.d, self.k, self.nb, self.engine, self.col_offset = int(n_items_shard), int(d), int(k), int(user_batch), engine, int(col_offset)
+        L = topkrec.lib()
+        need = (L.tkr_score_topk_tc_workspace_bytes(self.nb, self.ni, self.d, self.k, int(has_bias)) if engine == "tc"
+                else L.tkr_score_topk_workspace_bytes(self.nb, self.ni, self.d, self.k))
+        with torch.cuda.device(self.dev):
+            self.ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.dev)
+            self.buf = PeerBuffer(L.tkr_topk_exchange_bytes(self.nb, self.k, self.world), group, self.dev)
+            self.side = torch.cuda.Stream(self.dev)
+            self.slice = -(-self.nb // self.world)
+            self.local = [(torch.empty((self.nb, k), dtype=torch.int32, device=self.dev), torch.empty((self.nb, k), dtype=torch.float32, device=self.dev)) for _ in range(2)]
+            self.out = [(torch.empty((self.slice, k), dtype=torch.int32, device=self.dev), torch.empty((self.slice, k), dtype=torch.float32, device=self.dev)) for _ in range(2)]
+            self.pushed = [torch.cuda.Event() for _ in range(2)]
+            self.merged = [torch.cuda.Event() for _ in range(2)]
+        self.epoch = 0
+        self.prepared = False
+        if self.world > 1:
+            dist.barrier(group=group)
+
+    def rows_of(self, n, rank=None):
+        """[beg, end) of the user rows of a batch of n whose final lists live on ``rank`` (default: this rank)"""
+        rank = self.rank if rank is None else rank
+        sl = -(-n // self.world)
+        return min(n, rank * sl), min(n, (rank + 1) * sl)
+
+    def submit(self, U, V_shard, bias_shard=None, rated_indptr=None, rated_idx=None):
+        """Enqueue one user batch; returns (idx, score) device views of this rank's slice, valid on the main stream
+        after ``self.merged[slot]`` (already made a dependency of the main stream before the slot is reused) --
+        call ``wait()`` or read them on ``self.side``.  ``V_shard`` must stay the same table between calls while
+        ``self.prepared`` (its BF16 copy is reused)."""
+        t, L = self.t, self.t.lib()
+        n = U.shape[0]
+        if n > self.nb:
+            raise ValueError("batch of %d rows exceeds the scorer's user_batch %d" % (n, self.nb))
+        self.epoch += 1
+        s = self.epoch & 1
+        main = torch.cuda.current_stream(self.dev)
+        if self.epoch > 2:
+            main.wait_event(self.merged[s])            # the merge of epoch-2 has consumed local[s] / out[s] is free again
+        li, ls = self.local[s][0][:n], self.local[s][1][:n]
+        t.score_topk(U, V_shard, self.k, bias_shard, rated_indptr, rated_idx, col_offset=self.col_offset, engine=self.engine, ws=self.ws,
+                     out=(li, ls), items_prepared=self.prepared and self.engine == "tc" and n == self.nb)
+        self.prepared = n == self.nb
+        with torch.cuda.device(self.dev):
+            t._lib._check(L.tkr_topk_exchange_push(li.data_ptr(), ls.data_ptr(), n, self.nb, self.k, self.buf.peers_ptr, self.epoch, main.cuda_stream))
+            self.pushed[s].record(main)
+            beg, end = self.rows_of(n)
+            oi, osc = self.out[s][0][:end - beg], self.out[s][1][:end - beg]
+            with torch.cuda.stream(self.side):
+                self.side.wait_event(self.pushed[s])
+                t._lib._check(L.tkr_topk_exchange_merge(n, self.nb, self.k, self.buf.peers_ptr, self.epoch, oi.data_ptr(), osc.data_ptr(), self.side.cuda_stream))
+                self.merged[s].record(self.side)
+        return oi, osc
+
+    def wait(self):
+        """main stream waits for every merge submitted so far; raises if a cross-GPU barrier timed out"""
+        main = torch.cuda.current_stream(self.dev)
+        main.wait_stream(self.side)
+        with torch.cuda.device(self.dev):
+            self.t._lib._check(self.t.lib().tkr_topk_exchange_status(self.nb, self.k, self.buf.peers_ptr, main.cuda_stream))
+
+    def close(self):
+        self.buf.close()
+
+
+class DataParallelBpr:
+    """Synchronous data-parallel BPR step over the ranks of ``group``.
+
+    ``exchange='peer'`` (default on more than one rank): ``tkr_bpr_dp_step`` -- the item side (V, b and the double-
+    buffered gradient accumulators) lives in a peer-mapped exchange buffer; the gradient exchange is fused into the
+    update kernel (reduce-scatter by NVLink loads, one RMSProp update per owned item row, all-gather by NVLink stores,
+    two flag barriers), overlapped with this rank's user-row updates.  ``state['V']`` / ``state['b']`` are re-pointed
+    at views of that buffer; msV / msb rows are current only on their owner (row % world) until ``sync_slots()``.
+    ``exchange='nccl'``: tkr_bpr_grad -> ``all_reduce`` of [GV|Gb|tchV] -> tkr_bpr_apply (the round-1 route, kept as
+    the baseline the fused kernel is measured against)."""
+
+    def __init__(self, cfg, state, batch, group=None, exchange=None):
         import topkrec
         self.t = topkrec
         self.cfg, self.st, self.batch, self.group = cfg, state, int(batch), group
-        self.ws = topkrec.bpr_workspace(cfg, batch, state["U"].device)
-        self.item_grads = topkrec.bpr_item_grad_view(cfg, batch, self.ws)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.exchange = exchange or ("peer" if self.world > 1 else "local")
+        dev = state["U"].device
+        self.ws = topkrec.bpr_workspace(cfg, batch, dev)
+        self.item_grads = topkrec.bpr_item_grad_view(cfg, batch, self.ws)
+        self.epoch = 0
+        self.buf = None
+        if self.exchange == "peer":
+            from .peer import PeerBuffer
+            lay = topkrec.bpr_dp_layout(cfg)
+            with torch.cuda.device(dev):
+                self.buf = PeerBuffer(lay["total"], group, dev)
+            V = self.buf.view(lay["V"], (cfg.c.n_items, cfg.c.d))
+            b = self.buf.view(lay["b"], (cfg.c.n_items,))
+            V.copy_(state["V"]); b.copy_(state["b"])
+            state["V"], state["b"] = V, b              # the replicas now live in the exchange buffer
+            torch.cuda.synchronize(dev)
+            if self.world > 1:
+                dist.barrier(group=group)              # every rank's buffer is initialised before anyone steps
 
     def step(self, u=None, i=None, j=None, sampler=None, first_draw=0, loss=None):
         st, t = self.st, self.t
+        if self.exchange == "peer":
+            self.epoch += 1
+            t.bpr_dp_step(self.cfg, st["U"], st["msU"], st["msV"], st["msb"], u, i, j, self.batch, self.ws, self.buf, self.epoch,
+                          loss, sampler, first_draw)
+            return
         dp = self.world > 1
         t.bpr_grad(self.cfg, st["U"], st["V"], st["b"], u, i, j, self.batch, self.ws, loss, sampler, first_draw, data_parallel=dp)
         if dp:
             dist.all_reduce(self.item_grads, op=dist.ReduceOp.SUM, group=self.group)
         t.bpr_apply(self.cfg, st["U"], st["V"], st["b"], st["msU"], st["msV"], st["msb"], self.batch, self.ws, data_parallel=dp)
+
+    def check(self):
+        """synchronise and raise if a cross-GPU barrier of the fused kernel timed out"""
+        if self.exchange == "peer":
+            self.t.bpr_dp_status(self.cfg, self.buf)
+        else:
+            torch.cuda.synchronize(self.st["U"].device)
+
+    def sync_slots(self):
+        """fused route: bring every rank's msV / msb up to date (each row from its owner), e.g. before a checkpoint"""
+        if self.exchange != "peer" or self.world == 1:
+            return
+        for name in ("msV", "msb"):
+            x = self.st[name]
+            mine = torch.zeros_like(x)
+            mine[self.rank::self.world] = x[self.rank::self.world]
+            dist.all_reduce(mine, op=dist.ReduceOp.SUM, group=self.group)
+            x.copy_(mine)
+
+    def close(self):
+        if self.buf is not None:
+            V, b = self.st["V"].clone(), self.st["b"].clone()
+            self.st["V"], self.st["b"] = V, b
+            self.buf.close()
+            self.buf = None
 
 
 def balanced_row_bounds(indptr, world, row_cost=256):
