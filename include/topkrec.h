@@ -102,8 +102,9 @@ int tkr_bpr_workspace_set_hot_items(const tkr_bpr_cfg* cfg, int64_t batch, void*
 #define TKR_WS_CNTV 7
 #define TKR_WS_LISTV 8
 #define TKR_WS_HOTV 9      /* int32 hot_slot[n_items] (0 = cold, s+1 = privatised slot s) then int32 hot_ids[TKR_MAX_HOT] */
-#define TKR_WS_TOTAL 10
-#define TKR_WS_NFIELDS 11
+#define TKR_WS_STAGE 10    /* batches <= 1024: int32[3][65536] triples sampled ahead for the persistent multi-step kernel */
+#define TKR_WS_TOTAL 11
+#define TKR_WS_NFIELDS 12
 #define TKR_MAX_HOT 32
 int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t batch, int64_t* offsets);
 
@@ -258,6 +259,9 @@ void tkr_debug_set_filter_counters(long long* dev_buf);
 /* tkr_bpr_step path choice: -1 automatic (default), 0 never / 1 always (when legal) take the counting path that
  * updates rows occurring once in a batch in place; both paths follow the same step semantics. */
 void tkr_debug_set_count_mode(int32_t mode);
+/* tkr_bpr_step route for batches <= 1024: -1 automatic (default: the persistent cluster kernel, many steps per launch),
+ * 0 never (two launches per step), 1 same as -1; both routes follow the same step semantics. */
+void tkr_debug_set_persist_mode(int32_t mode);
 void tkr_debug_set_filter_mode(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */

@@ -58,7 +58,7 @@ def _assert_ws_clean(cfg, B, ws):
     lay = topkrec.bpr_workspace_layout(cfg, B)
     order = sorted(lay.items(), key=lambda kv: kv[1])
     for (name, beg), (_, end) in zip(order[:-1], order[1:]):
-        if name not in ("listU", "listV", "hotV"):
+        if name not in ("listU", "listV", "hotV", "stage"):
             assert int(ws[beg:end].count_nonzero().item()) == 0, "workspace region %s is not zero after the step" % name
 
 
@@ -136,6 +136,95 @@ def test_bpr_step_count_mode_equals_accumulator_path():
     L.tkr_debug_set_count_mode(-1)
     for name in outs[0]:
         assert _rel(outs[1][name], outs[0][name]) <= 1e-6, name
+
+
+def _set_persist(mode):
+    import ctypes
+    L = topkrec.lib()
+    L.tkr_debug_set_persist_mode.argtypes = [ctypes.c_int32]; L.tkr_debug_set_persist_mode.restype = None
+    L.tkr_debug_set_persist_mode(mode)
+
+
+@pytest.fixture
+def two_kernel_route():
+    """tkr_bpr_step takes the persistent cluster kernel for batches <= 1024 by default; this forces the two-launch route"""
+    _set_persist(0)
+    yield
+    _set_persist(-1)
+
+
+@pytest.mark.parametrize("shape", [(300, 200, 128, 256, 12), (3000, 800, 50, 256, 100), (7, 5, 128, 512, 20), (400, 300, 33, 64, 10),
+                                   (900, 700, 256, 1024, 6), (2000, 1500, 200, 700, 7), (50, 40, 7, 1, 30)])
+def test_bpr_step_two_kernel_route_matches_oracle(two_kernel_route, shape):
+    """the non-persistent route for small batches keeps the same parity bar (it is what larger batches and wide rows use)"""
+    nu, ni, d, B, steps = shape
+    _run_case(nu, ni, d, B, steps, seed=31 + d, item_skew=nu >= 300)
+
+
+@pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 100), (900, 700, 256, 1024, 6), (2000, 1500, 200, 700, 7), (50, 40, 7, 1, 30), (300, 200, 128, 97, 9)])
+def test_bpr_step_persistent_kernel_matches_oracle(shape):
+    """persistent cluster kernel (default for B <= 1024, d <= 256): one triple per warp (B <= 256) and the list path
+    (256 < B <= 1024), ragged batch sizes, a single triple"""
+    nu, ni, d, B, steps = shape
+    _run_case(nu, ni, d, B, steps, seed=41 + d, item_skew=nu >= 300)
+
+
+@pytest.mark.parametrize("kw", [dict(mode="l1"), dict(optimizer="sgd"), dict(lambda_b=0.05), dict(lr=1e-2, lambda_u=0.1, lambda_i=0.05, lambda_j=0.01, lambda_b=0.02)])
+def test_bpr_step_persistent_kernel_modes(kw):
+    _run_case(200, 150, 64, 256, 25, seed=42, cfg_kw=kw, init_scale=10.0)
+    _run_case(200, 150, 64, 600, 8, seed=43, cfg_kw=kw, init_scale=10.0)
+
+
+def test_bpr_step_persistent_equals_two_kernel_route_and_repeated_rows():
+    """same stream through both routes: equal to atomic-order noise; includes triples with i == j and a batch made of one
+    user (every warp claims the same row: exactly one updater)"""
+    rng = np.random.default_rng(44)
+    nu, ni, d, B, steps = 500, 300, 128, 256, 30
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    u = rng.integers(0, nu, B * steps).astype(np.int32); i = rng.integers(0, ni, B * steps).astype(np.int32); j = rng.integers(0, ni, B * steps).astype(np.int32)
+    j[:40] = i[:40]                      # degenerate triples (explicit streams may contain them)
+    u[B:2 * B] = 7                       # step 1: one user, 256 occurrences
+    i[2 * B:3 * B] = 11                  # step 2: one positive item
+    cfg = topkrec.BprCfg(nu, ni, d, lambda_b=0.01)
+    outs = []
+    for mode in (0, 1):
+        _set_persist(mode)
+        dst = _to_dev(st)
+        ws = topkrec.bpr_workspace(cfg, B)
+        loss = torch.empty(steps, device="cuda")
+        topkrec.bpr_step(cfg, dst["U"], dst["V"], dst["b"], dst["msU"], dst["msV"], dst["msb"], torch.from_numpy(u).cuda(),
+                         torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, ws, loss)
+        outs.append({k: v.cpu().numpy() for k, v in dst.items()} | {"loss": loss.cpu().numpy()})
+        _assert_ws_clean(cfg, B, ws)
+    _set_persist(-1)
+    for name in outs[0]:
+        assert _rel(outs[1][name], outs[0][name]) <= 2e-6, name
+    ref = {k: v.copy() for k, v in st.items()}
+    ref_loss = bpr_ref.bpr_train(ref, u, i, j, B, bpr_ref.BprCfg(lambda_b=0.01))
+    for name in ref:
+        assert _rel(outs[1][name], ref[name]) <= REL_TOL, name
+    assert np.allclose(outs[1]["loss"], ref_loss, rtol=1e-4)
+
+
+def test_bpr_step_persistent_fused_sampler_chunks(mini):
+    """fused sampler + persistent kernel: the triples of a chunk of steps are drawn into the workspace first; 700 steps of
+    256 cross the 65 536-triple staging buffer twice and must equal sampling everything up front"""
+    tr_users, tr_data, indptr, idx, nu, ni = _mini_tables(mini)
+    rng = np.random.default_rng(45)
+    d, B, steps, first = 64, 256, 700, 12345
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    smp = topkrec.Sampler(tr_users, indptr, idx, ni, seed=77)
+    cfg = topkrec.BprCfg(nu, ni, d)
+    ws = topkrec.bpr_workspace(cfg, B)
+    a, b2 = _to_dev(st), _to_dev(st)
+    la = torch.empty(steps, device="cuda"); lb = torch.empty(steps, device="cuda")
+    topkrec.bpr_step(cfg, a["U"], a["V"], a["b"], a["msU"], a["msV"], a["msb"], None, None, None, B, steps, ws, la, sampler=smp, first_draw=first)
+    u, i, j = topkrec.bpr_sample(smp, first, B * steps)
+    topkrec.bpr_step(cfg, b2["U"], b2["V"], b2["b"], b2["msU"], b2["msV"], b2["msb"], u, i, j, B, steps, ws, lb)
+    for n in a:
+        assert _rel(a[n].cpu().numpy(), b2[n].cpu().numpy()) <= 2e-6, n
+    assert np.allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-5)
+    _assert_ws_clean(cfg, B, ws)
 
 
 @pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 40), (5000, 1000, 128, 1 << 15, 4), (7, 5, 128, 512, 8), (900, 700, 256, 4096, 5),

@@ -19,7 +19,11 @@ struct StepWs {            // views into the caller's workspace
     int32_t* n_touched;    // [0] touched user rows, [1] touched item rows, [2] apply blocks finished
     int32_t* hot_slot;     // [n_items] 0 = cold, s+1 = the row's gradients are privatised in slot s of every block
     int32_t* hot_ids;      // [TKR_MAX_HOT] item id of slot s (-1 = unused)
+    int32_t* stage;        // batches <= kPersistMaxBatch: 3 x kStageTriples ids sampled ahead for the persistent kernel (else NULL)
 };
+
+constexpr int64_t kPersistMaxBatch = 1024;     // batches up to this size take the persistent multi-step kernel (bpr_persist.cu)
+constexpr int64_t kStageTriples = 1 << 16;
 
 // VBPR rides on the same kernels with concatenated rows U' = [ur|uc], V' = [ir | F.E]:
 //   item_cols  leading columns of an item row that are parameters (regularised, updated); the rest is the
@@ -47,6 +51,10 @@ int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, co
                       const int32_t* i, const int32_t* j, int64_t B, const SamplerDev& smp, uint64_t first_draw,
                       const StepWs& ws, int mode, const StepExtra& ex, float* loss, cudaStream_t st,
                       float* msU = nullptr, float* msV = nullptr);   // the slots are only needed by MODE_COUNT
+extern int g_persist_mode;
+bool bpr_persist_legal(const tkr_bpr_cfg* cfg, int64_t B);
+int bpr_persist_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
+                      const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const StepWs& ws, float* loss, cudaStream_t st);
 void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,
                       int64_t B, const StepWs& ws, int mode, const StepExtra& ex, cudaStream_t st);
 

@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
     }
 }
 
-struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, hotV, total; };
+struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, hotV, stage, total; };
 
 WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     WsLayout L;
@@ -390,6 +390,8 @@ WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     L.cntV = take(ni * 4);
     L.listV = take((size_t)(2 * B < (int64_t)ni ? 2 * B : (int64_t)ni) * 4);
     L.hotV = take(ni * 4 + TKR_MAX_HOT * 4);
+    // small batches (persistent multi-step kernel): room for kStageTriples sampled triples, drawn a chunk of steps ahead
+    L.stage = take(B <= kPersistMaxBatch ? (size_t)3 * kStageTriples * 4 : 0);
     L.total = o;
     return L;
 }
@@ -404,6 +406,7 @@ int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, Step
     out->n_touched = (int32_t*)(p + L.n_touched);
     out->listU = (int32_t*)(p + L.listU); out->listV = (int32_t*)(p + L.listV);
     out->hot_slot = (int32_t*)(p + L.hotV); out->hot_ids = out->hot_slot + cfg->n_items;
+    out->stage = B <= kPersistMaxBatch ? (int32_t*)(p + L.stage) : nullptr;
     return TKR_OK;
 }
 
@@ -512,7 +515,7 @@ extern "C" int tkr_bpr_workspace_layout(const tkr_bpr_cfg* cfg, int64_t B, int64
     if (int rc = bpr_check_cfg(cfg, B)) return rc;
     TKR_CHECK_ARG(offsets != nullptr, "offsets is NULL");
     const WsLayout L = ws_layout(cfg, B);
-    const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.hotV, L.total};
+    const size_t v[TKR_WS_NFIELDS] = {L.GU, L.cntU, L.listU, L.n_touched, L.GV, L.Gb, L.tchV, L.cntV, L.listV, L.hotV, L.stage, L.total};
     for (int t = 0; t < TKR_WS_NFIELDS; ++t) offsets[t] = (int64_t)v[t];
     return TKR_OK;
 }
@@ -642,6 +645,23 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     const int mode = pick_step_mode(cfg, B, u != nullptr);
     const StepExtra ex = plain_extra(cfg, b);
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
+    // Small batches (the reference's batch_size = 256, bpr.py:103): the persistent cluster kernel runs many steps per
+    // launch.  With the fused sampler the triples of a chunk of steps are drawn into the workspace first (same draws).
+    if (g_persist_mode != 0 && mode != MODE_COUNT && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch) {
+        const int64_t chunk = u ? n_steps : kStageTriples / B;
+        for (int64_t t = 0; t < n_steps; t += chunk) {
+            const int64_t ns = n_steps - t < chunk ? n_steps - t : chunk;
+            const int32_t *ut = u ? u + t * B : w.stage, *it = u ? i + t * B : w.stage + kStageTriples, *jt = u ? j + t * B : w.stage + 2 * kStageTriples;
+            if (u == nullptr) {
+                int64_t blocks = (ns * B + 255) / 256;
+                if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+                sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(sd, first_draw + (uint64_t)t * (uint64_t)B, ns * B, w.stage, w.stage + kStageTriples, w.stage + 2 * kStageTriples);
+                TKR_LAUNCH_CHECK();
+            }
+            if (int rc = bpr_persist_steps(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, ns, w, loss_out ? loss_out + t : nullptr, st)) return rc;
+        }
+        return TKR_OK;
+    }
     for (int64_t t = 0; t < n_steps; ++t) {
         const int32_t* ut = u ? u + t * B : nullptr;
         const int32_t* it = u ? i + t * B : nullptr;
@@ -669,11 +689,11 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
     int32_t* di = (int32_t*)p; p += align_up(n * 4, 256);
     int32_t* dj = (int32_t*)p; p += align_up(n * 4, 256);
     float* dl = (float*)p;
-    if (n_steps == 1) {
+    if (n_steps == 1 || (g_persist_mode != 0 && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch)) {
         TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
-        if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du, di, dj, B, 1, nullptr, 0, dl, ws, ws_bytes, stream)) return rc;
+        if (int rc = tkr_bpr_step(cfg, U, V, b, msU, msV, msb, du, di, dj, B, n_steps, nullptr, 0, dl, ws, ws_bytes, stream)) return rc;
     } else {
         // Several steps in one call: the triples of step t+1 travel on a side stream while step t computes
         // (pinned host memory assumed; pageable memory still works, without the overlap).

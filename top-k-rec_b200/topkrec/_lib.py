@@ -201,7 +201,7 @@ def bpr_workspace(cfg: BprCfg, batch, device="cuda"):
     return ws
 
 
-WS_FIELDS = ("GU", "cntU", "listU", "n_touched", "GV", "Gb", "tchV", "cntV", "listV", "hotV", "total")
+WS_FIELDS = ("GU", "cntU", "listU", "n_touched", "GV", "Gb", "tchV", "cntV", "listV", "hotV", "stage", "total")
 MAX_HOT = 32
 
 
