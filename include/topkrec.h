@@ -259,8 +259,9 @@ void tkr_debug_set_filter_counters(long long* dev_buf);
 /* tkr_bpr_step path choice: -1 automatic (default), 0 never / 1 always (when legal) take the counting path that
  * updates rows occurring once in a batch in place; both paths follow the same step semantics. */
 void tkr_debug_set_count_mode(int32_t mode);
-/* tkr_bpr_step route for batches <= 1024: -1 automatic (default: the persistent cluster kernel, many steps per launch),
- * 0 never (two launches per step), 1 same as -1; both routes follow the same step semantics. */
+/* tkr_bpr_step route for small batches: -1 automatic (default: the persistent cluster kernel -- many steps per launch --
+ * for batches <= 256), 0 never (two launches per step), 1 whenever legal (batches <= 1024, d <= 256); both routes follow
+ * the same step semantics. */
 void tkr_debug_set_persist_mode(int32_t mode);
 void tkr_debug_set_filter_mode(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */

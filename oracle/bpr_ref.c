@@ -120,3 +120,15 @@ int tkr_ref_bpr_step(const ref_bpr_cfg* c, float* U, float* V, float* b, float* 
     free(s); free(up); free(ul); free(GU); free(key); free(vp); free(vl);
     return 0;
 }
+
+/* bench.py's CPU legs: torch.distributed.run exports OMP_NUM_THREADS=1 to every rank, which would make the "all host
+ * cores" baseline single-threaded; n > 0 sets the team size explicitly, the return value is the size in effect. */
+#ifdef _OPENMP
+#include <omp.h>
+int tkr_ref_omp_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int tkr_ref_omp_threads(int n) { (void)n; return 1; }
+#endif

@@ -161,8 +161,16 @@ def test_bpr_step_two_kernel_route_matches_oracle(two_kernel_route, shape):
     _run_case(nu, ni, d, B, steps, seed=31 + d, item_skew=nu >= 300)
 
 
+@pytest.fixture
+def persistent_route():
+    """force the persistent cluster kernel wherever it is legal (B <= 1024; the automatic choice stops at B = 256)"""
+    _set_persist(1)
+    yield
+    _set_persist(-1)
+
+
 @pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 100), (900, 700, 256, 1024, 6), (2000, 1500, 200, 700, 7), (50, 40, 7, 1, 30), (300, 200, 128, 97, 9)])
-def test_bpr_step_persistent_kernel_matches_oracle(shape):
+def test_bpr_step_persistent_kernel_matches_oracle(persistent_route, shape):
     """persistent cluster kernel (default for B <= 1024, d <= 256): one triple per warp (B <= 256) and the list path
     (256 < B <= 1024), ragged batch sizes, a single triple"""
     nu, ni, d, B, steps = shape
@@ -170,7 +178,7 @@ def test_bpr_step_persistent_kernel_matches_oracle(shape):
 
 
 @pytest.mark.parametrize("kw", [dict(mode="l1"), dict(optimizer="sgd"), dict(lambda_b=0.05), dict(lr=1e-2, lambda_u=0.1, lambda_i=0.05, lambda_j=0.01, lambda_b=0.02)])
-def test_bpr_step_persistent_kernel_modes(kw):
+def test_bpr_step_persistent_kernel_modes(persistent_route, kw):
     _run_case(200, 150, 64, 256, 25, seed=42, cfg_kw=kw, init_scale=10.0)
     _run_case(200, 150, 64, 600, 8, seed=43, cfg_kw=kw, init_scale=10.0)
 

@@ -22,7 +22,8 @@ struct StepWs {            // views into the caller's workspace
     int32_t* stage;        // batches <= kPersistMaxBatch: 3 x kStageTriples ids sampled ahead for the persistent kernel (else NULL)
 };
 
-constexpr int64_t kPersistMaxBatch = 1024;     // batches up to this size take the persistent multi-step kernel (bpr_persist.cu)
+constexpr int64_t kPersistMaxBatch = 1024;     // batches up to this size CAN take the persistent multi-step kernel (bpr_persist.cu)
+constexpr int64_t kPersistAutoBatch = 256;     // ... and up to this size do by default (one triple per warp of the cluster)
 constexpr int64_t kStageTriples = 1 << 16;
 
 // VBPR rides on the same kernels with concatenated rows U' = [ur|uc], V' = [ir | F.E]:

@@ -113,7 +113,7 @@ __device__ __forceinline__ float persist_grad(const tkr_bpr_cfg& cfg, const Row<
         atomicAdd(ws.Gb + i, -s + reg_grad<L1>(bi, cfg.lambda_b));
         atomicAdd(ws.Gb + j, s + reg_grad<L1>(bj, cfg.lambda_b));
     }
-    if (loss_slot) {
+    if (loss_slot) {   // (a shared-memory word of the CTA: 256 same-address global atomics per step would sit in front of the barrier)
         reg = warp_sum(reg);
         if (lane == 0)
             atomicAdd(loss_slot, reg + fmaxf(-x, 0.f) + __logf(1.0f + __expf(-fabsf(x))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b));
@@ -133,6 +133,15 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
     const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
     const bool want_loss = loss_out != nullptr;
     constexpr unsigned FULL = 0xffffffffu;
+    __shared__ float cta_loss;                               // this CTA's share of the step's objective
+    if (threadIdx.x == 0) cta_loss = 0.f;
+    __syncthreads();
+    // Ordering across the cluster comes from the barrier itself (arrive.release / wait.acquire at cluster scope; the
+    // whole grid is one cluster), not from gpu-scope fences: a MEMBAR.GPU in front of each barrier cost more than the
+    // rest of the step.
+    // ids of the next step are fetched one step ahead (they are immutable; a first read comes from DRAM)
+    int un = 0, in_ = 0, jn = 0;
+    if (B <= nwarps && warp < B && n_steps > 0) { un = __ldg(ub + warp); in_ = __ldg(ib + warp); jn = __ldg(jb + warp); }
 
     for (int step = 0; step < n_steps; ++step) {
         const int32_t* us = ub + (int64_t)step * B;
@@ -145,7 +154,8 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
             float bi = 0.f, bj = 0.f;
             Row<VW, NCH> ru, ri, rj, mu, mi, mj;
             if (active) {
-                u = __ldg(us + warp); i = __ldg(is + warp); j = __ldg(js + warp);
+                u = un; i = in_; j = jn;
+                if (step + 1 < n_steps) { un = __ldg(us + B + warp); in_ = __ldg(is + B + warp); jn = __ldg(js + B + warp); }
                 ru.load_cg(U + (int64_t)u * d, d, lane);
                 ri.load_cg(V + (int64_t)i * d, d, lane);
                 rj.load_cg(V + (int64_t)j * d, d, lane);
@@ -155,8 +165,7 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     claim |= (int)(atomicAdd(ws.cntV + i, 1) == 0) << 1;
                     claim |= (int)(atomicAdd(ws.cntV + j, 1) == 0) << 2;
                 }
-                const float s = persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? loss_out + step : nullptr);
-                (void)s;
+                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
                 claim = __shfl_sync(FULL, claim, 0);
                 if (rms) {   // slots of the rows this warp will update: in flight while the cluster synchronises
                     if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
@@ -164,8 +173,8 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (claim & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
                 }
             }
-            __threadfence();
             cluster_sync_all();                              // barrier 1: every gradient of the batch is in the accumulators
+            if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }   // (next write: after barrier 2)
             if (active) {
                 if (claim & 1) {
                     persist_apply<VW, NCH>(cfg, ru, mu, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
@@ -180,7 +189,6 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (lane == 0) persist_apply_bias(cfg, b, msb, ws, j, bj, rms);
                 }
             }
-            __threadfence();
             cluster_sync_all();                              // barrier 2: every row of the batch is updated
         } else {
             // ---- 256 < B <= 1024: a warp takes several triples; first touchers append their rows to the step's lists
@@ -197,10 +205,10 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
                     if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
                 }
-                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? loss_out + step : nullptr);
+                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
             }
-            __threadfence();
             cluster_sync_all();
+            if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }
             const int nU = __ldcg(ws.n_touched + 0), nV = __ldcg(ws.n_touched + 1);
             for (int w = warp; w < nU + nV; w += nwarps) {
                 const bool user = w < nU;
@@ -216,10 +224,8 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     else persist_apply_bias(cfg, b, msb, ws, r, __ldcg(b + r), rms);
                 }
             }
-            __threadfence();
             cluster_sync_all();                              // every row updated, every warp has read the list lengths
             if (warp == 0 && lane == 0) { ws.n_touched[0] = 0; ws.n_touched[1] = 0; }
-            __threadfence();
             cluster_sync_all();                              // ... and they are re-armed before anyone appends again
         }
     }

@@ -647,7 +647,8 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     // Small batches (the reference's batch_size = 256, bpr.py:103): the persistent cluster kernel runs many steps per
     // launch.  With the fused sampler the triples of a chunk of steps are drawn into the workspace first (same draws).
-    if (g_persist_mode != 0 && mode != MODE_COUNT && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch) {
+    // (automatic choice: up to one triple per warp of the cluster; between 257 and 1024 triples the two-launch route is still faster)
+    if (g_persist_mode != 0 && mode != MODE_COUNT && bpr_persist_legal(cfg, B) && B <= (g_persist_mode == 1 ? kPersistMaxBatch : kPersistAutoBatch)) {
         const int64_t chunk = u ? n_steps : kStageTriples / B;
         for (int64_t t = 0; t < n_steps; t += chunk) {
             const int64_t ns = n_steps - t < chunk ? n_steps - t : chunk;
@@ -689,7 +690,7 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
     int32_t* di = (int32_t*)p; p += align_up(n * 4, 256);
     int32_t* dj = (int32_t*)p; p += align_up(n * 4, 256);
     float* dl = (float*)p;
-    if (n_steps == 1 || (g_persist_mode != 0 && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch)) {
+    if (n_steps == 1 || (g_persist_mode != 0 && bpr_persist_legal(cfg, B) && B <= (g_persist_mode == 1 ? kPersistMaxBatch : kPersistAutoBatch))) {
         TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
