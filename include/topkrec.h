@@ -263,6 +263,9 @@ void tkr_debug_set_count_mode(int32_t mode);
  * for batches <= 256), 0 never (two launches per step), 1 whenever legal (batches <= 1024, d <= 256); both routes follow
  * the same step semantics. */
 void tkr_debug_set_persist_mode(int32_t mode);
+/* profiling aid: device int64[8] receiving warp 0's cycles per phase of the persistent kernel (gather+gradient, slot
+ * prefetch, barrier 1, update, barrier 2, steps); NULL (default) disables it */
+void tkr_debug_set_persist_counters(long long* dev_buf);
 void tkr_debug_set_filter_mode(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */

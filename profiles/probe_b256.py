@@ -18,10 +18,10 @@ L.tkr_debug_set_persist_mode.argtypes = [ctypes.c_int32]; L.tkr_debug_set_persis
 tr_users, indptr, pos_idx = bench.synth_interactions()
 smp = topkrec.Sampler(tr_users, indptr, pos_idx, bench.N_ITEMS, seed=123, device=dev)
 out = []
-for (nu, ni, d) in ((70000, 10000, 128), (70000, 10000, 50), (70000, 10000, 256)):
+for (nu, ni, d) in ((70000, 10000, 128), (70000, 10000, 50)):
     st = {k: torch.from_numpy(v).to(dev) for k, v in bench.init_state_np(nu, ni, d).items()}
     cfg = topkrec.BprCfg(nu, ni, d)
-    for B in (64, 256, 512, 1024):
+    for B in (64, 256, 512):
         n_steps = 2048
         ws = topkrec.bpr_workspace(cfg, B, dev)
         loss = torch.zeros(n_steps, device=dev)

@@ -28,6 +28,8 @@ constexpr int kPersistWarps = 256;
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
 template <int VW> struct CgVec;
 template <> struct CgVec<4> { static __device__ __forceinline__ void load(Vec<4>& o, const float* p) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w; } };
@@ -61,6 +63,24 @@ __device__ __forceinline__ void persist_apply(const tkr_bpr_cfg& cfg, Row<VW, NC
             CgVec<VW>::load(g, G + off);
 #pragma unroll
             for (int t = 0; t < VW; ++t) { opt_update(cfg, g.v[t], var.c[k].v[t], ms.c[k].v[t]); z.v[t] = 0.f; }
+            var.c[k].store(pvar + off);
+            if (rms) ms.c[k].store(pms + off);
+            z.store(G + off);
+        }
+    }
+}
+
+// same with the summed gradient already in registers
+template <int VW, int NCH>
+__device__ __forceinline__ void persist_apply_loaded(const tkr_bpr_cfg& cfg, Row<VW, NCH>& var, Row<VW, NCH>& ms, const Row<VW, NCH>& g,
+                                                     float* __restrict__ pvar, float* __restrict__ pms, float* __restrict__ G, int d, int lane, bool rms) {
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int off = (k * 32 + lane) * VW;
+        if (off < d) {
+            Vec<VW> z;
+#pragma unroll
+            for (int t = 0; t < VW; ++t) { opt_update(cfg, g.c[k].v[t], var.c[k].v[t], ms.c[k].v[t]); z.v[t] = 0.f; }
             var.c[k].store(pvar + off);
             if (rms) ms.c[k].store(pms + off);
             z.store(G + off);
@@ -125,7 +145,7 @@ template <int VW, int NCH, bool L1, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
 bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, float* __restrict__ b, float* __restrict__ msU,
                    float* __restrict__ msV, float* __restrict__ msb, const int32_t* __restrict__ ub, const int32_t* __restrict__ ib,
-                   const int32_t* __restrict__ jb, int B, int n_steps, StepWs ws, float* __restrict__ loss_out) {
+                   const int32_t* __restrict__ jb, int B, int n_steps, StepWs ws, float* __restrict__ loss_out, long long* __restrict__ dbg) {
     const int lane = threadIdx.x & 31;
     const int warp = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     const int nwarps = (int)((gridDim.x * (unsigned)blockDim.x) >> 5);
@@ -150,6 +170,9 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
         if (B <= nwarps) {
             // ---- the common case (one triple per warp): the triple's rows stay in registers across the barrier
             const bool active = warp < B;                    // warp-uniform; idle warps only take part in the barriers
+            const bool prof = dbg != nullptr && warp == 0 && lane == 0;
+            long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
+            if (prof) c0 = clock64();
             int u = 0, i = 0, j = 0, claim = 0;              // claim bit 0/1/2: this warp updates the u / i / j row after the barrier
             float bi = 0.f, bj = 0.f;
             Row<VW, NCH> ru, ri, rj, mu, mi, mj;
@@ -166,30 +189,47 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     claim |= (int)(atomicAdd(ws.cntV + j, 1) == 0) << 2;
                 }
                 persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
+                if (prof) c1 = clock64();
                 claim = __shfl_sync(FULL, claim, 0);
-                if (rms) {   // slots of the rows this warp will update: in flight while the cluster synchronises
-                    if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
-                    if (claim & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
-                    if (claim & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
-                }
             }
-            cluster_sync_all();                              // barrier 1: every gradient of the batch is in the accumulators
+            cluster_arrive();                                // barrier 1 (arrive): this warp's gradients are on their way
+            if (active && rms) {   // slots of the rows this warp will update: fetched while the cluster synchronises
+                if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
+                if (claim & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
+                if (claim & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
+            }
+            if (prof) c2 = clock64();
+            cluster_wait();                                  // barrier 1 (wait): every gradient of the batch is in the accumulators
+            if (prof) c3 = clock64();
             if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }   // (next write: after barrier 2)
             if (active) {
+                // every load of the update phase goes out before the first result is used: up to three summed-gradient
+                // rows and the two bias words are one L2 round trip instead of three to five in a row
+                Row<VW, NCH> gu_, gi_, gj_;
+                float gbi = 0.f, gbj = 0.f, mbi = 0.f, mbj = 0.f;
+                if (claim & 1) gu_.load_cg(ws.GU + (int64_t)u * d, d, lane);
+                if (claim & 2) gi_.load_cg(ws.GV + (int64_t)i * d, d, lane);
+                if (claim & 4) gj_.load_cg(ws.GV + (int64_t)j * d, d, lane);
+                if (lane == 0) {
+                    if (claim & 2) { gbi = __ldcg(ws.Gb + i); if (rms) mbi = __ldcg(msb + i); }
+                    if (claim & 4) { gbj = __ldcg(ws.Gb + j); if (rms) mbj = __ldcg(msb + j); }
+                }
                 if (claim & 1) {
-                    persist_apply<VW, NCH>(cfg, ru, mu, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
+                    persist_apply_loaded<VW, NCH>(cfg, ru, mu, gu_, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
                     if (lane == 0) ws.cntU[u] = 0;
                 }
                 if (claim & 2) {
-                    persist_apply<VW, NCH>(cfg, ri, mi, V + (int64_t)i * d, msV + (int64_t)i * d, ws.GV + (int64_t)i * d, d, lane, rms);
-                    if (lane == 0) persist_apply_bias(cfg, b, msb, ws, i, bi, rms);
+                    persist_apply_loaded<VW, NCH>(cfg, ri, mi, gi_, V + (int64_t)i * d, msV + (int64_t)i * d, ws.GV + (int64_t)i * d, d, lane, rms);
+                    if (lane == 0) { opt_update(cfg, gbi, bi, mbi); b[i] = bi; if (rms) msb[i] = mbi; ws.Gb[i] = 0.f; ws.cntV[i] = 0; }
                 }
                 if (claim & 4) {                             // (i == j: the second claim on the row failed, bit 2 is clear)
-                    persist_apply<VW, NCH>(cfg, rj, mj, V + (int64_t)j * d, msV + (int64_t)j * d, ws.GV + (int64_t)j * d, d, lane, rms);
-                    if (lane == 0) persist_apply_bias(cfg, b, msb, ws, j, bj, rms);
+                    persist_apply_loaded<VW, NCH>(cfg, rj, mj, gj_, V + (int64_t)j * d, msV + (int64_t)j * d, ws.GV + (int64_t)j * d, d, lane, rms);
+                    if (lane == 0) { opt_update(cfg, gbj, bj, mbj); b[j] = bj; if (rms) msb[j] = mbj; ws.Gb[j] = 0.f; ws.cntV[j] = 0; }
                 }
             }
+            if (prof) c4 = clock64();
             cluster_sync_all();                              // barrier 2: every row of the batch is updated
+            if (prof) { const long long c5 = clock64(); dbg[0] += c1 - c0; dbg[1] += c2 - c1; dbg[2] += c3 - c2; dbg[3] += c4 - c3; dbg[4] += c5 - c4; dbg[5] += 1; }
         } else {
             // ---- 256 < B <= 1024: a warp takes several triples; first touchers append their rows to the step's lists
             for (int n = warp; n < B; n += nwarps) {
@@ -231,7 +271,8 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
     }
 }
 
-int g_persist_mode = -1;   // -1 auto (default), 0 never, 1 whenever legal (tkr_debug_set_persist_mode)
+int g_persist_mode = -1;
+long long* g_persist_dbg = nullptr;   // device int64[8]: cycles per phase of warp 0 (tkr_debug_set_persist_counters)   // -1 auto (default), 0 never, 1 whenever legal (tkr_debug_set_persist_mode)
 
 bool bpr_persist_legal(const tkr_bpr_cfg* cfg, int64_t B) {
     const int d = cfg->d;
@@ -265,7 +306,7 @@ static int launch_persist_l1(const tkr_bpr_cfg* cfg, float* U, float* V, float* 
         use_wide = ok ? 1 : 0;
     }
     ClusterLaunch cl(use_wide ? kPersistWarps / 16 : kPersistWarps / 32, use_wide ? 512 : 1024, st);
-    cudaError_t e = cudaLaunchKernelEx(&cl.lc, use_wide ? wide : tall, *cfg, U, V, b, msU, msV, msb, u, i, j, B, n_steps, ws, loss);
+    cudaError_t e = cudaLaunchKernelEx(&cl.lc, use_wide ? wide : tall, *cfg, U, V, b, msU, msV, msb, u, i, j, B, n_steps, ws, loss, g_persist_dbg);
     if (e != cudaSuccess) { set_error("persistent step kernel launch failed: %s", cudaGetErrorString(e)); return TKR_ERR_CUDA; }
     TKR_LAUNCH_CHECK();
     return TKR_OK;
@@ -293,4 +334,5 @@ int bpr_persist_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
 
 }  // namespace tkr
 
+extern "C" void tkr_debug_set_persist_counters(long long* dev_buf) { tkr::g_persist_dbg = dev_buf; }
 extern "C" void tkr_debug_set_persist_mode(int32_t m) { tkr::g_persist_mode = m < -1 || m > 1 ? -1 : m; }
