@@ -102,7 +102,7 @@ int tkr_bpr_workspace_set_hot_items(const tkr_bpr_cfg* cfg, int64_t batch, void*
 #define TKR_WS_CNTV 7
 #define TKR_WS_LISTV 8
 #define TKR_WS_HOTV 9      /* int32 hot_slot[n_items] (0 = cold, s+1 = privatised slot s) then int32 hot_ids[TKR_MAX_HOT] */
-#define TKR_WS_STAGE 10    /* batches <= 1024: int32[3][65536] triples sampled ahead for the persistent multi-step kernel */
+#define TKR_WS_STAGE 10    /* batches <= 1024: 256 B of barrier words + int32[3][65536] triples sampled ahead for the persistent multi-step kernel */
 #define TKR_WS_TOTAL 11
 #define TKR_WS_NFIELDS 12
 #define TKR_MAX_HOT 32

@@ -20,6 +20,7 @@ struct StepWs {            // views into the caller's workspace
     int32_t* hot_slot;     // [n_items] 0 = cold, s+1 = the row's gradients are privatised in slot s of every block
     int32_t* hot_ids;      // [TKR_MAX_HOT] item id of slot s (-1 = unused)
     int32_t* stage;        // batches <= kPersistMaxBatch: 3 x kStageTriples ids sampled ahead for the persistent kernel (else NULL)
+    uint32_t* sync;        // ... and the persistent kernel's barrier words: [0] arrival counter, [1] its value at the end of the last launch
 };
 
 constexpr int64_t kPersistMaxBatch = 1024;     // batches up to this size CAN take the persistent multi-step kernel (bpr_persist.cu)

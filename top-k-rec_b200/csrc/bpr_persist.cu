@@ -28,8 +28,33 @@ constexpr int kPersistWarps = 256;
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// Grid-wide barrier of the (co-scheduled) cluster through ONE global counter: the CTA synchronises, its thread 0 arrives
+// with a gpu-scope RELEASE (the CTA's gradients / rows are performed at L2 first) and polls with relaxed loads, the CTA
+// synchronises again.  No acquire on the waiting side on purpose: every acquire at cluster scope or wider -- the
+// hardware cluster barrier's wait included -- invalidates the SM's L1 (CCTL.IVALL), and the first loads behind it then
+// took ~3 000 extra cycles per phase (phase counters, profiles/r02_persist_phases.txt); all mutable data is read with
+// ld.global.cg, which never looks at L1, so there is nothing to invalidate.
+struct GridBarrier {
+    uint32_t* counter;
+    uint32_t target;            // value of the counter once every CTA has arrived at the current barrier
+    uint32_t nctas;
+    __device__ __forceinline__ void arrive() {
+        __syncthreads();
+        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    }
+    __device__ __forceinline__ void wait() {
+        if (threadIdx.x == 0) {
+            uint32_t v, spins = 0;
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+                if (++spins > (1u << 28)) __trap();              // a protocol bug traps instead of hanging the GPU
+            } while ((int32_t)(v - target) < 0);
+        }
+        __syncthreads();
+        target += nctas;
+    }
+    __device__ __forceinline__ void sync() { arrive(); wait(); }
+};
 
 template <int VW> struct CgVec;
 template <> struct CgVec<4> { static __device__ __forceinline__ void load(Vec<4>& o, const float* p) { float4 t = __ldcg(reinterpret_cast<const float4*>(p)); o.v[0] = t.x; o.v[1] = t.y; o.v[2] = t.z; o.v[3] = t.w; } };
@@ -155,6 +180,11 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ float cta_loss;                               // this CTA's share of the step's objective
     if (threadIdx.x == 0) cta_loss = 0.f;
+    // barrier counter: ws.sync[0]; its value when this launch started was left in ws.sync[1] by the previous launch
+    GridBarrier gb;
+    gb.counter = ws.sync;
+    gb.nctas = gridDim.x;
+    gb.target = __ldcg(ws.sync + 1) + gridDim.x;
     __syncthreads();
     // Ordering across the cluster comes from the barrier itself (arrive.release / wait.acquire at cluster scope; the
     // whole grid is one cluster), not from gpu-scope fences: a MEMBAR.GPU in front of each barrier cost more than the
@@ -192,14 +222,14 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                 if (prof) c1 = clock64();
                 claim = __shfl_sync(FULL, claim, 0);
             }
-            cluster_arrive();                                // barrier 1 (arrive): this warp's gradients are on their way
+            gb.arrive();                                     // barrier 1 (arrive): this CTA's gradients are performed at L2
             if (active && rms) {   // slots of the rows this warp will update: fetched while the cluster synchronises
                 if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
                 if (claim & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
                 if (claim & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
             }
             if (prof) c2 = clock64();
-            cluster_wait();                                  // barrier 1 (wait): every gradient of the batch is in the accumulators
+            gb.wait();                                       // barrier 1 (wait): every gradient of the batch is in the accumulators
             if (prof) c3 = clock64();
             if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }   // (next write: after barrier 2)
             if (active) {
@@ -228,7 +258,7 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                 }
             }
             if (prof) c4 = clock64();
-            cluster_sync_all();                              // barrier 2: every row of the batch is updated
+            gb.sync();                                       // barrier 2: every row of the batch is updated
             if (prof) { const long long c5 = clock64(); dbg[0] += c1 - c0; dbg[1] += c2 - c1; dbg[2] += c3 - c2; dbg[3] += c4 - c3; dbg[4] += c5 - c4; dbg[5] += 1; }
         } else {
             // ---- 256 < B <= 1024: a warp takes several triples; first touchers append their rows to the step's lists
@@ -247,7 +277,7 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                 }
                 persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
             }
-            cluster_sync_all();
+            gb.sync();
             if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }
             const int nU = __ldcg(ws.n_touched + 0), nV = __ldcg(ws.n_touched + 1);
             for (int w = warp; w < nU + nV; w += nwarps) {
@@ -264,11 +294,13 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     else persist_apply_bias(cfg, b, msb, ws, r, __ldcg(b + r), rms);
                 }
             }
-            cluster_sync_all();                              // every row updated, every warp has read the list lengths
+            gb.sync();                                       // every row updated, every warp has read the list lengths
             if (warp == 0 && lane == 0) { ws.n_touched[0] = 0; ws.n_touched[1] = 0; }
-            cluster_sync_all();                              // ... and they are re-armed before anyone appends again
+            gb.sync();                                       // ... and they are re-armed before anyone appends again
         }
     }
+    // every CTA has passed the last barrier of this launch; the next launch starts counting from here
+    if (blockIdx.x == 0 && threadIdx.x == 0) ws.sync[1] = gb.target - gb.nctas;
 }
 
 int g_persist_mode = -1;

@@ -391,7 +391,7 @@ WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     L.listV = take((size_t)(2 * B < (int64_t)ni ? 2 * B : (int64_t)ni) * 4);
     L.hotV = take(ni * 4 + TKR_MAX_HOT * 4);
     // small batches (persistent multi-step kernel): room for kStageTriples sampled triples, drawn a chunk of steps ahead
-    L.stage = take(B <= kPersistMaxBatch ? (size_t)3 * kStageTriples * 4 : 0);
+    L.stage = take(B <= kPersistMaxBatch ? 256 + (size_t)3 * kStageTriples * 4 : 0);   // (+ the kernel's barrier words)
     L.total = o;
     return L;
 }
@@ -406,7 +406,8 @@ int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, Step
     out->n_touched = (int32_t*)(p + L.n_touched);
     out->listU = (int32_t*)(p + L.listU); out->listV = (int32_t*)(p + L.listV);
     out->hot_slot = (int32_t*)(p + L.hotV); out->hot_ids = out->hot_slot + cfg->n_items;
-    out->stage = B <= kPersistMaxBatch ? (int32_t*)(p + L.stage) : nullptr;
+    out->sync = B <= kPersistMaxBatch ? (uint32_t*)(p + L.stage) : nullptr;
+    out->stage = B <= kPersistMaxBatch ? (int32_t*)(p + L.stage + 256) : nullptr;
     return TKR_OK;
 }
 
