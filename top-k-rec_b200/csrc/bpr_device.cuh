@@ -56,7 +56,10 @@ template <bool L1> __device__ __forceinline__ float reg_val(float x, float lam) 
 __device__ __forceinline__ void opt_update(const tkr_bpr_cfg& cfg, float g, float& v, float& m) {
     if (cfg.optimizer == TKR_OPT_RMSPROP) {
         m = cfg.rms_decay * m + (1.0f - cfg.rms_decay) * g * g;
-        v = v - cfg.lr * g / sqrtf(m + cfg.rms_eps);
+        // rsqrt * lr * g: the form of TF's SparseApplyRMSProp kernel (training_ops.cc).  One MUFU.RSQ (<= 2 ulp) instead of
+        // an IEEE sqrt and an IEEE divide: in the persistent small-batch kernel those two were 1 800 of a row update's
+        // cycles on the critical path; the update term is lr-scaled, 2 ulp of it is ~1e-11 of the parameter.
+        v = v - cfg.lr * g * rsqrtf(m + cfg.rms_eps);
     } else {
         v = v - cfg.lr * g;
     }

@@ -126,7 +126,7 @@ __device__ __forceinline__ void persist_apply_bias(const tkr_bpr_cfg& cfg, float
 // one triple, whole warp: x, s = sigma(-x), per-occurrence gradients into the accumulators, loss term (App. A.1-A.2)
 template <int VW, int NCH, bool L1>
 __device__ __forceinline__ float persist_grad(const tkr_bpr_cfg& cfg, const Row<VW, NCH>& ru, const Row<VW, NCH>& ri, const Row<VW, NCH>& rj,
-                                              float bi, float bj, int u, int i, int j, const StepWs& ws, int d, int lane, float* loss_slot) {
+                                              float bi, float bj, int u, int i, int j, const StepWs& ws, int d, int lane, bool want_reg, float& x_out, float& reg_out) {
     constexpr unsigned FULL = 0xffffffffu;
     float x = 0.f;
 #pragma unroll
@@ -149,7 +149,7 @@ __device__ __forceinline__ float persist_grad(const tkr_bpr_cfg& cfg, const Row<
                 a.v[e] = fmaf(-s, ri.c[k].v[e] - rj.c[k].v[e], reg_grad<L1>(ru.c[k].v[e], cfg.lambda_u));
                 p.v[e] = fmaf(-s, ru.c[k].v[e], reg_grad<L1>(ri.c[k].v[e], cfg.lambda_i));
                 q.v[e] = fmaf(s, ru.c[k].v[e], reg_grad<L1>(rj.c[k].v[e], cfg.lambda_j));
-                if (loss_slot) reg += reg_val<L1>(ru.c[k].v[e], cfg.lambda_u) + reg_val<L1>(ri.c[k].v[e], cfg.lambda_i) + reg_val<L1>(rj.c[k].v[e], cfg.lambda_j);
+                if (want_reg) reg += reg_val<L1>(ru.c[k].v[e], cfg.lambda_u) + reg_val<L1>(ri.c[k].v[e], cfg.lambda_i) + reg_val<L1>(rj.c[k].v[e], cfg.lambda_j);
             }
             a.red_add(gu + off); p.red_add(gi + off); q.red_add(gj + off);
         }
@@ -158,12 +158,18 @@ __device__ __forceinline__ float persist_grad(const tkr_bpr_cfg& cfg, const Row<
         atomicAdd(ws.Gb + i, -s + reg_grad<L1>(bi, cfg.lambda_b));
         atomicAdd(ws.Gb + j, s + reg_grad<L1>(bj, cfg.lambda_b));
     }
-    if (loss_slot) {   // (a shared-memory word of the CTA: 256 same-address global atomics per step would sit in front of the barrier)
-        reg = warp_sum(reg);
-        if (lane == 0)
-            atomicAdd(loss_slot, reg + fmaxf(-x, 0.f) + __logf(1.0f + __expf(-fabsf(x))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b));
-    }
+    x_out = x;
+    reg_out = reg;             // per-lane partial of the regulariser value (summed later, off the critical path)
     return s;
+}
+
+// the triple's term of the batch objective (bpr.py:92-99), added to the CTA's shared word; called between the arrive and
+// the wait of barrier 1 so that its two SFU chains and its shuffle tree overlap the barrier instead of preceding it
+template <bool L1>
+__device__ __forceinline__ void persist_loss(const tkr_bpr_cfg& cfg, float x, float reg, float bi, float bj, int lane, float* cta_loss) {
+    reg = warp_sum(reg);
+    if (lane == 0)
+        atomicAdd(cta_loss, reg + fmaxf(-x, 0.f) + __logf(1.0f + __expf(-fabsf(x))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b));
 }
 
 template <int VW, int NCH, bool L1, int THREADS>
@@ -204,7 +210,7 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
             long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
             if (prof) c0 = clock64();
             int u = 0, i = 0, j = 0, claim = 0;              // claim bit 0/1/2: this warp updates the u / i / j row after the barrier
-            float bi = 0.f, bj = 0.f;
+            float bi = 0.f, bj = 0.f, x_t = 0.f, reg_t = 0.f;
             Row<VW, NCH> ru, ri, rj, mu, mi, mj;
             if (active) {
                 u = un; i = in_; j = jn;
@@ -218,11 +224,12 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     claim |= (int)(atomicAdd(ws.cntV + i, 1) == 0) << 1;
                     claim |= (int)(atomicAdd(ws.cntV + j, 1) == 0) << 2;
                 }
-                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
+                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss, x_t, reg_t);
                 if (prof) c1 = clock64();
                 claim = __shfl_sync(FULL, claim, 0);
             }
             gb.arrive();                                     // barrier 1 (arrive): this CTA's gradients are performed at L2
+            if (active && want_loss) persist_loss<L1>(cfg, x_t, reg_t, bi, bj, lane, &cta_loss);
             if (active && rms) {   // slots of the rows this warp will update: fetched while the cluster synchronises
                 if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
                 if (claim & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
@@ -244,10 +251,16 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (claim & 2) { gbi = __ldcg(ws.Gb + i); if (rms) mbi = __ldcg(msb + i); }
                     if (claim & 4) { gbj = __ldcg(ws.Gb + j); if (rms) mbj = __ldcg(msb + j); }
                 }
+                if (prof) {   // (profiling only: time until the gradient rows have landed, then the first row's update)
+                    float t = gu_.c[0].v[0] + gi_.c[0].v[0] + gj_.c[0].v[0] + gbi + gbj + mu.c[0].v[0] + mi.c[0].v[0] + mj.c[0].v[0];
+                    asm volatile("" ::"f"(t) : "memory");
+                    dbg[6] += clock64() - c3;
+                }
                 if (claim & 1) {
                     persist_apply_loaded<VW, NCH>(cfg, ru, mu, gu_, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
                     if (lane == 0) ws.cntU[u] = 0;
                 }
+                if (prof) dbg[7] += clock64() - c3;
                 if (claim & 2) {
                     persist_apply_loaded<VW, NCH>(cfg, ri, mi, gi_, V + (int64_t)i * d, msV + (int64_t)i * d, ws.GV + (int64_t)i * d, d, lane, rms);
                     if (lane == 0) { opt_update(cfg, gbi, bi, mbi); b[i] = bi; if (rms) msb[i] = mbi; ws.Gb[i] = 0.f; ws.cntV[i] = 0; }
@@ -275,7 +288,9 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
                     if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
                 }
-                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss ? &cta_loss : nullptr);
+                float x_t, reg_t;
+                persist_grad<VW, NCH, L1>(cfg, ru, ri, rj, bi, bj, u, i, j, ws, d, lane, want_loss, x_t, reg_t);
+                if (want_loss) persist_loss<L1>(cfg, x_t, reg_t, bi, bj, lane, &cta_loss);
             }
             gb.sync();
             if (want_loss && threadIdx.x == 0) { atomicAdd(loss_out + step, cta_loss); cta_loss = 0.f; }
