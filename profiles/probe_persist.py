@@ -30,4 +30,4 @@ for (nu, ni, d, B) in ((70000, 10000, 128, 256), (70000, 10000, 128, 64), (2000,
         c = dbg.cpu().numpy()
         n = max(1, int(c[5]))
         print(dict(nu=nu, ni=ni, d=d, B=B, loss=with_loss, us_per_step=1e3 * e0.elapsed_time(e1) / n_steps,
-                   cycles=dict(gather_grad=int(c[0] // n), slot_prefetch=int(c[1] // n), barrier1=int(c[2] // n), update=int(c[3] // n), barrier2=int(c[4] // n), upd_loads_landed=int(c[6] // n), upd_first_row_done=int(c[7] // n))), flush=True)
+                   cycles=dict(gather_grad=int(c[0] // n), slot_prefetch=int(c[1] // n), barrier1=int(c[2] // n), update=int(c[3] // n), barrier2=int(c[4] // n))), flush=True)

@@ -32,8 +32,9 @@ __device__ __forceinline__ void cluster_sync_all() {
 // with a gpu-scope RELEASE (the CTA's gradients / rows are performed at L2 first) and polls with relaxed loads, the CTA
 // synchronises again.  No acquire on the waiting side on purpose: every acquire at cluster scope or wider -- the
 // hardware cluster barrier's wait included -- invalidates the SM's L1 (CCTL.IVALL), and the first loads behind it then
-// took ~3 000 extra cycles per phase (phase counters, profiles/r02_persist_phases.txt); all mutable data is read with
-// ld.global.cg, which never looks at L1, so there is nothing to invalidate.
+// is paired with an L1 invalidation (CCTL.IVALL) this kernel has no use for: all mutable data is read with ld.global.cg,
+// which never looks at L1.  (Measured: same step time as the hardware barrier, profiles/r02_persist_phases.txt -- the cost of a
+// barrier here is the release itself, ~1 000-1 500 cycles of waiting for the CTA's outstanding writes.)
 struct GridBarrier {
     uint32_t* counter;
     uint32_t target;            // value of the counter once every CTA has arrived at the current barrier
@@ -251,16 +252,10 @@ bpr_persist_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V
                     if (claim & 2) { gbi = __ldcg(ws.Gb + i); if (rms) mbi = __ldcg(msb + i); }
                     if (claim & 4) { gbj = __ldcg(ws.Gb + j); if (rms) mbj = __ldcg(msb + j); }
                 }
-                if (prof) {   // (profiling only: time until the gradient rows have landed, then the first row's update)
-                    float t = gu_.c[0].v[0] + gi_.c[0].v[0] + gj_.c[0].v[0] + gbi + gbj + mu.c[0].v[0] + mi.c[0].v[0] + mj.c[0].v[0];
-                    asm volatile("" ::"f"(t) : "memory");
-                    dbg[6] += clock64() - c3;
-                }
                 if (claim & 1) {
                     persist_apply_loaded<VW, NCH>(cfg, ru, mu, gu_, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
                     if (lane == 0) ws.cntU[u] = 0;
                 }
-                if (prof) dbg[7] += clock64() - c3;
                 if (claim & 2) {
                     persist_apply_loaded<VW, NCH>(cfg, ri, mi, gi_, V + (int64_t)i * d, msV + (int64_t)i * d, ws.GV + (int64_t)i * d, d, lane, rms);
                     if (lane == 0) { opt_update(cfg, gbi, bi, mbi); b[i] = bi; if (rms) msb[i] = mbi; ws.Gb[i] = 0.f; ws.cntV[i] = 0; }
