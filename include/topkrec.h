@@ -198,7 +198,10 @@ int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
  *   bsum[n_items] = rb + F.c,  E[d_feat, k/2],  c[d_feat];  rms slots msU, msV (ir columns used), msrb, msE, msc.
  * cfg.base.d = k (even).  tkr_vbpr_project refreshes V[:, k/2:] and bsum from E, c (call it once after
  * initialising / importing E, c, rb); tkr_vbpr_step runs n_steps synchronous steps exactly like
- * tkr_bpr_step (same triple / sampler / loss conventions) and leaves V, bsum projected with the final E, c. */
+ * tkr_bpr_step (same triple / sampler / loss conventions) and leaves V, bsum projected with the final E, c.
+ * Large batches (every item potentially touched per step) with dense features run the two content GEMMs on the tensor
+ * cores (tcgen05 kind::tf32, 3-term split: fp32-level accuracy); the workspace then also holds F^T, built at the first
+ * step and keyed by the address of F -- re-initialise the workspace if the CONTENTS of F change under the same address. */
 typedef struct tkr_vbpr_cfg {
     tkr_bpr_cfg base;
     int32_t d_feat;
@@ -267,6 +270,9 @@ void tkr_debug_set_persist_mode(int32_t mode);
  * prefetch, barrier 1, update, barrier 2, steps); NULL (default) disables it */
 void tkr_debug_set_persist_counters(long long* dev_buf);
 void tkr_debug_set_filter_mode(int32_t mode);
+/* tkr_vbpr_step content GEMMs: -1 automatic (tcgen05 3xTF32 route for large batches with dense 16-byte-aligned features), 0 never
+ * (fp32 CUDA-core GEMMs).  Read when the workspace is SIZED as well: keep it fixed between tkr_vbpr_workspace_bytes and the steps. */
+void tkr_debug_set_vbpr_tc_mode(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */
 

@@ -29,6 +29,21 @@ def _dev_state(st, F, k):
     return d
 
 
+def _set_tc(mode):
+    import ctypes
+    L = topkrec.lib()
+    L.tkr_debug_set_vbpr_tc_mode.argtypes = [ctypes.c_int32]; L.tkr_debug_set_vbpr_tc_mode.restype = None
+    L.tkr_debug_set_vbpr_tc_mode(mode)
+
+
+def _core_ws_bytes(cfg, B):
+    """size of the step workspace without the tensor-core route's buffers (F^T and the pre-split B operands stay non-zero)"""
+    _set_tc(0)
+    n = topkrec.lib().tkr_vbpr_workspace_bytes(cfg.ptr, B)
+    _set_tc(-1)
+    return n
+
+
 def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, **cfg_kw):
     rng = np.random.default_rng(seed)
     st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
@@ -61,7 +76,9 @@ def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, **cfg_kw):
     # export identity (vbpr.py:124-126): the engine state IS (fue, fie, fib)
     fue, fie, fib = bpr_ref.vbpr_export(st, F)
     assert _rel(got["U"], fue) <= REL_TOL and _rel(got["V"], fie) <= REL_TOL and _rel(got["bsum"], fib.ravel()) <= REL_TOL
-    assert int(ws.count_nonzero().item()) <= 4 * (min(B, nu) + min(2 * B, ni)), "accumulators must be re-zeroed (only the row lists may be stale)"
+    core = ws[:_core_ws_bytes(cfg, B)]
+    assert int(core.count_nonzero().item()) <= 4 * (min(B, nu) + min(2 * B, ni)) + 8, "accumulators must be re-zeroed (only the row lists may be stale)"
+    return d
 
 
 @pytest.mark.parametrize("k,dF", [(128, 512), (50, 300), (16, 70), (64, 1030)])
@@ -103,3 +120,50 @@ def test_vbpr_class_end_to_end(tmp_path, mini):
     m.export_embeddings(str(tmp_path / "vbpr"))
     m.train(epochs=1, batch_size=64, epoch_sample_limit=10e2, model_path=str(tmp_path / "vbpr"))
     assert np.isfinite(m.fue).all()
+
+
+def test_vbpr_tensor_core_gemms_fp32_level_accuracy():
+    """the two content GEMMs on tcgen05 kind::tf32 with the 3-term split, at the C3 shape (10 000 x 4096, h = 64): the
+    projection [F.E | F.c] and one step's dE / dc against fp64 -- the error must be fp32-level (plain TF32 would be ~1e-3)"""
+    rng = np.random.default_rng(7)
+    nu, ni, k, dF, B = 2000, 10000, 128, 4096, 1 << 15
+    h = k // 2
+    F = np.abs(rng.standard_normal((ni, dF), dtype=np.float32)); F /= np.linalg.norm(F, axis=1, keepdims=True)
+    st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
+    st["E"] = (0.05 * rng.standard_normal((dF, h))).astype(np.float32)
+    st["c"] = (0.05 * rng.standard_normal(dF)).astype(np.float32)
+    st["rb"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    cfg = topkrec.VbprCfg(nu, ni, k, dF)
+    d = _dev_state(st, F, k)
+    Fd = torch.from_numpy(F).cuda()
+    ws = topkrec.vbpr_workspace(cfg, B)
+    assert ws.numel() > _core_ws_bytes(cfg, B), "this shape must take the tensor-core route"
+    z = torch.zeros(B, dtype=torch.int32, device="cuda")
+    topkrec.vbpr_step(cfg, d, Fd, z, z, z, B, 0, ws, None)                                   # zero steps: just the projection
+    P = F.astype(np.float64) @ st["E"].astype(np.float64)
+    q = st["rb"].astype(np.float64) + F.astype(np.float64) @ st["c"].astype(np.float64)
+    got = d["V"].cpu().numpy()[:, h:]
+    err = np.abs(got - P).max() / np.abs(P).max()
+    errq = np.abs(d["bsum"].cpu().numpy() - q).max() / np.abs(q).max()
+    assert err <= 2e-6 and errq <= 2e-6, (err, errq)
+    # the fp32 CUDA-core projection (tkr_vbpr_project) is no closer to fp64 than that
+    d2 = _dev_state(st, F, k)
+    topkrec.vbpr_project(cfg, d2, Fd)
+    err_cc = np.abs(d2["V"].cpu().numpy()[:, h:] - P).max() / np.abs(P).max()
+    assert err <= 4 * err_cc + 1e-7, (err, err_cc)
+
+
+@pytest.mark.parametrize("shape", [(500, 250, 128, 256, 4096, 4), (3000, 1000, 50, 1000, 1 << 14, 3), (800, 129, 16, 68, 2048, 5)])
+def test_vbpr_tensor_core_route_equals_cuda_core_route(shape):
+    """the same stream through both routes of the content GEMMs (ragged M / K tiles, h + 1 not a multiple of 16,
+    split-K gradient): states agree far inside the parity bar, and both meet it against the oracle"""
+    nu, ni, k, dF, B, steps = shape
+    outs = []
+    for mode in (0, -1):
+        _set_tc(mode)
+        try:
+            outs.append({n: v.cpu().numpy() for n, v in _run(nu, ni, k, dF, B, steps, seed=9).items()})
+        finally:
+            _set_tc(-1)
+    for n in outs[0]:
+        assert _rel(outs[1][n], outs[0][n]) <= 2e-5, n

@@ -16,6 +16,15 @@
 
 namespace tkr {
 
+// tensor-core route of the two content GEMMs (gemm_tf32x3.cu)
+int gemm3_np(int h);
+bool gemm3_legal(int M, int K, int h, int64_t a_pitch, const void* A);
+int gemm3_build_b(const float* src, int ld, int off, const float* vec, int K, int Kp, int h, float* Bhi, float* Blo, cudaStream_t st);
+int gemm3_transpose(const float* F, int M, int Kd, int Mp, float* Ft, cudaStream_t st);
+int gemm3_run(int epi, const float* A, int M, int K, int64_t a_pitch, const float* Bhi, const float* Blo, int64_t b_pitch, int h,
+              float* out, int ld, int off, float* vec_out, const float* vec_add, int splits, cudaStream_t st);
+int g_vbpr_tc_mode = -1;   // -1 automatic, 0 never, 1 same as -1 (tkr_debug_set_vbpr_tc_mode: tests run both routes)
+
 constexpr int GT = 64;   // GEMM tile edge (output tile GT x GT per block)
 constexpr int GK = 32;   // K chunk staged per iteration; the four 64-thread groups of a block take 8 k's each
 
@@ -257,12 +266,30 @@ __global__ void __launch_bounds__(256) vbpr_apply_dense_kernel(tkr_bpr_cfg cfg, 
     }
 }
 
-struct VbprWs { StepWs s; float* wq; float* GE; float* Gc; size_t total; };
+struct VbprWs {
+    StepWs s; float* wq; float* GE; float* Gc; size_t total;
+    // tensor-core route (large batches, dense features): F^T built once per workspace, the pre-split B operands per step
+    bool tc; int Mp; float* Ft; float* Bp_hi; float* Bp_lo; float* Bg_hi; float* Bg_lo; unsigned long long* ft_tag;
+};
+
+// The content GEMMs go to the tensor cores when every item row is (potentially) touched each step -- the dense mode of
+// large batches -- and the shapes fit the TMA descriptors; small batches keep the list-driven CUDA-core kernels, which
+// only read the <= 2B touched feature rows.
+static bool vbpr_tc_shape(const tkr_vbpr_cfg* cfg, int64_t B) {
+    const int h = cfg->base.d / 2;
+    return g_vbpr_tc_mode != 0 && bpr_pick_mode(&cfg->base, B, 0) == MODE_DENSE && cfg->d_feat % 4 == 0 && cfg->d_feat >= 64 &&
+           cfg->base.n_items >= 128 && gemm3_np(h) <= 256;
+}
 
 static size_t vbpr_ws_bytes(const tkr_vbpr_cfg* cfg, int64_t B) {
     const size_t h = cfg->base.d / 2;
-    return align_up(bpr_ws_total(&cfg->base, B), 256) + align_up((size_t)cfg->base.n_items * 4, 256) +
-           align_up((size_t)cfg->d_feat * h * 4, 256) + align_up((size_t)cfg->d_feat * 4, 256);
+    size_t n = align_up(bpr_ws_total(&cfg->base, B), 256) + align_up((size_t)cfg->base.n_items * 4, 256) +
+               align_up((size_t)cfg->d_feat * h * 4, 256) + align_up((size_t)cfg->d_feat * 4, 256);
+    if (vbpr_tc_shape(cfg, B)) {
+        const size_t Mp = align_up((size_t)cfg->base.n_items, 4), NP = (size_t)gemm3_np((int)h);
+        n += align_up((size_t)cfg->d_feat * Mp * 4, 1024) + 2 * align_up(NP * cfg->d_feat * 4, 1024) + 2 * align_up(NP * Mp * 4, 1024) + 1024;
+    }
+    return n;
 }
 
 static int vbpr_carve(const tkr_vbpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, VbprWs* out) {
@@ -273,7 +300,19 @@ static int vbpr_carve(const tkr_vbpr_cfg* cfg, int64_t B, void* ws, size_t ws_by
     char* p = (char*)ws + align_up(bpr_ws_total(&cfg->base, B), 256);
     out->wq = (float*)p; p += align_up((size_t)cfg->base.n_items * 4, 256);
     out->GE = (float*)p; p += align_up((size_t)cfg->d_feat * h * 4, 256);
-    out->Gc = (float*)p;
+    out->Gc = (float*)p; p += align_up((size_t)cfg->d_feat * 4, 256);
+    out->tc = vbpr_tc_shape(cfg, B);
+    if (out->tc) {
+        const size_t Mp = align_up((size_t)cfg->base.n_items, 4), NP = (size_t)gemm3_np((int)h);
+        p = (char*)align_up((size_t)(uintptr_t)p, 1024);
+        out->Mp = (int)Mp;
+        out->ft_tag = (unsigned long long*)p; p += 1024;
+        out->Ft = (float*)p; p += align_up((size_t)cfg->d_feat * Mp * 4, 1024);
+        out->Bp_hi = (float*)p; p += align_up(NP * cfg->d_feat * 4, 1024);
+        out->Bp_lo = (float*)p; p += align_up(NP * cfg->d_feat * 4, 1024);
+        out->Bg_hi = (float*)p; p += align_up(NP * Mp * 4, 1024);
+        out->Bg_lo = (float*)p;
+    }
     out->total = need;
     return TKR_OK;
 }
@@ -307,6 +346,8 @@ static void launch_project(const tkr_vbpr_cfg* cfg, const float* F, const float*
 }  // namespace tkr
 
 using namespace tkr;
+
+extern "C" void tkr_debug_set_vbpr_tc_mode(int32_t m) { g_vbpr_tc_mode = m < -1 || m > 1 ? -1 : m; }
 
 extern "C" size_t tkr_vbpr_workspace_bytes(const tkr_vbpr_cfg* cfg, int64_t B) {
     if (cfg == nullptr || B <= 0 || cfg->base.n_users <= 0 || cfg->base.n_items <= 0 || cfg->base.d <= 0 || cfg->d_feat <= 0) return 0;
@@ -358,16 +399,43 @@ extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float*
     int splitk = (2 * kNumSMs + tiles - 1) / tiles;
     if (splitk < 1) splitk = 1;
     if (splitk > 64) splitk = 64;
-    for (int64_t t = 0; t < n_steps; ++t) {
-        float* lt = loss_out ? loss_out + t : nullptr;
+    // tensor-core route: F must be 16-byte aligned for the TMA descriptor; F^T is built once per (workspace, F)
+    const bool tc = w.tc && gemm3_legal(bc->n_items, dF, h, dF, F);
+    if (tc) {
+        unsigned long long tag = 0;
+        TKR_CUDA(cudaMemcpyAsync(&tag, w.ft_tag, 8, cudaMemcpyDeviceToHost, st));
+        TKR_CUDA(cudaStreamSynchronize(st));
+        if (tag != (unsigned long long)(uintptr_t)F) {            // (a workspace is zero-initialised: tag 0 = not built)
+            if (int rc = gemm3_transpose(F, bc->n_items, dF, w.Mp, w.Ft, st)) return rc;
+            tag = (unsigned long long)(uintptr_t)F;
+            TKR_CUDA(cudaMemcpyAsync(w.ft_tag, &tag, 8, cudaMemcpyHostToDevice, st));
+            TKR_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    const int tc_splits = tc ? (kNumSMs + (dF + 127) / 128 - 1) / ((dF + 127) / 128) : 1;
+    auto project = [&]() -> int {
+        if (tc) {
+            if (int rc = gemm3_build_b(E, h, 0, c, dF, dF, h, w.Bp_hi, w.Bp_lo, st)) return rc;
+            return gemm3_run(0, F, bc->n_items, dF, dF, w.Bp_hi, w.Bp_lo, dF, h, V, bc->d, h, bsum, rb, 1, st);
+        }
         launch_project(cfg, F, E, c, rb, V, bsum, st);
         TKR_LAUNCH_CHECK();
+        return TKR_OK;
+    };
+    for (int64_t t = 0; t < n_steps; ++t) {
+        float* lt = loss_out ? loss_out + t : nullptr;
+        if (int rc = project()) return rc;
         if (int rc = bpr_dispatch_grad(bc, U, V, bsum, u ? u + t * B : nullptr, u ? i + t * B : nullptr, u ? j + t * B : nullptr, B, sd,
                                        first_draw + (uint64_t)t * (uint64_t)B, w.s, mode, ex, lt, st)) return rc;
-        dim3 grid((dF + GT - 1) / GT, (h + GT - 1) / GT, splitk);
-        vbpr_grad_dense_kernel<<<grid, 256, 0, st>>>(F, dF, w.s.GV, bc->d, h, h, w.wq, mode == MODE_LIST ? w.s.listV : nullptr,
-                                                     w.s.n_touched + 1, bc->n_items, w.GE, w.Gc);
-        TKR_LAUNCH_CHECK();
+        if (tc) {   // [dE | dc] += F^T . [W | wq] over all items (untouched rows of W are zero)
+            if (int rc = gemm3_build_b(w.s.GV, bc->d, h, w.wq, bc->n_items, w.Mp, h, w.Bg_hi, w.Bg_lo, st)) return rc;
+            if (int rc = gemm3_run(1, w.Ft, dF, bc->n_items, w.Mp, w.Bg_hi, w.Bg_lo, w.Mp, h, w.GE, h, 0, w.Gc, nullptr, tc_splits, st)) return rc;
+        } else {
+            dim3 grid((dF + GT - 1) / GT, (h + GT - 1) / GT, splitk);
+            vbpr_grad_dense_kernel<<<grid, 256, 0, st>>>(F, dF, w.s.GV, bc->d, h, h, w.wq, mode == MODE_LIST ? w.s.listV : nullptr,
+                                                         w.s.n_touched + 1, bc->n_items, w.GE, w.Gc);
+            TKR_LAUNCH_CHECK();
+        }
         bpr_launch_apply(bc, U, V, rb, msU, msV, msrb, B, w.s, mode, ex, st);
         TKR_LAUNCH_CHECK();
         const int64_t nE = (int64_t)dF * h;
@@ -377,7 +445,6 @@ extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float*
         TKR_LAUNCH_CHECK();
     }
     // leave V[:, h:] = F.E and bsum = rb + F.c consistent with the final E, c: they ARE the export (vbpr.py:124-126)
-    launch_project(cfg, F, E, c, rb, V, bsum, st);
-    TKR_LAUNCH_CHECK();
+    if (int rc = project()) return rc;
     return TKR_OK;
 }
