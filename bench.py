@@ -150,14 +150,6 @@ def device_time_ms(fn, reps, warm=2):
     return e0.elapsed_time(e1) / reps
 
 
-def measured_l2_copy_gbs(dev):
-    """read+write rate of a device copy whose 2 x 24 MB stay in the 126 MB L2 -- the roof of an L2-resident gather/scatter"""
-    import torch
-    a = torch.empty(24 << 20, dtype=torch.uint8, device=dev); b = torch.empty_like(a)
-    ms = device_time_ms(lambda: b.copy_(a), 200, 20)
-    return 2 * a.numel() / (ms / 1e3) / 1e9
-
-
 def measured_fp32_tflops(dev):
     """cuBLAS SGEMM 8192^3 with TF32 off: the FMA-pipe roof used for the fp32 kernels (ALS, VBPR content GEMMs)"""
     import torch
@@ -375,12 +367,10 @@ def run_ours(args, rank, local_rank, world):
                             "traffic_source": "ncu --set full of this configuration, profiles/r02a_ncu_bpr_streaming.txt (dram read + write of the three launches of a step)",
                             "note": "tables far beyond L2: every row comes from HBM.  The headline workload (C2, 123 MB of state) is L2-resident; its rate is in roofline.c2",
                             "c2": {"achieved_algorithmic_gbs": achieved_c2, "frac_of_hbm_peak": achieved_c2 / peaks["hbm_gbs"],
-                                   "l2_resident": True, "l2_copy_gbs_measured": None, "frac_of_l2_copy": None,
-                                   "dram_traffic_per_minibatch": profile_traffic("bpr_step"),
+                                   "l2_resident": True, "dram_traffic_per_minibatch": profile_traffic("bpr_step"),
                                    "note": "algorithmic bytes (duplicates counted per triple) / mini-batch time; > HBM peak because parameters, slots and accumulators "
-                                           "stay in the 126 MB L2 (ncu: 0.32 GB of DRAM traffic per 6.49 GB algorithmic); the roof there is L2 / atomic throughput"}}
-        l2 = measured_l2_copy_gbs(dev)
-        line["roofline"]["c2"].update(l2_copy_gbs_measured=l2, frac_of_l2_copy=achieved_c2 / l2)
+                                           "stay in the 126 MB L2 and the ~200 occurrences of a popular item row per mini-batch are served on chip (ncu: 0.32 GB of DRAM traffic per 6.49 GB "
+                                           "algorithmic); what binds there is gather latency and L2 atomic throughput (profiles/r01p_ncu_bpr.txt), not a bandwidth roof"}}
     barrier()
 
     if world == 1 and not args.skip_sweep:
@@ -503,6 +493,7 @@ def vbpr_points(smp, dev, fp32_peak, d_feat=4096, k=128):
     out = []
     for B, n_steps in ((256, 256), (1 << 16, 16), (1 << 20, 4)):
         ws = topkrec.vbpr_workspace(cfg, B, dev)
+        topkrec.vbpr_set_hot_items(cfg, B, ws, topkrec.popular_items(smp.pos_idx, N_ITEMS))
         loss = torch.zeros(n_steps, dtype=torch.float32, device=dev)
         state = {"r": 0}
 
@@ -724,9 +715,11 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
                     if eng == "tc" else "f32 (exact fma-chain scores, CUDA cores)",
            "gpu_launches": launches, "clocks": clk.summary(),
            "roofline": {"bound": "tensor", "kernel": "score_filter_kernel" if eng == "tc" else "score_topk_kernel",
-                        "achieved": flops / world / (ms / 1e3) / 1e12, "peak": peaks["bf16_tflops"], "peak_source": peak_src, "unit": "TFLOP/s",
-                        "frac": flops / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
-                        "note": "per GPU: FLOP = 2*nu*(ni/world)*d over the whole step (convert + filter + merge + refine + fallback [+ exchange]), against the burst bf16 peak"},
+                        "achieved": flops / world / (ms / 1e3) / 1e12, "peak": peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                        "peak_source": peak_src + ": sustained cuBLAS bf16 rate (this timed region is >= 1 s of back-to-back tensor work and runs into the power cap, see clocks)",
+                        "unit": "TFLOP/s", "frac": flops / world / (ms / 1e3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
+                        "frac_of_burst_peak": flops / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
+                        "note": "per GPU: FLOP = 2*nu*(ni/world)*d over the whole step (convert + filter + merge + refine + fallback [+ exchange])"},
            "scaling": "strong: the same %d-user batch at every N; item columns sharded over the GPUs, candidates exchanged by user slice over peer memory" % nb}
     if world == 1 and eng == "tc":
         out["rows_redone_by_exact_fallback_last_step"] = int(nfb.item())

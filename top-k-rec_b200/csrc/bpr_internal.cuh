@@ -62,11 +62,11 @@ void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
 
 // Plain BPR rows: every column is a parameter; up to 16 KB of shared memory per block for the privatised hot rows
 // (costs nothing when the caller named none: the per-triple slot lookups read zeros).
-inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) {
-    int rows = (16 * 1024) / ((cfg->d + 2) * (int)sizeof(float));
-    if (rows > TKR_MAX_HOT) rows = TKR_MAX_HOT;
-    return StepExtra{cfg->d, b, nullptr, rows};
+inline int hot_rows_for(int d) {
+    int rows = (16 * 1024) / ((d + 3) * (int)sizeof(float));
+    return rows > TKR_MAX_HOT ? TKR_MAX_HOT : rows;
 }
+inline StepExtra plain_extra(const tkr_bpr_cfg* cfg, const float* b) { return StepExtra{cfg->d, b, nullptr, hot_rows_for(cfg->d)}; }
 
 
 }  // namespace tkr

@@ -138,12 +138,13 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
     constexpr unsigned FULL = 0xffffffffu;
     // Popular item rows named by the caller (tkr_bpr_workspace_set_hot_items) are summed here, per block, and added to
     // the global accumulators once at the end: one L2 atomic per block instead of one per occurrence.
-    extern __shared__ float hot_smem[];                        // [hmax][d] rows, [hmax] biases, [hmax] dirty flags
+    extern __shared__ float hot_smem[];                        // [hmax][d] rows, [hmax] biases, [hmax] dirty flags, [hmax] wq sums
     const int hmax = ex.hot_rows;
     float* hot_b = hot_smem + (size_t)hmax * d;
     float* hot_dirty = hot_b + hmax;
+    float* hot_wq = hot_dirty + hmax;
     if (hmax > 0) {
-        for (int t = threadIdx.x; t < hmax * (d + 2); t += blockDim.x) hot_smem[t] = 0.f;
+        for (int t = threadIdx.x; t < hmax * (d + 3); t += blockDim.x) hot_smem[t] = 0.f;
         __syncthreads();
     }
 
@@ -261,7 +262,10 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
             const float gbi = -s_mine + reg_grad<L1>(bi, cfg.lambda_b), gbj = s_mine + reg_grad<L1>(bj, cfg.lambda_b);
             if (hs_i) { sh_red_add(hot_b + hs_i - 1, gbi); hot_dirty[hs_i - 1] = 1.f; } else atomicAdd(ws.Gb + i, gbi);
             if (hs_j) { sh_red_add(hot_b + hs_j - 1, gbj); hot_dirty[hs_j - 1] = 1.f; } else atomicAdd(ws.Gb + j, gbj);
-            if (ex.wq != nullptr) { atomicAdd(ex.wq + i, -s_mine); atomicAdd(ex.wq + j, s_mine); }
+            if (ex.wq != nullptr) {
+                if (hs_i) sh_red_add(hot_wq + hs_i - 1, -s_mine); else atomicAdd(ex.wq + i, -s_mine);
+                if (hs_j) sh_red_add(hot_wq + hs_j - 1, s_mine); else atomicAdd(ex.wq + j, s_mine);
+            }
             if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)
                 loss_acc += fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
         }
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
                 for (int e = 0; e < VW; ++e) a.v[e] = hot_smem[(size_t)sl * d + off + e];
                 a.red_add(ws.GV + (int64_t)id * d + off);
             }
-            if (lane == 0) atomicAdd(ws.Gb + id, hot_b[sl]);
+            if (lane == 0) { atomicAdd(ws.Gb + id, hot_b[sl]); if (ex.wq != nullptr) atomicAdd(ex.wq + id, hot_wq[sl]); }
         }
     }
     if (!want_loss) return;
@@ -449,7 +453,7 @@ static void launch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, 
     const int tpw = tpw64 > 32 ? 32 : (int)tpw64;
     int64_t blocks = ((B + tpw - 1) / tpw + 7) / 8;
     if (blocks > grid_cap()) blocks = grid_cap();
-    const size_t hot_bytes = (size_t)ex.hot_rows * (cfg->d + 2) * sizeof(float);
+    const size_t hot_bytes = (size_t)ex.hot_rows * (cfg->d + 3) * sizeof(float);
 #define TKR_K(L1_, S_, IP_) bpr_grad_kernel<VW, NCH, L1_, S_, IP_><<<(unsigned)blocks, 256, hot_bytes, st>>>(*cfg, U, V, b, u, i, j, B, smp, first_draw, ws, mode, tpw, ex, loss, msU, msV)
     if (mode == MODE_COUNT) TKR_K(false, false, true);   // (bpr_pick_mode only returns it for l2 + explicit triples)
     else if (cfg->l1) { if (u == nullptr) TKR_K(true, true, false); else TKR_K(true, false, false); }

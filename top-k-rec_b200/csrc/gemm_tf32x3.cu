@@ -96,6 +96,8 @@ enum { EPI_PROJECT = 0, EPI_GRAD = 1 };
 struct Args {
     int M, K, NP, h;              // rows of A, reduction length, padded N, real content width (column h of C = the vector product)
     int stages, nacc;
+    int wide;                     // 1: ah . [bh | bl] is ONE instruction of N = 2 NP (both B tiles are contiguous in the stage)
+    int keep_raw;                 // 1 (experiment): do not overwrite a with ah -- relies on the tensor core ignoring the low 13 mantissa bits
     int kb_per_split;             // K blocks per blockIdx.y
     // EPI_PROJECT: out[m * ld + off + n] = C[m][n] (n < h), vec_out[m] = vec_add[m] + C[m][h]
     // EPI_GRAD   : out[m * ld + n] += C[m][n] (red.add),     vec_out[m] += C[m][h]
@@ -123,7 +125,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int kb0 = blockIdx.y * p.kb_per_split;
     const int kb1 = min(kb_total, kb0 + p.kb_per_split);
     const int nkb = kb1 - kb0;                                          // >= 1 by construction of the grid
-    const uint32_t tmem_cols = p.nacc * p.NP <= 128 ? 128u : (p.nacc * p.NP <= 256 ? 256u : 512u);
+    const int acc_cols = p.wide ? 2 * p.NP : p.NP;                       // columns of one accumulator
+    const uint32_t tmem_cols = p.nacc * acc_cols <= 128 ? 128u : (p.nacc * acc_cols <= 256 ? 256u : 512u);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(split + s, 4); mbar_init(empty + s, 1); }
@@ -157,7 +160,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(p.NP);
+            const uint32_t idesc = idesc_tf32(p.NP), idesc2 = idesc_tf32(2 * p.NP);
             const uint64_t desc_hi = make_sw128_desc(0);
             for (int it = 0; it < nkb; ++it) {
                 const int s = it % p.stages;
@@ -168,14 +171,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const uint32_t a_hi = (st & 0x3FFFF) >> 4, a_lo = ((st + A_TILE_BYTES) & 0x3FFFF) >> 4;
                 const uint32_t b_hi = ((st + 2 * A_TILE_BYTES) & 0x3FFFF) >> 4, b_lo = ((st + 2 * A_TILE_BYTES + b_tile) & 0x3FFFF) >> 4;
                 const int acc = it % p.nacc;
-                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.NP);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
                 const uint32_t first = it < p.nacc ? 0u : 1u;          // first K block of an accumulator overwrites it
 #pragma unroll
                 for (int ks = 0; ks < BK / 8; ++ks) {                  // K = 8 tf32 = 32 bytes per instruction
                     const uint64_t o = (uint64_t)(ks * 2);
-                    umma_tf32(tmem_d, desc_hi | (a_lo + o), desc_hi | (b_hi + o), idesc, first | (uint32_t)(ks != 0));   // small terms first
-                    umma_tf32(tmem_d, desc_hi | (a_hi + o), desc_hi | (b_lo + o), idesc, 1u);
-                    umma_tf32(tmem_d, desc_hi | (a_hi + o), desc_hi | (b_hi + o), idesc, 1u);
+                    if (p.wide) {
+                        // columns [0, NP) <- ah.bh, [NP, 2NP) <- ah.bl in one instruction (A is read once for both), then al.bh
+                        // on top of the first half: two instructions and 15.5 KB of operand reads per K step instead of three and 19.5
+                        umma_tf32(tmem_d, desc_hi | (a_hi + o), desc_hi | (b_hi + o), idesc2, first | (uint32_t)(ks != 0));
+                        umma_tf32(tmem_d, desc_hi | (a_lo + o), desc_hi | (b_hi + o), idesc, 1u);
+                    } else {
+                        umma_tf32(tmem_d, desc_hi | (a_lo + o), desc_hi | (b_hi + o), idesc, first | (uint32_t)(ks != 0));   // small terms first
+                        umma_tf32(tmem_d, desc_hi | (a_hi + o), desc_hi | (b_lo + o), idesc, 1u);
+                        umma_tf32(tmem_d, desc_hi | (a_hi + o), desc_hi | (b_hi + o), idesc, 1u);
+                    }
                 }
                 umma_commit(empty + s);
             }
@@ -197,7 +207,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float4 hi, lo;
                 hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
                 lo.x = tf32_hi(v.x - hi.x); lo.y = tf32_hi(v.y - hi.y); lo.z = tf32_hi(v.z - hi.z); lo.w = tf32_hi(v.w - hi.w);
-                a[e] = hi; al[e] = lo;
+                if (!p.keep_raw) a[e] = hi;
+                al[e] = lo;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
             __syncwarp();
@@ -215,10 +226,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             for (int e = 0; e < 16; ++e) acc[e] = 0.f;
             for (int a = 0; a < p.nacc && a < nkb; ++a) {
                 uint32_t v[16];
-                tmem_ld16(taddr0 + (uint32_t)(a * p.NP + c0), v);
+                tmem_ld16(taddr0 + (uint32_t)(a * acc_cols + c0), v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[e]);
+                if (p.wide) {
+                    tmem_ld16(taddr0 + (uint32_t)(a * acc_cols + p.NP + c0), v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) acc[e] += __uint_as_float(v[e]);
+                }
             }
             if (m < p.M) {
 #pragma unroll
@@ -318,6 +335,8 @@ static int make_tmap_f32(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
 
 }  // namespace g3
 
+int g_gemm3_flags = 0;   // experiments (tkr_debug_set_gemm3_flags): 1 = keep the raw A tile as ah, 2 = three separate products
+
 // ---- interface used by vbpr_step.cu -------------------------------------------------------------------------------
 int gemm3_np(int h) { return (h + 1 + 15) / 16 * 16; }
 bool gemm3_legal(int M, int K, int h, int64_t a_pitch, const void* A) {
@@ -350,7 +369,10 @@ int gemm3_run(int epi, const float* A, int M, int K, int64_t a_pitch, const floa
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { set_error("gemm_tf32x3: N = %d does not leave room for two pipeline stages", p.NP); return TKR_ERR_UNSUPPORTED; }
     p.stages = stages;
-    p.nacc = 512 / p.NP < 4 ? 512 / p.NP : 4;
+    p.wide = (2 * p.NP <= 256 && !(g_gemm3_flags & 2)) ? 1 : 0;
+    p.keep_raw = (g_gemm3_flags & 1) ? 1 : 0;
+    const int acc_cols = p.wide ? 2 * p.NP : p.NP;
+    p.nacc = 512 / acc_cols < 4 ? 512 / acc_cols : 4;
     const int kb_total = (K + BK - 1) / BK;
     if (splits < 1) splits = 1;
     if (splits > kb_total) splits = kb_total;
@@ -375,3 +397,5 @@ int gemm3_run(int epi, const float* A, int M, int K, int64_t a_pitch, const floa
 }
 
 }  // namespace tkr
+
+extern "C" void tkr_debug_set_gemm3_flags(int32_t f) { tkr::g_gemm3_flags = f; }

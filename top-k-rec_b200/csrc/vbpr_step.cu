@@ -392,7 +392,7 @@ extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float*
     const tkr_bpr_cfg* bc = &cfg->base;
     const int h = bc->d / 2, dF = cfg->d_feat;
     const int mode = bpr_pick_mode(bc, B, 0);
-    const StepExtra ex{h, rb, w.wq};
+    const StepExtra ex{h, rb, w.wq, hot_rows_for(bc->d)};    // popular item rows privatised per block, as in the plain BPR step
     if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     // split-K so that the dE GEMM covers the chip: (dF/64) x (h/64) output tiles
     const int tiles = ((dF + GT - 1) / GT) * ((h + GT - 1) / GT);

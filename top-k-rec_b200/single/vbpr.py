@@ -104,6 +104,9 @@ class VBPR(BPR):
         if self._ws is None or self._ws_batch != batch_size:
             self._ws = topkrec.vbpr_workspace(self._cfg, batch_size, self.device)
             self._ws_batch = batch_size
+            if self.tr_data:      # the most liked items: their gradient sums are privatised per thread block
+                pos = np.fromiter((i for items in self.tr_data.values() for i in items), np.int64)
+                topkrec.vbpr_set_hot_items(self._cfg, batch_size, self._ws, topkrec.popular_items(pos, self.n_items))
         chunk = max(1, min(n_steps, (1 << 20) // batch_size, 1024))
         host_gen = self._uniform_user_sampling(batch_size) if self.sampler_backend == 'numpy' else None
         done = 0

@@ -322,6 +322,15 @@ def vbpr_workspace(cfg: VbprCfg, batch, device="cuda"):
     return ws
 
 
+def vbpr_set_hot_items(cfg: VbprCfg, batch, ws, item_ids):
+    """bpr_set_hot_items for a VBPR workspace (it starts with the BPR step workspace): the named popular item rows get
+    their gradients -- rating part, content part W and the wq sums -- summed per thread block in shared memory."""
+    ids = np.ascontiguousarray(np.asarray(item_ids, np.int32)[:MAX_HOT])
+    with torch.cuda.device(ws.device):
+        _check(lib().tkr_bpr_workspace_set_hot_items(C.byref(cfg.c.base), int(batch), ws.data_ptr(), ws.numel(),
+                                                     ids.ctypes.data if ids.size else None, int(ids.size), _stream()))
+
+
 def vbpr_project(cfg: VbprCfg, st, F):
     """Refresh st['V'][:, k/2:] = F.E and st['bsum'] = rb + F.c."""
     f32 = torch.float32
