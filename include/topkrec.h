@@ -273,7 +273,7 @@ void tkr_debug_set_filter_mode(int32_t mode);
 /* tkr_vbpr_step content GEMMs: -1 automatic (tcgen05 3xTF32 route for large batches with dense 16-byte-aligned features), 0 never
  * (fp32 CUDA-core GEMMs).  Read when the workspace is SIZED as well: keep it fixed between tkr_vbpr_workspace_bytes and the steps. */
 void tkr_debug_set_vbpr_tc_mode(int32_t mode);
-/* experiments on the 3xTF32 GEMM: bit 0 = do not overwrite the A tile with its TF32-exact part, bit 1 = three separate products */
+/* experiments on the 3xTF32 GEMM: bit 0 = overwrite the A tile with its TF32-exact part, bit 1 = three separate products */
 void tkr_debug_set_gemm3_flags(int32_t flags);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */

@@ -21,7 +21,7 @@ P = Fh.astype(np.float64) @ E.astype(np.float64)
 F = torch.from_numpy(Fh).to(dev)
 cfg = topkrec.VbprCfg(bench.N_USERS, ni, k, dF)
 out = []
-for flags, tc in ((0, -1), (2, -1), (1, -1), (0, 0)):
+for flags, tc in ((0, -1), (1, -1)):
     L.tkr_debug_set_gemm3_flags(flags); L.tkr_debug_set_vbpr_tc_mode(tc)
     g = torch.Generator(device=dev); g.manual_seed(2)
     st = {"U": torch.randn(bench.N_USERS, k, device=dev, generator=g) * 0.01, "V": torch.zeros(ni, k, device=dev),

@@ -10,11 +10,12 @@
 // A is constant (the item features; F^T is built once), so it streams from HBM through TMA untouched and is split in
 // shared memory by the CUDA-core warps; B is small, rebuilt per step, and arrives pre-split (Bhi, Blo).
 //
-// One CTA per SM, 192 threads:
+// One CTA per SM, 320 threads:
 //   warp 0      TMA producer: per K block of 32 floats one {32 x 128} box of A and one {32 x NP} box each of Bhi / Blo
 //               (128-byte swizzle) into a ring of stages; out-of-range rows / columns are zero-filled by the TMA unit
-//   warps 2-5   split the landed A tile in place: ah overwrites a, al goes to a second tile of the stage (element-wise on
-//               the swizzled bytes: the layout does not matter), fence.proxy.async, arrive
+//   warps 2-9   split the landed A tile: al = TF32(a - ah) goes to a second tile of the stage (element-wise on the swizzled
+//               bytes: the layout does not matter; a itself stays, the tensor core reads its top 19 bits = ah),
+//               fence.proxy.async, arrive
 //   warp 1      one thread issues 3 x 4 tcgen05.mma (M=128, N=NP, K=8) per stage into TMEM; K blocks rotate over NACC
 //               independent accumulators (summed in the epilogue with round-to-nearest adds) so that the tensor core's
 //               own accumulation chain -- which truncates -- stays short; tcgen05.commit frees the stage
@@ -29,7 +30,8 @@ namespace g3 {
 
 constexpr int BM = 128, BK = 32;                  // BK fp32 = one 128-byte swizzle span
 constexpr int A_TILE_BYTES = BM * BK * 4;         // 16 KB
-constexpr int THREADS = 192;
+constexpr int SPLIT_WARPS = 8;                    // warps 2..9 split the landed A tile; warps 2..5 also run the epilogue
+constexpr int THREADS = 64 + 32 * SPLIT_WARPS;
 constexpr int MAX_STAGES = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,7 +99,8 @@ struct Args {
     int M, K, NP, h;              // rows of A, reduction length, padded N, real content width (column h of C = the vector product)
     int stages, nacc;
     int wide;                     // 1: ah . [bh | bl] is ONE instruction of N = 2 NP (both B tiles are contiguous in the stage)
-    int keep_raw;                 // 1 (experiment): do not overwrite a with ah -- relies on the tensor core ignoring the low 13 mantissa bits
+    int keep_raw;                 // 1 (default): the raw A tile IS ah -- kind::tf32 ignores the 13 low mantissa bits of an fp32 operand (measured:
+                                  // bit-identical results with and without overwriting a by its TF32-exact part, profiles/r02f_probe_gemm3.json)
     int kb_per_split;             // K blocks per blockIdx.y
     // EPI_PROJECT: out[m * ld + off + n] = C[m][n] (n < h), vec_out[m] = vec_add[m] + C[m][h]
     // EPI_GRAD   : out[m * ld + n] += C[m][n] (red.add),     vec_out[m] += C[m][h]
@@ -129,7 +132,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t tmem_cols = p.nacc * acc_cols <= 128 ? 128u : (p.nacc * acc_cols <= 256 ? 256u : 512u);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(split + s, 4); mbar_init(empty + s, 1); }
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full + s, 1); mbar_init(split + s, SPLIT_WARPS); mbar_init(empty + s, 1); }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -193,7 +196,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     } else {
         // ===================== A splitter, then epilogue (warps 2-5) =====================
-        const int t = threadIdx.x - 64;                                 // 0..127
+        const int t = threadIdx.x - 64;                                 // 0..32*SPLIT_WARPS-1
         for (int it = 0; it < nkb; ++it) {
             const int s = it % p.stages;
             const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
@@ -201,8 +204,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             float4* a = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
             float4* al = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes + A_TILE_BYTES);
 #pragma unroll
-            for (int j = 0; j < A_TILE_BYTES / 16 / 128; ++j) {         // 8 float4 per thread
-                const int e = t + j * 128;
+            for (int j = 0; j < A_TILE_BYTES / 16 / (32 * SPLIT_WARPS); ++j) {
+                const int e = t + j * 32 * SPLIT_WARPS;
                 const float4 v = a[e];
                 float4 hi, lo;
                 hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
@@ -214,6 +217,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(split + s);
         }
+        if (warp < 6) {                                                 // epilogue: one warp per TMEM lane quarter
         mbar_wait(done, 0);
         tc_fence_after();
         const int q = warp & 3;                                         // TMEM lane quarter this warp may read
@@ -252,6 +256,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -335,7 +340,7 @@ static int make_tmap_f32(CUtensorMap* tm, const void* ptr, int64_t rows, int64_t
 
 }  // namespace g3
 
-int g_gemm3_flags = 0;   // experiments (tkr_debug_set_gemm3_flags): 1 = keep the raw A tile as ah, 2 = three separate products
+int g_gemm3_flags = 0;   // experiments (tkr_debug_set_gemm3_flags): 1 = overwrite the A tile with its TF32-exact part, 2 = three separate products
 
 // ---- interface used by vbpr_step.cu -------------------------------------------------------------------------------
 int gemm3_np(int h) { return (h + 1 + 15) / 16 * 16; }
@@ -370,7 +375,7 @@ int gemm3_run(int epi, const float* A, int M, int K, int64_t a_pitch, const floa
     if (stages < 2) { set_error("gemm_tf32x3: N = %d does not leave room for two pipeline stages", p.NP); return TKR_ERR_UNSUPPORTED; }
     p.stages = stages;
     p.wide = (2 * p.NP <= 256 && !(g_gemm3_flags & 2)) ? 1 : 0;
-    p.keep_raw = (g_gemm3_flags & 1) ? 1 : 0;
+    p.keep_raw = (g_gemm3_flags & 1) ? 0 : 1;
     const int acc_cols = p.wide ? 2 * p.NP : p.NP;
     p.nacc = 512 / acc_cols < 4 ? 512 / acc_cols : 4;
     const int kb_total = (K + BK - 1) / BK;

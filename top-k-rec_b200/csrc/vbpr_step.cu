@@ -412,7 +412,8 @@ extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float*
             TKR_CUDA(cudaStreamSynchronize(st));
         }
     }
-    const int tc_splits = tc ? (kNumSMs + (dF + 127) / 128 - 1) / ((dF + 127) / 128) : 1;
+    // split-K of the gradient GEMM: as many K ranges as fit ONE wave of CTAs (160 CTAs on 148 SMs ran as two waves)
+    const int tc_splits = tc ? (kNumSMs / ((dF + 127) / 128) > 0 ? kNumSMs / ((dF + 127) / 128) : 1) : 1;
     auto project = [&]() -> int {
         if (tc) {
             if (int rc = gemm3_build_b(E, h, 0, c, dF, dF, h, w.Bp_hi, w.Bp_lo, st)) return rc;
