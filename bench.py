@@ -380,6 +380,7 @@ def run_ours(args, rank, local_rank, world):
         line["vbpr"] = vbpr_points(smp, dev, fp32_peak)
         line["als"] = als_points(dev, fp32_peak, cpu=not args.skip_cpu)
     if world > 1 and not args.skip_sweep:
+        line["vbpr"] = vbpr_dp_point(smp, dev, rank, world, barrier, max_over_ranks)
         line["als"] = als_sharded_point(dev, rank, world, barrier, max_over_ranks)
     if rank == 0 and world == 1 and not args.skip_cpu:
         # bounded CPU sample: ~10-30 s of the OpenMP port on the same workload
@@ -514,6 +515,50 @@ def vbpr_points(smp, dev, fp32_peak, d_feat=4096, k=128):
                                  "note": "whole step time charged to the content GEMM FLOP (<= 2B item rows projected / differentiated per step)"}})
         del ws
     return out
+
+
+def vbpr_dp_point(smp, dev, rank, world, barrier, max_over_ranks, d_feat=4096, k=128, B=1 << 20):
+    """BASELINE configs[2] at N GPUs: data-parallel VBPR (topkrec.dist.DataParallelVbpr: users partitioned, item / content tables
+    replicated, all-reduce of the item-side gradients and of dE / dc), 2^20 triples per GPU per step (weak scaling)."""
+    import torch
+    import torch.distributed as dist
+    import topkrec
+    from topkrec import dist as tdist
+    g = torch.Generator(device=dev); g.manual_seed(2)              # the same tables on every rank
+    F = torch.randn(N_ITEMS, d_feat, device=dev, generator=g).abs_()
+    F /= F.norm(dim=1, keepdim=True)
+    h = k // 2
+    cfg = topkrec.VbprCfg(N_USERS, N_ITEMS, k, d_feat)
+    st = {"U": torch.randn(N_USERS, k, device=dev, generator=g) * 0.01, "V": torch.zeros(N_ITEMS, k, device=dev),
+          "rb": torch.zeros(N_ITEMS, device=dev), "bsum": torch.zeros(N_ITEMS, device=dev),
+          "E": torch.full((d_feat, h), 2.0 / (d_feat * k), device=dev), "c": torch.zeros(d_feat, device=dev)}
+    st["V"][:, :h] = torch.randn(N_ITEMS, h, device=dev, generator=g) * 0.01
+    for n, m in (("U", "msU"), ("V", "msV"), ("rb", "msrb"), ("E", "msE"), ("c", "msc")):
+        st[m] = torch.ones_like(st[n])
+    eng = tdist.DataParallelVbpr(cfg, st, F, B)
+    topkrec.vbpr_set_hot_items(cfg, B, eng.ws, topkrec.popular_items(smp.pos_idx, N_ITEMS))
+    topkrec.vbpr_project(cfg, st, F)
+    state = {"r": 0}
+
+    def run():
+        state["r"] += 1
+        eng.step(sampler=smp, first_draw=(13 << 32) + state["r"] * B)
+    for _ in range(5):
+        run()
+    barrier()
+    reps = 400
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / reps
+    hi, lo = st["E"].clone(), st["E"].clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    return [{"batch_size": B, "n_gpus": world, "us_per_step": 1e3 * ms, "triples_per_sec": world * B / (ms / 1e3), "timed_seconds": ms * reps / 1e3, "scaling": "weak",
+             "replicas_bit_identical_E": bool(torch.equal(hi, lo)),
+             "config": "VBPR %d users x %d items, k=%d, %d-d dense features, data-parallel over %d GPUs: NCCL all-reduce of [GV|Gb|tchV] (%.1f MB) and [GE|Gc] (%.1f MB) per step"
+                       % (N_USERS, N_ITEMS, k, d_feat, world, eng.sparse.numel() * 4 / 1e6, eng.dense.numel() * 4 / 1e6)}]
 
 
 def als_workload(n_users, n_items, mean_pos):

@@ -216,6 +216,20 @@ int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float*
                   const int32_t* i, const int32_t* j, int64_t batch, int64_t n_steps, const tkr_sampler* smp,
                   uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes, void* stream);
 
+/* The two halves of one VBPR step for data-parallel training (users partitioned over the ranks, every
+ * other table replicated):  tkr_vbpr_grad = projection + gather/scatter gradients + this rank's dE / dc; the caller then sums
+ * over the ranks the two fp32 regions named by tkr_vbpr_workspace_layout -- offsets[0..1) = [GV|Gb|tchV] (item rows, incl. the
+ * content gradient W), offsets[2..3) = [GE|Gc] (dE and dc: linear in W, so the sum of the local products is the product of the
+ * sum) --; tkr_vbpr_apply = the sparse and dense optimiser updates, identical on every replica.  With data_parallel != 0 item
+ * rows are flagged through tchV as in tkr_bpr_grad / tkr_bpr_apply.  Call tkr_vbpr_project after the last step before
+ * exporting V / bsum. */
+int tkr_vbpr_grad(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c, const float* F,
+                  const int32_t* u, const int32_t* i, const int32_t* j, int64_t batch, const tkr_sampler* smp, uint64_t first_draw,
+                  float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream);
+int tkr_vbpr_apply(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* E, float* c, float* msU, float* msV, float* msrb,
+                   float* msE, float* msc, int64_t batch, float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream);
+int tkr_vbpr_workspace_layout(const tkr_vbpr_cfg* cfg, int64_t batch, int64_t* offsets /* [4] */);
+
 /* Draw `n` triples (draw indices first_draw .. first_draw+n-1) with the
  * semantics of single/bpr.py:155-165: user uniform over tr_users with
  * replacement, positive uniform over the user's positives, negative uniform

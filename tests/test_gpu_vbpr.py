@@ -173,3 +173,48 @@ def test_vbpr_tensor_core_route_equals_cuda_core_route(shape):
             _set_tc(-1)
     for n in outs[0]:
         assert _rel(outs[1][n], outs[0][n]) <= 2e-5, n
+
+
+def test_vbpr_data_parallel_halves_equal_one_big_batch():
+    """tkr_vbpr_grad on two user-partitioned half batches + summed [GV|Gb|tchV] and [GE|Gc] regions + tkr_vbpr_apply on both
+    == one step over the union batch (what 2 ranks + two all-reduces compute), for 3 steps."""
+    rng = np.random.default_rng(31)
+    nu, ni, k, dF, B, steps = 600, 300, 64, 256, 2048, 3
+    h = k // 2
+    st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
+    st["rb"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    st["c"] = (0.001 * rng.standard_normal(dF)).astype(np.float32)
+    F = np.abs(rng.standard_normal((ni, dF))).astype(np.float32); F /= np.linalg.norm(F, axis=1, keepdims=True)
+    Fd = torch.from_numpy(F).cuda()
+    ocfg = bpr_ref.BprCfg(lambda_e=0.01, lambda_b=0.01)
+    cfg = topkrec.VbprCfg(nu, ni, k, dF, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lambda_e, ocfg.lr, ocfg.mode, ocfg.optimizer)
+    ranks = []
+    for r in range(2):
+        d = _dev_state(st, F, k)
+        ws = topkrec.vbpr_workspace(cfg, B)
+        topkrec.vbpr_project(cfg, d, Fd)
+        ranks.append((d, ws, topkrec.vbpr_grad_views(cfg, B, ws)))
+    for t in range(steps):
+        u = rng.integers(0, nu, 2 * B).astype(np.int32); i = rng.integers(0, ni, 2 * B).astype(np.int32); j = rng.integers(0, ni, 2 * B).astype(np.int32)
+        u[:B] = u[:B] // 2 * 2; u[B:] = u[B:] // 2 * 2 + 1              # rank r owns users u % 2 == r
+        loss = [torch.zeros(1, device="cuda") for _ in range(2)]
+        for r, (d, ws, _) in enumerate(ranks):
+            sl = slice(r * B, (r + 1) * B)
+            topkrec.vbpr_grad(cfg, d, Fd, torch.from_numpy(u[sl]).cuda(), torch.from_numpy(i[sl]).cuda(), torch.from_numpy(j[sl]).cuda(), B, ws, loss[r],
+                              data_parallel=True)
+        for v in range(2):                                                # the two all-reduces
+            total = ranks[0][2][v] + ranks[1][2][v]
+            ranks[0][2][v].copy_(total); ranks[1][2][v].copy_(total)
+        for d, ws, _ in ranks:
+            topkrec.vbpr_apply(cfg, d, B, ws, None, data_parallel=True)
+        ref_loss = bpr_ref.vbpr_step(st, F, u, i, j, ocfg)
+        data_loss = (loss[0] + loss[1]).item()                            # (the halves add the batch terms; the tiny E / c regularisers come with apply)
+        assert abs(data_loss - ref_loss) / ref_loss < 1e-2
+    a, b = ranks[0][0], ranks[1][0]
+    for n in ("V", "rb", "E", "c", "msV", "msrb", "msE", "msc"):          # replicas identical ...
+        assert torch.equal(a[n][:, :h] if n in ("V", "msV") else a[n], b[n][:, :h] if n in ("V", "msV") else b[n]), n
+    got = {n: v.cpu().numpy() for n, v in a.items()}
+    for n, g in (("IR", got["V"][:, :h]), ("rb", got["rb"]), ("E", got["E"]), ("c", got["c"]), ("msIR", got["msV"][:, :h]), ("msE", got["msE"]), ("msc", got["msc"])):
+        assert _rel(g, st[n]) <= REL_TOL, (n, _rel(g, st[n]))             # ... and equal to the union batch
+    U = got["U"].copy(); U[1::2] = b["U"].cpu().numpy()[1::2]             # each rank updated only its own users
+    assert _rel(U[:, :h], st["UR"]) <= REL_TOL and _rel(U[:, h:], st["UC"]) <= REL_TOL

@@ -371,36 +371,45 @@ extern "C" int tkr_vbpr_project(const tkr_vbpr_cfg* cfg, const float* F, const f
     return TKR_OK;
 }
 
-extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c,
-                             const float* F, float* msU, float* msV, float* msrb, float* msE, float* msc, const int32_t* u,
-                             const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const tkr_sampler* smp,
-                             uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+namespace tkr {
+enum { VBPR_ALL = 0, VBPR_GRAD = 1, VBPR_APPLY = 2 };
+
+// The step loop of tkr_vbpr_step; with phase = VBPR_GRAD / VBPR_APPLY (n_steps = 1) it runs the two halves of one step for
+// data-parallel training: everything up to the gradients (projection, gather/scatter step, LOCAL dE / dc), then -- after the
+// caller has summed [GV|Gb|tchV] and [GE|Gc] over the ranks -- the sparse and dense updates.
+static int vbpr_run(int phase, int data_parallel, const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c,
+                    const float* F, float* msU, float* msV, float* msrb, float* msE, float* msc, const int32_t* u,
+                    const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const tkr_sampler* smp,
+                    uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
     if (int rc = vbpr_check(cfg, B)) return rc;
-    TKR_CHECK_ARG(U && V && rb && bsum && E && c && F, "U, V, rb, bsum, E, c, F must not be NULL");
-    TKR_CHECK_ARG(cfg->base.optimizer == TKR_OPT_SGD || (msU && msV && msrb && msE && msc), "RMSProp needs every rms slot");
+    TKR_CHECK_ARG(U && V && rb && E && c, "U, V, rb, E, c must not be NULL");
+    TKR_CHECK_ARG(phase == VBPR_APPLY || (bsum && F), "bsum and F must not be NULL");
+    TKR_CHECK_ARG(phase == VBPR_GRAD || cfg->base.optimizer == TKR_OPT_SGD || (msU && msV && msrb && msE && msc), "RMSProp needs every rms slot");
     TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
     SamplerDev sd = {};
-    if (u == nullptr) {
-        if (int rc = bpr_make_sampler(smp, &sd)) return rc;
-        TKR_CHECK_ARG(smp->n_items == cfg->base.n_items, "sampler n_items != cfg n_items");
-    } else {
-        TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
+    if (phase != VBPR_APPLY) {
+        if (u == nullptr) {
+            if (int rc = bpr_make_sampler(smp, &sd)) return rc;
+            TKR_CHECK_ARG(smp->n_items == cfg->base.n_items, "sampler n_items != cfg n_items");
+        } else {
+            TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
+        }
     }
     VbprWs w;
     if (int rc = vbpr_carve(cfg, B, ws, ws_bytes, &w)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const tkr_bpr_cfg* bc = &cfg->base;
     const int h = bc->d / 2, dF = cfg->d_feat;
-    const int mode = bpr_pick_mode(bc, B, 0);
+    const int mode = bpr_pick_mode(bc, B, data_parallel);
     const StepExtra ex{h, rb, w.wq, hot_rows_for(bc->d)};    // popular item rows privatised per block, as in the plain BPR step
-    if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
+    if (phase == VBPR_ALL && loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
     // split-K so that the dE GEMM covers the chip: (dF/64) x (h/64) output tiles
     const int tiles = ((dF + GT - 1) / GT) * ((h + GT - 1) / GT);
     int splitk = (2 * kNumSMs + tiles - 1) / tiles;
     if (splitk < 1) splitk = 1;
     if (splitk > 64) splitk = 64;
     // tensor-core route: F must be 16-byte aligned for the TMA descriptor; F^T is built once per (workspace, F)
-    const bool tc = w.tc && gemm3_legal(bc->n_items, dF, h, dF, F);
+    const bool tc = phase != VBPR_APPLY && w.tc && mode == MODE_DENSE && gemm3_legal(bc->n_items, dF, h, dF, F);
     if (tc) {
         unsigned long long tag = 0;
         TKR_CUDA(cudaMemcpyAsync(&tag, w.ft_tag, 8, cudaMemcpyDeviceToHost, st));
@@ -425,27 +434,69 @@ extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float*
     };
     for (int64_t t = 0; t < n_steps; ++t) {
         float* lt = loss_out ? loss_out + t : nullptr;
-        if (int rc = project()) return rc;
-        if (int rc = bpr_dispatch_grad(bc, U, V, bsum, u ? u + t * B : nullptr, u ? i + t * B : nullptr, u ? j + t * B : nullptr, B, sd,
-                                       first_draw + (uint64_t)t * (uint64_t)B, w.s, mode, ex, lt, st)) return rc;
-        if (tc) {   // [dE | dc] += F^T . [W | wq] over all items (untouched rows of W are zero)
-            if (int rc = gemm3_build_b(w.s.GV, bc->d, h, w.wq, bc->n_items, w.Mp, h, w.Bg_hi, w.Bg_lo, st)) return rc;
-            if (int rc = gemm3_run(1, w.Ft, dF, bc->n_items, w.Mp, w.Bg_hi, w.Bg_lo, w.Mp, h, w.GE, h, 0, w.Gc, nullptr, tc_splits, st)) return rc;
-        } else {
-            dim3 grid((dF + GT - 1) / GT, (h + GT - 1) / GT, splitk);
-            vbpr_grad_dense_kernel<<<grid, 256, 0, st>>>(F, dF, w.s.GV, bc->d, h, h, w.wq, mode == MODE_LIST ? w.s.listV : nullptr,
-                                                         w.s.n_touched + 1, bc->n_items, w.GE, w.Gc);
+        if (phase != VBPR_APPLY) {
+            if (int rc = project()) return rc;
+            if (int rc = bpr_dispatch_grad(bc, U, V, bsum, u ? u + t * B : nullptr, u ? i + t * B : nullptr, u ? j + t * B : nullptr, B, sd,
+                                           first_draw + (uint64_t)t * (uint64_t)B, w.s, mode, ex, lt, st)) return rc;
+            if (tc) {   // [dE | dc] += F^T . [W | wq] over all items (untouched rows of W are zero)
+                if (int rc = gemm3_build_b(w.s.GV, bc->d, h, w.wq, bc->n_items, w.Mp, h, w.Bg_hi, w.Bg_lo, st)) return rc;
+                if (int rc = gemm3_run(1, w.Ft, dF, bc->n_items, w.Mp, w.Bg_hi, w.Bg_lo, w.Mp, h, w.GE, h, 0, w.Gc, nullptr, tc_splits, st)) return rc;
+            } else {
+                dim3 grid((dF + GT - 1) / GT, (h + GT - 1) / GT, splitk);
+                vbpr_grad_dense_kernel<<<grid, 256, 0, st>>>(F, dF, w.s.GV, bc->d, h, h, w.wq, mode == MODE_LIST ? w.s.listV : nullptr,
+                                                             w.s.n_touched + 1, bc->n_items, w.GE, w.Gc);
+                TKR_LAUNCH_CHECK();
+            }
+        }
+        if (phase != VBPR_GRAD) {
+            bpr_launch_apply(bc, U, V, rb, msU, msV, msrb, B, w.s, mode, ex, st);
+            TKR_LAUNCH_CHECK();
+            const int64_t nE = (int64_t)dF * h;
+            int64_t blocks = (nE + dF + 255) / 256;
+            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            vbpr_apply_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>(*bc, cfg->lambda_e, E, msE, w.GE, nE, c, msc, w.Gc, dF, lt);
             TKR_LAUNCH_CHECK();
         }
-        bpr_launch_apply(bc, U, V, rb, msU, msV, msrb, B, w.s, mode, ex, st);
-        TKR_LAUNCH_CHECK();
-        const int64_t nE = (int64_t)dF * h;
-        int64_t blocks = (nE + dF + 255) / 256;
-        if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-        vbpr_apply_dense_kernel<<<(unsigned)blocks, 256, 0, st>>>(*bc, cfg->lambda_e, E, msE, w.GE, nE, c, msc, w.Gc, dF, lt);
-        TKR_LAUNCH_CHECK();
     }
     // leave V[:, h:] = F.E and bsum = rb + F.c consistent with the final E, c: they ARE the export (vbpr.py:124-126)
-    if (int rc = project()) return rc;
+    if (phase == VBPR_ALL)
+        if (int rc = project()) return rc;
+    return TKR_OK;
+}
+}  // namespace tkr
+
+extern "C" int tkr_vbpr_step(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c,
+                             const float* F, float* msU, float* msV, float* msrb, float* msE, float* msc, const int32_t* u,
+                             const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const tkr_sampler* smp,
+                             uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes, void* stream) {
+    return vbpr_run(VBPR_ALL, 0, cfg, U, V, rb, bsum, E, c, F, msU, msV, msrb, msE, msc, u, i, j, B, n_steps, smp, first_draw, loss_out, ws, ws_bytes, stream);
+}
+
+extern "C" int tkr_vbpr_grad(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* bsum, float* E, float* c, const float* F,
+                             const int32_t* u, const int32_t* i, const int32_t* j, int64_t B, const tkr_sampler* smp, uint64_t first_draw,
+                             float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
+    return vbpr_run(VBPR_GRAD, data_parallel, cfg, U, V, rb, bsum, E, c, F, nullptr, nullptr, nullptr, nullptr, nullptr, u, i, j, B, 1, smp, first_draw,
+                    loss_out, ws, ws_bytes, stream);
+}
+
+extern "C" int tkr_vbpr_apply(const tkr_vbpr_cfg* cfg, float* U, float* V, float* rb, float* E, float* c, float* msU, float* msV, float* msrb,
+                              float* msE, float* msc, int64_t B, float* loss_out, void* ws, size_t ws_bytes, int32_t data_parallel, void* stream) {
+    return vbpr_run(VBPR_APPLY, data_parallel, cfg, U, V, rb, nullptr, E, c, nullptr, msU, msV, msrb, msE, msc, nullptr, nullptr, nullptr, B, 1, nullptr, 0,
+                    loss_out, ws, ws_bytes, stream);
+}
+
+// byte offsets of the regions a data-parallel caller sums over the ranks: offsets[0..1] = [begin, end) of the fp32 region
+// [GV | Gb | tchV] (the sparse item side), offsets[2..3] = [begin, end) of the fp32 region [GE | (pad) | Gc] (dense content side)
+extern "C" int tkr_vbpr_workspace_layout(const tkr_vbpr_cfg* cfg, int64_t B, int64_t* offsets) {
+    if (int rc = vbpr_check(cfg, B)) return rc;
+    TKR_CHECK_ARG(offsets != nullptr, "offsets is NULL");
+    int64_t o[TKR_WS_NFIELDS];
+    if (int rc = tkr_bpr_workspace_layout(&cfg->base, B, o)) return rc;
+    const size_t h = cfg->base.d / 2, ni = cfg->base.n_items;
+    offsets[0] = o[TKR_WS_GV];
+    offsets[1] = o[TKR_WS_GV] + (int64_t)(ni * cfg->base.d + 2 * ni) * 4;
+    const size_t ge = align_up(bpr_ws_total(&cfg->base, B), 256) + align_up(ni * 4, 256);
+    offsets[2] = (int64_t)ge;
+    offsets[3] = (int64_t)(ge + align_up((size_t)cfg->d_feat * h * 4, 256) + (size_t)cfg->d_feat * 4);
     return TKR_OK;
 }

@@ -76,6 +76,9 @@ def lib():
     L.tkr_vbpr_workspace_init.argtypes = [vcfgp, i64, vp, sz, vp]
     L.tkr_vbpr_project.argtypes = [vcfgp] + [vp] * 6 + [vp]
     L.tkr_vbpr_step.argtypes = [vcfgp] + [vp] * 12 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
+    L.tkr_vbpr_grad.argtypes = [vcfgp] + [vp] * 7 + [vp] * 3 + [i64, smpp, u64, vp, vp, sz, i32, vp]
+    L.tkr_vbpr_apply.argtypes = [vcfgp] + [vp] * 10 + [i64, vp, vp, sz, i32, vp]
+    L.tkr_vbpr_workspace_layout.argtypes = [vcfgp, i64, C.POINTER(C.c_int64)]
     L.tkr_score_topk_workspace_bytes.restype = sz; L.tkr_score_topk_workspace_bytes.argtypes = [i64, i64, i32, i32]
     L.tkr_score_topk.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, vp, vp, sz, vp]
     L.tkr_score_topk_tc_workspace_bytes.restype = sz; L.tkr_score_topk_tc_workspace_bytes.argtypes = [i64, i64, i32, i32, i32]
@@ -98,7 +101,7 @@ def lib():
     L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
     L.tkr_als_gram.argtypes = [vp, i32, vp, i64, C.c_float, C.c_float, vp, vp, sz, vp]
     L.tkr_als_solve_rows.argtypes = [C.POINTER(tkr_als_cfg), C.POINTER(tkr_als_plan), vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    for name in ("tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    for name in ("tkr_vbpr_grad", "tkr_vbpr_apply", "tkr_vbpr_workspace_layout", "tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
@@ -349,6 +352,34 @@ def vbpr_step(cfg: VbprCfg, st, F, u, i, j, batch, n_steps, ws, loss=None, sampl
                                    *(_dev(st.get(n), f32, n) for n in VBPR_SLOTS), _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"),
                                    int(batch), int(n_steps), sampler.ptr if sampler is not None else None, int(first_draw),
                                    _dev(loss, f32, "loss"), ws.data_ptr(), ws.numel(), _stream()))
+
+
+def vbpr_grad(cfg: VbprCfg, st, F, u, i, j, batch, ws, loss=None, sampler=None, first_draw=0, data_parallel=False):
+    """first half of a data-parallel VBPR step: projection, gather/scatter gradients, this rank's dE / dc (tkr_vbpr_grad)"""
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(F, st["U"], ws)
+    with torch.cuda.device(F.device):
+        _check(lib().tkr_vbpr_grad(cfg.ptr, *(_dev(st[n], f32, n) for n in VBPR_STATE), _dev(F, f32, "F"),
+                                   _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"), int(batch),
+                                   sampler.ptr if sampler is not None else None, int(first_draw), _dev(loss, f32, "loss"),
+                                   ws.data_ptr(), ws.numel(), int(bool(data_parallel)), _stream()))
+
+
+def vbpr_apply(cfg: VbprCfg, st, batch, ws, loss=None, data_parallel=False):
+    """second half: sparse + dense optimiser updates from the (summed) gradients in the workspace (tkr_vbpr_apply)"""
+    f32 = torch.float32
+    _need_cuda(st["U"], ws)
+    with torch.cuda.device(ws.device):
+        _check(lib().tkr_vbpr_apply(cfg.ptr, *(_dev(st[n], f32, n) for n in ("U", "V", "rb", "E", "c")),
+                                    *(_dev(st.get(n), f32, n) for n in VBPR_SLOTS), int(batch), _dev(loss, f32, "loss"),
+                                    ws.data_ptr(), ws.numel(), int(bool(data_parallel)), _stream()))
+
+
+def vbpr_grad_views(cfg: VbprCfg, batch, ws):
+    """fp32 views of the two workspace regions a data-parallel caller sums over the ranks: [GV|Gb|tchV] and [GE|Gc]"""
+    off = (C.c_int64 * 4)()
+    _check(lib().tkr_vbpr_workspace_layout(cfg.ptr, int(batch), off))
+    return ws[off[0]:off[1]].view(torch.float32), ws[off[2]:off[3]].view(torch.float32)
 
 
 def bpr_sample(sampler: Sampler, first_draw, n, device="cuda"):

@@ -221,6 +221,34 @@ class DataParallelBpr:
             self.buf = None
 
 
+class DataParallelVbpr:
+    """Synchronous data-parallel VBPR step: users partitioned over the ranks (U = [ur|uc] rows never
+    move), every other table replicated.  Per step: tkr_vbpr_grad (projection, gradients, this rank's dE / dc) -> all-reduce
+    of the item-side region [GV|Gb|tchV] (which carries the content gradient W in its F.E columns) and of [GE|Gc] (dE and
+    dc are linear in W: the sum of the local products is the product of the sum, and NCCL hands every rank the same bits)
+    -> tkr_vbpr_apply.  Replicas of V, rb, E, c stay bit-identical; equals one GPU stepping the union batch up to fp32
+    summation order."""
+
+    def __init__(self, cfg, state, F, batch, group=None):
+        import topkrec
+        self.t, self.cfg, self.st, self.F, self.batch, self.group = topkrec, cfg, state, F, int(batch), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.ws = topkrec.vbpr_workspace(cfg, batch, F.device)
+        self.sparse, self.dense = topkrec.vbpr_grad_views(cfg, batch, self.ws)
+
+    def step(self, u=None, i=None, j=None, sampler=None, first_draw=0, loss=None):
+        dp = self.world > 1
+        self.t.vbpr_grad(self.cfg, self.st, self.F, u, i, j, self.batch, self.ws, loss, sampler, first_draw, data_parallel=dp)
+        if dp:
+            dist.all_reduce(self.sparse, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(self.dense, op=dist.ReduceOp.SUM, group=self.group)
+        self.t.vbpr_apply(self.cfg, self.st, self.batch, self.ws, None, data_parallel=dp)
+
+    def finish(self):
+        """refresh V[:, k/2:] = F.E and bsum = rb + F.c from the final E, c (the export layout, vbpr.py:124-126)"""
+        self.t.vbpr_project(self.cfg, self.st, self.F)
+
+
 def balanced_row_bounds(indptr, world, row_cost=256):
     """Contiguous [beg, end) row ranges per rank with about equal work, a row costing its positives + ``row_cost``
     (the factorisation is a fixed cost per row; SURVEY.md 8(e): U-step sharded by user, V-step by item)."""
