@@ -85,6 +85,80 @@ def _worker_dp(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_dp_owner(rank, world, port, q):
+    """the fused exchange of tkr_bpr_dp_step, emulated: every rank keeps its partial [GV|Gb|tch]; the OWNER of an item row
+    (row % world) reads that row from every rank in rank order, sums, applies the optimiser once with its local slot, and
+    writes the new row into every replica.  Must equal one process stepping the union batch, with identical replicas."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(6)
+    nu, ni, d, B = 30, 13, 8, 48
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    st["b"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
+    whole = {k: v.copy() for k, v in st.items()}
+    cfg = bpr_ref.BprCfg(lambda_b=0.01)
+    ok = True
+    for step in range(3):
+        u = rng.integers(0, nu, world * B); i = rng.integers(0, ni - 2, world * B); j = rng.integers(0, ni - 2, world * B)   # two items never touched
+        keep = u % world == rank
+        _, _, gU, gVi, gVj, gbi, gbj = bpr_ref.bpr_occurrence_grads(st["U"], st["V"], st["b"], u[keep], i[keep], j[keep], cfg)
+        G = np.zeros((ni, d + 2), np.float32)                              # [GV | Gb | tch] per item row
+        np.add.at(G[:, :d], i[keep], gVi); np.add.at(G[:, :d], j[keep], gVj)
+        np.add.at(G[:, d], i[keep], gbi); np.add.at(G[:, d], j[keep], gbj)
+        np.add.at(G[:, d + 1], i[keep], 1); np.add.at(G[:, d + 1], j[keep], 1)
+        parts = [torch.zeros(ni, d + 2) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(G))                        # stands in for the NVLink loads of the peers' rows
+        newV, newb = np.zeros_like(st["V"]), np.zeros_like(st["b"])
+        for r in range(rank, ni, world):                                   # owned rows
+            tot = np.zeros(d + 2, np.float32)
+            for p in range(world):
+                tot += parts[p][r].numpy()
+            if tot[d + 1] == 0:
+                newV[r], newb[r] = st["V"][r], st["b"][r]
+                continue
+            rows = np.array([r])
+            bpr_ref.apply_sparse(st["V"], st["msV"], rows, tot[None, :d], cfg)
+            bpr_ref.apply_sparse(st["b"], st["msb"], rows, tot[d:d + 1], cfg)
+            newV[r], newb[r] = st["V"][r], st["b"][r]
+        tv, tb = torch.from_numpy(newV), torch.from_numpy(newb)
+        dist.all_reduce(tv); dist.all_reduce(tb)                           # stands in for the NVLink stores into every replica (disjoint rows)
+        st["V"][:], st["b"][:] = tv.numpy(), tb.numpy()
+        rU, GU = bpr_ref.segment_sum(u[keep], gU)
+        bpr_ref.apply_sparse(st["U"], st["msU"], rU, GU, cfg)
+        bpr_ref.bpr_step(whole, u, i, j, cfg)
+        ok = ok and all(np.abs(st[n] - whole[n]).max() <= 2e-6 * np.abs(whole[n]).max() for n in ("V", "b"))
+        own_items = np.arange(ni) % world == rank
+        ok = ok and all(np.abs(st[n][own_items] - whole[n][own_items]).max() <= 2e-6 * np.abs(whole[n]).max() for n in ("msV", "msb"))
+        own = np.arange(nu) % world == rank
+        ok = ok and all(np.abs(st[n][own] - whole[n][own]).max() <= 2e-6 * np.abs(whole[n]).max() for n in ("U", "msU"))
+        t = torch.from_numpy(st["V"].copy()); ref = t.clone(); dist.broadcast(ref, 0)
+        ok = ok and torch.equal(t, ref)
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def _worker_slices(rank, world, port, q):
+    """user-slice ownership of the item-sharded scorer (tkr_topk_exchange_*): owner of row u = u // ceil(n / world); every
+    rank's shard lists of a slice, merged by the owner, equal the unsharded lists; the slices tile the batch."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    n, ni, d, k = 37, 203, 12, 10
+    U = rng.standard_normal((n, d)).astype(np.float32); V = rng.standard_normal((ni, d)).astype(np.float32)
+    beg, end = tdist.shard_bounds(ni, world)[rank]
+    li, ls = topk_ref.score_topk(U, V[beg:end], k, col_offset=beg)          # this rank's lists of ALL users
+    sl = -(-n // world)
+    lo, hi = min(n, rank * sl), min(n, (rank + 1) * sl)
+    gi = [torch.zeros((n, k), dtype=torch.int32) for _ in range(world)]; gs = [torch.zeros((n, k)) for _ in range(world)]
+    dist.all_gather(gi, torch.from_numpy(li)); dist.all_gather(gs, torch.from_numpy(ls))
+    mi, ms = topk_ref.topk_merge(np.stack([g[lo:hi].numpy() for g in gi]), np.stack([g[lo:hi].numpy() for g in gs]))
+    wi, ws = topk_ref.score_topk(U[lo:hi], V, k)
+    cover = torch.zeros(n); cover[lo:hi] = 1
+    dist.all_reduce(cover)
+    q.put((rank, bool(np.array_equal(mi, wi) and np.array_equal(ms, ws) and bool((cover == 1).all()))))
+    dist.destroy_process_group()
+
+
 class _CpuSide:
     def __init__(self, indptr, idx):
         self.indptr, self.idx = indptr, idx
@@ -139,7 +213,7 @@ def _worker_als(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp, _worker_als])
+@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp, _worker_dp_owner, _worker_slices, _worker_als])
 def test_world2_gloo(worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
