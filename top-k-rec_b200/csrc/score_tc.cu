@@ -217,6 +217,8 @@ struct FilterParams {
     int64_t nu, ni, col_offset;
     int kb, cps, stages, tiles_per_split;   // K chunks of 64, chunks per smem stage, ring depth
     int seed_tiles;          // tiles of each sweep (evenly spread) scanned first in seed mode (0 = off)
+    int seed_rank;           // 4 or 3: the row's seed threshold is the smallest of the column quarters' seed_rank-th largest chunk maxima
+    int cap_trigger;         // a row's candidate buffer is compacted to its best KPRIME once it would exceed this many keys (<= CAP)
     float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
@@ -559,7 +561,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             if (T0 > 0 && tl == T0) {
                 // end of seed mode: each thread holds its 4th largest chunk maximum; the row threshold is the smallest
                 // of the four column quarters' (>= 16 scores of the seed tiles reach it)
-                seed_sh[cq * FM + row] = s4;
+                seed_sh[cq * FM + row] = p.seed_rank == 3 ? s3 : s4;
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * F_EPI_WARPS) : "memory");
                 if (cq == 0) {
                     const float tau0 = fminf(fminf(seed_sh[row], seed_sh[FM + row]), fminf(seed_sh[2 * FM + row], seed_sh[3 * FM + row]));
@@ -679,7 +681,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
                     const int rq = (int)((hb[j] >> COL_BITS) & 31u);           // row within the quarter
                     int cnt = __shfl_sync(0xffffffffu, cnt_reg, rq);
                     uint64_t* buf = bufq + rq * CAP;
-                    if (cnt + __popc(bal[j]) > CAP) {                          // would overflow: keep the best KPRIME first
+                    if (cnt + __popc(bal[j]) > p.cap_trigger) {               // would overflow: keep the best KPRIME first
                         const long long k0 = tick<DBG>();
                         __syncwarp();
                         const int row = q * 32 + rq;
@@ -877,6 +879,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int dpad, i
 long long* g_filter_dbg = nullptr;   // set through tkr_debug_set_filter_counters (profiling aid)
 int g_seed_div = 12;                 // a sweep seeds on its first 1/g_seed_div tiles (tkr_debug_set_seed_div)
 int g_filter_mode = 1;               // kernel MODE used while the counters are set (tkr_debug_set_filter_mode)
+int g_seed_rank = 0, g_cap_trigger = 0;   // 0 = automatic (tkr_debug_set_filter_tuning)
 
 struct TcPlan {
     int dpad, kb, cps, stages, ns, tps;
@@ -935,6 +938,10 @@ using namespace tkr;
 
 extern "C" void tkr_debug_set_filter_counters(long long* dev_buf) { g_filter_dbg = dev_buf; }
 extern "C" void tkr_debug_set_seed_div(int32_t div) { g_seed_div = div >= 4 && div <= 1024 ? div : 12; }
+extern "C" void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t cap_trigger) {
+    g_seed_rank = (seed_rank == 3 || seed_rank == 4) ? seed_rank : 0;
+    g_cap_trigger = (cap_trigger >= KPRIME + 8 && cap_trigger <= CAP) ? cap_trigger : 0;
+}
 extern "C" void tkr_debug_set_filter_mode(int32_t mode) { g_filter_mode = mode >= 1 && mode <= 5 ? mode : 1; }
 // CTA pairs of the filter kernel that can be resident at once on the current device (74 on a full B200), or < 0.
 extern "C" int32_t tkr_debug_filter_max_pairs(int32_t d) {
@@ -1001,6 +1008,11 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
     fp.seed_tiles = P.seed_tiles; fp.out_tau0 = (float*)(w + P.o_tau0);
+    // (tuning aids; measured on item shards of 2^17 .. 2^20 items, profiles/r02_filter_roles.txt: seeding on the 3rd largest
+    // chunk maximum sends a handful of rows per batch to the exact fallback, which costs more than the hand-offs it saves,
+    // and compacting at 96 keys is a wash -- the defaults stay 4 / CAP)
+    fp.seed_rank = g_seed_rank ? g_seed_rank : 4;
+    fp.cap_trigger = g_cap_trigger ? g_cap_trigger : CAP;
     dim3 grid((unsigned)(2 * ((nu + 2 * FM - 1) / (2 * FM))), (unsigned)P.ns);   // clusters of 2 along x
 #define TKR_FILTER_LAUNCH(MODE)                                                                                                 \
     do {                                                                                                                        \
