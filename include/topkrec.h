@@ -284,8 +284,8 @@ void tkr_debug_set_persist_mode(int32_t mode);
  * prefetch, barrier 1, update, barrier 2, steps); NULL (default) disables it */
 void tkr_debug_set_persist_counters(long long* dev_buf);
 void tkr_debug_set_filter_mode(int32_t mode);
-/* filter tuning aid: seed_rank 3 | 4 (0 = automatic = 4); results do not depend on it */
-void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t reserved);
+/* filter tuning aid: seed_rank 3 | 4 (0 = automatic), cap_trigger in [72, 128] (0 = automatic); results do not depend on them */
+void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t cap_trigger);
 /* tkr_vbpr_step content GEMMs: -1 automatic (tcgen05 3xTF32 route for large batches with dense 16-byte-aligned features), 0 never
  * (fp32 CUDA-core GEMMs).  Read when the workspace is SIZED as well: keep it fixed between tkr_vbpr_workspace_bytes and the steps. */
 void tkr_debug_set_vbpr_tc_mode(int32_t mode);

@@ -22,7 +22,7 @@ out = []
 for shift in (20, 19, 18, 17):
     ni = 1 << shift
     V = Vfull[:ni].contiguous()
-    for div in (12,):
+    for div in (12, 8, 6, 4):
         L.tkr_debug_set_seed_div(div)
         ws = torch.empty(L.tkr_score_topk_tc_workspace_bytes(nb, ni, D, k, 0), dtype=torch.uint8, device=dev)
         nfb = torch.zeros(1, dtype=torch.int32, device=dev)

@@ -56,18 +56,18 @@ constexpr int F_WARPS = F_SEL_WARPS + F_EPI_WARPS + 2;
 // lowest ids, the TMEM-draining epilogue the middle ones, and the two single-thread issuers the highest.
 constexpr int W_SEL = 0, W_EPI = F_SEL_WARPS, W_TMA = F_SEL_WARPS + F_EPI_WARPS, W_MMA = W_TMA + 1;
 constexpr int F_THREADS = 32 * F_WARPS;            // warps 0-3 selection, 4-19 epilogue, 20 TMA, 21 MMA + TMEM alloc
-constexpr int NENT = 512;                         // hand-off entries per selection warp (power of two)
+constexpr int NBLK = 32;                          // hand-off blocks per selection warp
 constexpr int COL_BITS = 26;                      // a sweep (item split) spans < 2^26 tile-space columns
 
-// Hand-off from the epilogue (which must keep pace with the MMA) to the selection warps (which own the rows' candidate
-// lists).  An epilogue thread whose 32-score chunk contains a score that reaches its row's threshold pushes every such
-// score as ONE 64-bit entry: 1 << 63 | row-in-quarter << 58 | sweep-relative column << 32 | score bits (a single aligned
-// 64-bit store publishes it; 0 = empty slot, the consumer clears a slot before it advances `tail`).  The selection warp
-// then takes up to 32 entries per pass, one per lane.  (Round 1 handed whole 32-score chunks over and the selection warp
-// searched them: ~400 cycles per chunk for typically one hit -- 77 % of its time on the short sweeps of an item-sharded
-// run and what the tensor pipe waited for there, profiles/r02_filter_roles.txt.)
+// Hand-off from the epilogue (which must keep pace with the MMA) to the selection warps (which do the rare,
+// latency-bound work).  An epilogue thread whose 32-score chunk contains a score that reaches its row's threshold
+// dumps the chunk into a block (8 vector stores) and publishes a header word: 1 << 31 | row-in-quarter << 26 |
+// sweep-relative column of the first score.  No fence on the producer side (same-thread shared-memory stores are
+// performed in order); header 0 = empty block, the consumer clears it before it advances `tail`.  The selection
+// warp then tests the block one score per lane -- the cost of finding the hits is off the epilogue's path.
 struct SelShared {
-    unsigned long long ent[NENT];
+    float data[NBLK][32];
+    uint32_t hdr[NBLK];
     int head;                     // next reservation (atomic add by producers)
     volatile int tail;            // reservations consumed
     volatile int done;            // producer warps finished (F_CQ per selection warp)
@@ -218,6 +218,7 @@ struct FilterParams {
     int kb, cps, stages, tiles_per_split;   // K chunks of 64, chunks per smem stage, ring depth
     int seed_tiles;          // tiles of each sweep (evenly spread) scanned first in seed mode (0 = off)
     int seed_rank;           // 4 or 3: the row's seed threshold is the smallest of the column quarters' seed_rank-th largest chunk maxima
+    int cap_trigger;         // a row's candidate buffer is compacted to its best KPRIME once it would exceed this many keys (<= CAP)
     float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
@@ -306,25 +307,23 @@ __device__ __forceinline__ void sh_st_v4(uint32_t addr, uint32_t a, uint32_t b, 
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// Publish every score of a chunk that reaches the row threshold to the row quarter's selection warp (see SelShared);
-// ring = its shared-space address; hw = 1 << 31 | row-in-quarter << 26 | sweep-relative column of v[0].
-__device__ __forceinline__ void push_hits(const uint32_t (&v)[32], uint32_t hw, float tau, uint32_t ring) {
+// Publish one 32-score chunk to the row quarter's selection warp (see SelShared); ring = its shared-space address.
+__device__ __forceinline__ void dump_chunk(const uint32_t (&v)[32], uint32_t hdr, uint32_t ring) {
+    const int slot = sh_atomic_inc(ring + (uint32_t)offsetof(SelShared, head));
+    while (slot - sh_ld_volatile(ring + (uint32_t)offsetof(SelShared, tail)) >= NBLK) __nanosleep(64);   // all blocks in use
+    const uint32_t blk = (uint32_t)slot & (NBLK - 1);
+    const uint32_t dst = ring + blk * 128u;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-        if (__uint_as_float(v[i]) >= tau) {
-            const int slot = sh_atomic_inc(ring + (uint32_t)offsetof(SelShared, head));
-            while (slot - sh_ld_volatile(ring + (uint32_t)offsetof(SelShared, tail)) >= NENT) __nanosleep(64);   // ring full
-            asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(ring + 8u * ((uint32_t)slot & (NENT - 1))), "r"(v[i]), "r"(hw + (uint32_t)i) : "memory");
-        }
-    }
+    for (int i = 0; i < 8; ++i) sh_st_v4(dst + 16u * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    sh_st_volatile_u32(ring + (uint32_t)offsetof(SelShared, hdr) + 4u * blk, hdr);
 }
 
 // Epilogue scan of one tile slice (64 scores of one row): two max trees and a compare each against the row threshold.
 __device__ __forceinline__ void scan_tile(const uint32_t (&va)[32], const uint32_t (&vb)[32], uint32_t hdr, float tau, uint32_t ring) {
     const float ma = max32(va), mb = max32(vb);
     if (fmaxf(ma, mb) >= tau) {
-        if (ma >= tau) push_hits(va, hdr, tau, ring);
-        if (mb >= tau) push_hits(vb, hdr + 32, tau, ring);
+        if (ma >= tau) dump_chunk(va, hdr, ring);
+        if (mb >= tau) dump_chunk(vb, hdr + 32, ring);
     }
 }
 
@@ -616,10 +615,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
         // (explicit shared-space accesses: through generic volatile pointers every poll is an LD.E.STRONG.SYS)
         const int q = warp - W_SEL;
         const uint32_t ring = smem_u32(sel + q);
-        const uint32_t ent_a = ring + (uint32_t)offsetof(SelShared, ent), head_a = ring + (uint32_t)offsetof(SelShared, head);
+        const uint32_t hdr_a = ring + (uint32_t)offsetof(SelShared, hdr), head_a = ring + (uint32_t)offsetof(SelShared, head);
         const uint32_t tail_a = ring + (uint32_t)offsetof(SelShared, tail), done_a = ring + (uint32_t)offsetof(SelShared, done);
-        const uint32_t tau_a = smem_u32(const_cast<float*>(tau_sh)) + 128u * (uint32_t)q;     // thresholds of the quarter's 32 rows
-        const uint32_t cnt_a = smem_u32(cnt_sh) + 128u * (uint32_t)q;                         // ... and their buffered-candidate counts
+        const uint32_t tau_a = smem_u32(const_cast<float*>(tau_sh)) + 128u * (uint32_t)q;
         const int64_t sweep_col0 = t0 * FN;
         const uint32_t ni_rel = (uint32_t)(p.ni - sweep_col0 < ((int64_t)1 << COL_BITS) ? p.ni - sweep_col0 : ((int64_t)1 << COL_BITS));   // valid sweep-relative columns
         const int32_t gc_base = (int32_t)(sweep_col0 + p.col_offset);   // global column of sweep-relative column 0
@@ -628,16 +626,19 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
         uint64_t* bufq = p.cand + ((size_t)split * p.nu + (size_t)row0 + (size_t)q * 32) * CAP;   // row r of the quarter at bufq + r*CAP
         uint64_t skey[4];
         int tail = 0;
+        int cnt_reg = 0;                                                  // lane r: candidates buffered for row r of the quarter
+        float tau_reg = row0 + q * 32 + lane < p.nu ? -INFINITY : INFINITY;   // lane r: its threshold (mirrored in tau_sh for the epilogue)
+        bool tau_seeded = T0 == 0;
         long long dbg_idle = 0, dbg_busy = 0, dbg_n = 0, dbg_cmp = 0;
         for (;;) {
-            // lane l looks at entry tail + l; the published prefix is consumed, one entry per lane
+            // lane l looks at block tail + l; the published prefix is consumed block by block, one score per lane
             const long long i0 = tick<DBG>();
-            uint32_t sc = 0, hw = 0;
+            uint32_t h;
             int n;
             bool finished = false;
             for (;;) {
-                asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sc), "=r"(hw) : "r"(ent_a + 8u * (uint32_t)((tail + lane) & (NENT - 1))) : "memory");
-                const unsigned bal = __ballot_sync(0xffffffffu, (hw >> 31) != 0u);
+                h = (uint32_t)sh_ld_volatile(hdr_a + 4u * (uint32_t)((tail + lane) & (NBLK - 1)));
+                const unsigned bal = __ballot_sync(0xffffffffu, h != 0u);
                 n = bal == 0xffffffffu ? 32 : __ffs(~bal) - 1;
                 if (n > 0) break;
                 int fin = 0;
@@ -649,40 +650,55 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             if (finished) break;
             const long long i1 = tick<DBG>();
             dbg_idle += i1 - i0;
-            // fast path: a shared-memory atomic reserves the entry's place in its row's buffer
-            const int rq = (int)((hw >> COL_BITS) & 31u);                      // row within the quarter
-            const uint32_t crel = hw & ((1u << COL_BITS) - 1u);                // sweep-relative column
-            const float x = __uint_as_float(sc);
-            bool pass = lane < n && crel < ni_rel && x >= __int_as_float(sh_ld_volatile(tau_a + 4u * (uint32_t)rq));
-            int pos = 0;
-            if (pass) {
-                pos = sh_atomic_inc(cnt_a + 4u * (uint32_t)rq);
-                if (pos < CAP) bufq[rq * CAP + pos] = make_key(x + 0.0f, gc_base + (int32_t)crel);
+            if (!tau_seeded) {      // blocks only appear after seed mode: pick up the seed thresholds the epilogue stored
+                tau_reg = fmaxf(tau_reg, __int_as_float(sh_ld_volatile(tau_a + 4u * (uint32_t)lane)));
+                tau_seeded = true;
             }
-            // slow path (a row's buffer is full): compact it to its best KPRIME, raise its threshold, append what still passes
-            unsigned ovf = __ballot_sync(0xffffffffu, pass && pos >= CAP);
-            while (ovf) {
-                const long long k0 = tick<DBG>();
-                const int leader = __ffs(ovf) - 1;
-                const int r = __shfl_sync(0xffffffffu, rq, leader);
-                unsigned grp = __ballot_sync(0xffffffffu, pass && pos >= CAP && rq == r);
-                ovf &= ~grp;
-                __threadfence_block();                                         // (the buffer slots written above by other lanes)
-                __syncwarp();
-                const int row = q * 32 + r;
-                int kept = 0;
-                const float nt = sel_compact(bufq + r * CAP, CAP, lane, has_rated ? rated_idx : nullptr, rlo_sh[row], rhi_sh[row], &kept);
-                const float tr = fmaxf(__int_as_float(sh_ld_volatile(tau_a + 4u * (uint32_t)r)), nt);
-                grp = __ballot_sync(0xffffffffu, ((grp >> lane) & 1u) != 0u && x >= tr);
-                if ((grp >> lane) & 1u) bufq[r * CAP + kept + __popc(grp & ((1u << lane) - 1u))] = make_key(x + 0.0f, gc_base + (int32_t)crel);
-                if (lane == 0) {
-                    sh_st_volatile_u32(tau_a + 4u * (uint32_t)r, __float_as_uint(tr));
-                    sh_st_volatile_u32(cnt_a + 4u * (uint32_t)r, (uint32_t)(kept + __popc(grp)));
+            // Blocks are taken four at a time with their loads and votes issued together: the per-block chain
+            // (load, compare, vote, count, store) is latency-bound, and one selection warp -- which issues an
+            // instruction every ~6 cycles at best -- has to keep up with four epilogue warps.  Row counts and
+            // thresholds live in lane registers (lane r <-> row r of the quarter).
+            for (int b0 = 0; b0 < n; b0 += 4) {
+                uint32_t hb[4], bal[4];
+                float x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    hb[j] = __shfl_sync(0xffffffffu, h, (b0 + j) & 31);
+                    x[j] = __int_as_float(sh_ld_volatile(ring + 128u * (uint32_t)((tail + b0 + j) & (NBLK - 1)) + 4u * (uint32_t)lane));
                 }
-                __syncwarp();
-                dbg_cmp += tick<DBG>() - k0;
+                bool pass[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float tr = __shfl_sync(0xffffffffu, tau_reg, (int)(hb[j] >> COL_BITS));   // shfl takes the row index mod 32
+                    const uint32_t crel = (hb[j] & ((1u << COL_BITS) - 1u)) + (uint32_t)lane;       // sweep-relative column
+                    pass[j] = b0 + j < n && crel < ni_rel && x[j] >= tr;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bal[j] = __ballot_sync(0xffffffffu, pass[j]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (bal[j] == 0u) continue;                                // (also skips the blocks past n)
+                    const int rq = (int)((hb[j] >> COL_BITS) & 31u);           // row within the quarter
+                    int cnt = __shfl_sync(0xffffffffu, cnt_reg, rq);
+                    uint64_t* buf = bufq + rq * CAP;
+                    if (cnt + __popc(bal[j]) > p.cap_trigger) {               // would overflow: keep the best KPRIME first
+                        const long long k0 = tick<DBG>();
+                        __syncwarp();
+                        const int row = q * 32 + rq;
+                        const float nt = sel_compact(buf, cnt, lane, has_rated ? rated_idx : nullptr, rlo_sh[row], rhi_sh[row], &cnt);
+                        const float tr = fmaxf(__shfl_sync(0xffffffffu, tau_reg, rq), nt);
+                        if (lane == rq) { tau_reg = tr; sh_st_volatile_u32(tau_a + 4u * (uint32_t)rq, __float_as_uint(tr)); }
+                        bal[j] = __ballot_sync(0xffffffffu, ((bal[j] >> lane) & 1u) != 0u && x[j] >= tr);
+                        dbg_cmp += tick<DBG>() - k0;
+                    }
+                    if ((bal[j] >> lane) & 1u) {
+                        const uint32_t crel = (hb[j] & ((1u << COL_BITS) - 1u)) + (uint32_t)lane;
+                        buf[cnt + __popc(bal[j] & ((1u << lane) - 1u))] = make_key(x[j] + 0.0f, gc_base + (int32_t)crel);
+                    }
+                    if (lane == rq) cnt_reg = cnt + __popc(bal[j]);
+                }
             }
-            if (lane < n) asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %1};" ::"r"(ent_a + 8u * (uint32_t)((tail + lane) & (NENT - 1))), "r"(0u) : "memory");   // slots free again
+            if (lane < n) sh_st_volatile_u32(hdr_a + 4u * (uint32_t)((tail + lane) & (NBLK - 1)), 0u);   // blocks free again
             __syncwarp();                                                      // clears ordered before the tail store below
             tail += n;
             if (lane == 0) sh_st_volatile_u32(tail_a, (uint32_t)tail);
@@ -693,7 +709,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             const int row = q * 32 + r;
             const int64_t grow = row0 + row;
             if (grow >= p.nu) break;
-            const int cn = sh_ld_volatile(cnt_a + 4u * (uint32_t)r);
+            const int cn = __shfl_sync(0xffffffffu, cnt_reg, r);
             sel_sort(bufq + (size_t)r * CAP, cn < CAP ? cn : CAP, lane, skey, has_rated ? rated_idx : nullptr, rlo_sh[row], rhi_sh[row]);
             const int64_t o = ((int64_t)split * p.nu + grow) * KPRIME;
 #pragma unroll
@@ -863,7 +879,7 @@ static int make_tmap(CUtensorMap* tm, const void* ptr, int64_t rows, int dpad, i
 long long* g_filter_dbg = nullptr;   // set through tkr_debug_set_filter_counters (profiling aid)
 int g_seed_div = 12;                 // a sweep seeds on its first 1/g_seed_div tiles (tkr_debug_set_seed_div)
 int g_filter_mode = 1;               // kernel MODE used while the counters are set (tkr_debug_set_filter_mode)
-int g_seed_rank = 0;                 // 0 = automatic (tkr_debug_set_filter_tuning)
+int g_seed_rank = 0, g_cap_trigger = 0;   // 0 = automatic (tkr_debug_set_filter_tuning)
 
 struct TcPlan {
     int dpad, kb, cps, stages, ns, tps;
@@ -922,9 +938,9 @@ using namespace tkr;
 
 extern "C" void tkr_debug_set_filter_counters(long long* dev_buf) { g_filter_dbg = dev_buf; }
 extern "C" void tkr_debug_set_seed_div(int32_t div) { g_seed_div = div >= 4 && div <= 1024 ? div : 12; }
-extern "C" void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t reserved) {
-    (void)reserved;
+extern "C" void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t cap_trigger) {
     g_seed_rank = (seed_rank == 3 || seed_rank == 4) ? seed_rank : 0;
+    g_cap_trigger = (cap_trigger >= KPRIME + 8 && cap_trigger <= CAP) ? cap_trigger : 0;
 }
 extern "C" void tkr_debug_set_filter_mode(int32_t mode) { g_filter_mode = mode >= 1 && mode <= 5 ? mode : 1; }
 // CTA pairs of the filter kernel that can be resident at once on the current device (74 on a full B200), or < 0.
@@ -992,9 +1008,11 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
     fp.seed_tiles = P.seed_tiles; fp.out_tau0 = (float*)(w + P.o_tau0);
-    // (tuning aid; measured on item shards of 2^17 .. 2^20 items, profiles/r02_filter_roles.txt: seeding on the 3rd largest
-    // chunk maximum sends a handful of rows per batch to the exact fallback, which costs more than the hand-offs it saves)
+    // (tuning aids; measured on item shards of 2^17 .. 2^20 items, profiles/r02_filter_roles.txt: seeding on the 3rd largest
+    // chunk maximum sends a handful of rows per batch to the exact fallback, which costs more than the hand-offs it saves,
+    // and compacting at 96 keys is a wash -- the defaults stay 4 / CAP)
     fp.seed_rank = g_seed_rank ? g_seed_rank : 4;
+    fp.cap_trigger = g_cap_trigger ? g_cap_trigger : CAP;
     dim3 grid((unsigned)(2 * ((nu + 2 * FM - 1) / (2 * FM))), (unsigned)P.ns);   // clusters of 2 along x
 #define TKR_FILTER_LAUNCH(MODE)                                                                                                 \
     do {                                                                                                                        \
