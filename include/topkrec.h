@@ -184,6 +184,13 @@ int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* ms
                  const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* ws, size_t ws_bytes,
                  void* stream);
 
+/* Barrier-free ("Hogwild") plain-SGD steps (SURVEY 8(f) NEXT-4; update rule of old/methods/bpr.py:57-61 without its batch
+ * synchrony): ONE kernel per step adds -lr * gradient of every occurrence straight onto the parameter rows while other warps
+ * read them.  A throughput mode: not bit-reproducible, no parity claim beyond "equals tkr_bpr_step(optimizer = SGD) when no row
+ * occurs twice in a batch".  No workspace, no slots; same triple / sampler / loss conventions as tkr_bpr_step. */
+int tkr_bpr_hogwild(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, const int32_t* u, const int32_t* i, const int32_t* j,
+                    int64_t batch, int64_t n_steps, const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* stream);
+
 /* Same, with the triples and the losses in HOST memory (the feed_dict /
  * fetch of sess.run): copies u/i/j host->device into `staging` (device,
  * >= 3*batch*n_steps*4 bytes), runs the steps, copies loss back, synchronises. */
@@ -206,6 +213,11 @@ typedef struct tkr_vbpr_cfg {
     tkr_bpr_cfg base;
     int32_t d_feat;
     float lambda_e; /* single/vbpr.py:18 */
+    /* 0: per-triple objective x_n = r_n + y_n (what the code evidently means; any batch size).
+     * 1: the graph exactly as written: the bias variables are [n_items,1] / [d,1], so vbpr.py:61 broadcasts x to [B,B],
+     *    x[a,b] = r_a + y_b with r = rb_i - rb_j + (f_i - f_j).c and y = x_ui - x_uj, and the loss sums over all B*B entries
+     *    (reference defect D-14).  O(B^2) per step: batch <= 4096. */
+    int32_t pairwise;
 } tkr_vbpr_cfg;
 size_t tkr_vbpr_workspace_bytes(const tkr_vbpr_cfg* cfg, int64_t batch);
 int tkr_vbpr_workspace_init(const tkr_vbpr_cfg* cfg, int64_t batch, void* ws, size_t ws_bytes, void* stream);

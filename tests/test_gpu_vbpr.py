@@ -44,7 +44,7 @@ def _core_ws_bytes(cfg, B):
     return n
 
 
-def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, **cfg_kw):
+def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, pairwise=False, **cfg_kw):
     rng = np.random.default_rng(seed)
     st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
     st["rb"] = (0.01 * rng.standard_normal(ni)).astype(np.float32)
@@ -58,7 +58,7 @@ def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, **cfg_kw):
     p = 1.0 / np.arange(1, ni + 1); p /= p.sum()
     i = rng.choice(ni, B * steps, p=p).astype(np.int32); j = rng.integers(0, ni, B * steps).astype(np.int32)
     ocfg = bpr_ref.BprCfg(**cfg_kw)
-    cfg = topkrec.VbprCfg(nu, ni, k, dF, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lambda_e, ocfg.lr, ocfg.mode, ocfg.optimizer)
+    cfg = topkrec.VbprCfg(nu, ni, k, dF, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lambda_e, ocfg.lr, ocfg.mode, ocfg.optimizer, pairwise=pairwise)
     d = _dev_state(st, F, k)
     Fd = torch.from_numpy(F).cuda()
     ws = topkrec.vbpr_workspace(cfg, B)
@@ -67,7 +67,7 @@ def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, **cfg_kw):
     loss = torch.empty(steps, dtype=torch.float32, device="cuda")
     topkrec.vbpr_project(cfg, d, Fd)
     topkrec.vbpr_step(cfg, d, Fd, torch.from_numpy(u).cuda(), torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, ws, loss)
-    ref_loss = np.array([bpr_ref.vbpr_step(st, F, u[t * B:(t + 1) * B], i[t * B:(t + 1) * B], j[t * B:(t + 1) * B], ocfg) for t in range(steps)])
+    ref_loss = np.array([bpr_ref.vbpr_step(st, F, u[t * B:(t + 1) * B], i[t * B:(t + 1) * B], j[t * B:(t + 1) * B], ocfg, pairwise=pairwise) for t in range(steps)])
     h = k // 2
     got = {n: v.cpu().numpy() for n, v in d.items()}
     pairs = {"UR": got["U"][:, :h], "UC": got["U"][:, h:], "IR": got["V"][:, :h], "rb": got["rb"], "E": got["E"], "c": got["c"],
@@ -218,3 +218,39 @@ def test_vbpr_data_parallel_halves_equal_one_big_batch():
         assert _rel(g, st[n]) <= REL_TOL, (n, _rel(g, st[n]))             # ... and equal to the union batch
     U = got["U"].copy(); U[1::2] = b["U"].cpu().numpy()[1::2]             # each rank updated only its own users
     assert _rel(U[:, :h], st["UR"]) <= REL_TOL and _rel(U[:, h:], st["UC"]) <= REL_TOL
+
+
+@pytest.mark.parametrize("shape,kw", [((300, 200, 64, 300, 256, 6), {}), ((200, 150, 32, 128, 64, 10), dict(lambda_e=0.01, lambda_b=0.05)),
+                                      ((400, 300, 50, 500, 700, 3), dict(mode="l1", lambda_b=0.01)), ((300, 200, 16, 70, 4096, 2), {})])
+def test_vbpr_graph_as_written_matches_oracle(shape, kw):
+    """tkr_vbpr_cfg.pairwise = 1: the reference's graph exactly as written -- vbpr.py:61 broadcasts x to [B, B] (D-14), every
+    embedding-side weight is a column sum and every bias-side weight a row sum of sigma(-x) -- against the oracle whose pairwise
+    form agrees with the literal torch transcription of the graph (tests/test_oracle.py)"""
+    nu, ni, k, dF, B, steps = shape
+    _run(nu, ni, k, dF, B, steps, seed=51, pairwise=True, **kw)
+
+
+def test_vbpr_graph_as_written_fused_sampler_and_limits(mini):
+    """the pairwise pre-pass needs the batch's triples before the gradient kernel: with the fused sampler they are drawn ahead
+    (same draws); batches beyond 4096 are refused"""
+    from test_gpu_bpr import _mini_tables
+    tr_users, tr_data, indptr, idx, nu, ni = _mini_tables(mini)
+    rng = np.random.default_rng(52)
+    k, dF, B, steps = 16, 40, 128, 5
+    st = bpr_ref.new_vbpr_state(nu, ni, k, dF, rng)
+    F = np.abs(rng.standard_normal((ni, dF))).astype(np.float32)
+    cfg = topkrec.VbprCfg(nu, ni, k, dF, pairwise=True)
+    smp = topkrec.Sampler(tr_users, indptr, idx, ni, seed=5)
+    Fd = torch.from_numpy(F).cuda()
+    a, b = _dev_state(st, F, k), _dev_state(st, F, k)
+    ws = topkrec.vbpr_workspace(cfg, B)
+    la, lb = torch.empty(steps, device="cuda"), torch.empty(steps, device="cuda")
+    topkrec.vbpr_project(cfg, a, Fd); topkrec.vbpr_project(cfg, b, Fd)
+    topkrec.vbpr_step(cfg, a, Fd, None, None, None, B, steps, ws, la, sampler=smp, first_draw=77)
+    u, i, j = topkrec.bpr_sample(smp, 77, B * steps)
+    topkrec.vbpr_step(cfg, b, Fd, u, i, j, B, steps, ws, lb)
+    for n in a:
+        assert _rel(a[n].cpu().numpy(), b[n].cpu().numpy()) <= 2e-6, n
+    assert np.allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-5)
+    with pytest.raises(topkrec.TkrError, match="O\\(B\\^2\\)"):
+        topkrec.vbpr_workspace(cfg, 8192)

@@ -36,13 +36,21 @@ struct StepExtra {
     int item_cols;
     const float* b_reg;
     float* wq;
-    int hot_rows = 0;      // privatised item rows per block (0 = off): shared memory holds hot_rows * (d + 2) floats
+    int hot_rows = 0;      // privatised item rows per block (0 = off): shared memory holds hot_rows * (d + 3) floats
+    // VBPR with the graph exactly as written (vbpr.py:61 broadcasts x to [B, B], defect D-14): the weight of triple n is
+    // s_emb[n] = sum_a sigma(-x[a, n]) on everything reached through the embeddings and s_bias[n] = sum_b sigma(-x[n, b])
+    // on the biases / wq, both computed beforehand (vbpr_pair_kernel); the data term of the loss comes from there as well.
+    const float* s_emb = nullptr;
+    const float* s_bias = nullptr;
 };
 
 // MODE_LIST / MODE_DENSE: every touched row goes through the gradient accumulators (touched rows listed / flagged).
 // MODE_COUNT: a counting pre-pass tells how often each row occurs in the batch; rows that occur once are updated
 //             in place by the gradient kernel (no accumulator round trip), the others take the accumulator path.
 constexpr int MODE_LIST = 0, MODE_DENSE = 1, MODE_COUNT = 2;
+// MODE_HOGWILD: no accumulators, no barrier, no apply pass -- every occurrence adds -lr * gradient straight onto the
+//             parameter rows (ws.GU / GV / Gb point AT U / V / b); rows read while others update them (SURVEY 8(f) NEXT-4).
+constexpr int MODE_HOGWILD = 3;
 
 size_t bpr_ws_total(const tkr_bpr_cfg* cfg, int64_t B);
 int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, StepWs* out);

@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
         const float bdiff = valid ? __ldg(b + i) - __ldg(b + j) : 0.f;
         const float bi = valid ? __ldg(ex.b_reg + i) : 0.f, bj = valid ? __ldg(ex.b_reg + j) : 0.f;   // regularised bias
         float x_mine = 0.f, s_mine = 0.f;
+        const bool pairwise = ex.s_emb != nullptr;                       // (VBPR as written: weights precomputed per triple)
+        const float se_mine = (pairwise && valid) ? __ldg(ex.s_emb + n) : 0.f;
         // MODE_COUNT: bit 0/1/2 = the u / i / j row of this triple occurs once in the batch -> updated in place
         int hs_i = 0, hs_j = 0;        // privatised slot + 1 of the item rows (0 = cold)
         if (hmax > 0 && valid) {
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
 #pragma unroll
                 for (int q = 0; q < VW; ++q) x = fmaf(cur.u[c].v[q], cur.i[c].v[q] - cur.j[c].v[q], x);   // <U_u, V_i - V_j>
             x = warp_sum(x) + __shfl_sync(FULL, bdiff, t);           // x_uij, bpr.py:87-89
-            const float s = __fdividef(1.0f, 1.0f + __expf(x));      // sigma(-x) = -d/dx log(1+e^-x)
+            const float s = pairwise ? __shfl_sync(FULL, se_mine, t) : __fdividef(1.0f, 1.0f + __expf(x));      // sigma(-x) = -d/dx log(1+e^-x)
             if (lane == t) { x_mine = x; s_mine = s; }
             if (want_loss) {
 #pragma unroll
@@ -219,6 +221,10 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
                         a.v[e] = fmaf(-s, cur.i[c].v[e] - cur.j[c].v[e], reg_grad<L1>(cur.u[c].v[e], cfg.lambda_u));  // gU   (App. A.2)
                         p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], lam_i[c]));                      // gV_i
                         q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], lam_j[c]));                       // gV_j
+                    }
+                    if (mode == MODE_HOGWILD) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) { a.v[e] *= -cfg.lr; p.v[e] *= -cfg.lr; q.v[e] *= -cfg.lr; }
                     }
                     if (INPLACE && (sg & 1)) {   // the only occurrence of this row: optimiser update in place
 #pragma unroll
@@ -250,8 +256,8 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
         }
         // lane-parallel scalar tail: lane t finishes triple t
         if (valid) {
-            if (mode == MODE_COUNT) {
-                // the counts are the touched flags
+            if (mode == MODE_COUNT || mode == MODE_HOGWILD) {
+                // the counts are the touched flags / nothing to flag
             } else if (mode == MODE_DENSE) {
                 ws.cntU[u] = 1; ws.tchV[i] = 1.0f; ws.tchV[j] = 1.0f;
             } else {   // first toucher of a row appends it to the step's touched list
@@ -259,15 +265,17 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
                 if (atomicAdd(ws.cntV + i, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = i;
                 if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
             }
-            const float gbi = -s_mine + reg_grad<L1>(bi, cfg.lambda_b), gbj = s_mine + reg_grad<L1>(bj, cfg.lambda_b);
+            if (pairwise) s_mine = __ldg(ex.s_bias + n);           // the bias / wq path of the [B, B] graph sums over the other index
+            const float gsc = mode == MODE_HOGWILD ? -cfg.lr : 1.0f;
+            const float gbi = gsc * (-s_mine + reg_grad<L1>(bi, cfg.lambda_b)), gbj = gsc * (s_mine + reg_grad<L1>(bj, cfg.lambda_b));
             if (hs_i) { sh_red_add(hot_b + hs_i - 1, gbi); hot_dirty[hs_i - 1] = 1.f; } else atomicAdd(ws.Gb + i, gbi);
             if (hs_j) { sh_red_add(hot_b + hs_j - 1, gbj); hot_dirty[hs_j - 1] = 1.f; } else atomicAdd(ws.Gb + j, gbj);
             if (ex.wq != nullptr) {
                 if (hs_i) sh_red_add(hot_wq + hs_i - 1, -s_mine); else atomicAdd(ex.wq + i, -s_mine);
                 if (hs_j) sh_red_add(hot_wq + hs_j - 1, s_mine); else atomicAdd(ex.wq + j, s_mine);
             }
-            if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)
-                loss_acc += fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
+            if (want_loss)   // log(1+e^-x) = max(-x,0) + log(1 + e^-|x|)   (pairwise: the B*B data terms were summed by vbpr_pair_kernel)
+                loss_acc += (pairwise ? 0.f : fmaxf(-x_mine, 0.f) + __logf(1.0f + __expf(-fabsf(x_mine)))) + reg_val<L1>(bi, cfg.lambda_b) + reg_val<L1>(bj, cfg.lambda_b);
         }
     }
     if (hmax > 0) {    // flush the block's privatised sums: one vector red per chunk per dirty row
@@ -728,5 +736,32 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
     }
     if (loss_host != nullptr) TKR_CUDA(cudaMemcpyAsync(loss_host, dl, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, st));
     TKR_CUDA(cudaStreamSynchronize(st));
+    return TKR_OK;
+}
+
+// Barrier-free ("Hogwild") plain SGD: one kernel per step, every occurrence's -lr * gradient is added straight onto the
+// parameter rows with red.global.add while other warps read them (SURVEY 8(f) NEXT-4; the update rule of
+// old/methods/bpr.py:57-61 without its batch synchrony).  Not bit-reproducible; equal to the synchronous SGD step when no
+// row occurs twice in a batch.  No workspace.
+extern "C" int tkr_bpr_hogwild(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, const int32_t* u, const int32_t* i, const int32_t* j,
+                               int64_t B, int64_t n_steps, const tkr_sampler* smp, uint64_t first_draw, float* loss_out, void* stream) {
+    if (int rc = bpr_check_cfg(cfg, B)) return rc;
+    if (int rc = check_state(cfg, U, V, b)) return rc;
+    TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
+    SamplerDev sd = {};
+    if (u == nullptr) {
+        if (int rc = bpr_make_sampler(smp, &sd)) return rc;
+        TKR_CHECK_ARG(smp->n_items == cfg->n_items, "sampler n_items != cfg n_items");
+    } else {
+        TKR_CHECK_ARG(i && j, "i, j must not be NULL when u is given");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    StepWs w = {};
+    w.GU = U; w.GV = V; w.Gb = b;                               // the "accumulators" are the parameters themselves
+    StepExtra ex{cfg->d, b, nullptr, 0};
+    if (loss_out != nullptr && n_steps > 0) TKR_CUDA(cudaMemsetAsync(loss_out, 0, sizeof(float) * (size_t)n_steps, st));
+    for (int64_t t = 0; t < n_steps; ++t)
+        if (int rc = bpr_dispatch_grad(cfg, U, V, b, u ? u + t * B : nullptr, u ? i + t * B : nullptr, u ? j + t * B : nullptr, B, sd,
+                                       first_draw + (uint64_t)t * (uint64_t)B, w, MODE_HOGWILD, ex, loss_out ? loss_out + t : nullptr, st)) return rc;
     return TKR_OK;
 }

@@ -266,10 +266,52 @@ __global__ void __launch_bounds__(256) vbpr_apply_dense_kernel(tkr_bpr_cfg cfg, 
     }
 }
 
+// ---- VBPR with the graph as written (D-14): x[a, b] = r_a + y_b ------------------------------------------------------
+// r_n = b'_i - b'_j (b' = rb + F.c), y_n = <U'_u, V'_i - V'_j> over all k columns (V' = [ir | F.E]); one warp per triple.
+__global__ void __launch_bounds__(256) vbpr_xparts_kernel(const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ bsum,
+                                                          const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb,
+                                                          int B, int d, float* __restrict__ r, float* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    for (int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < B; n += (gridDim.x * blockDim.x) >> 5) {
+        const int u = ub[n], i = ib[n], j = jb[n];
+        float acc = 0.f;
+        for (int c = lane; c < d; c += 32) acc = fmaf(U[(int64_t)u * d + c], V[(int64_t)i * d + c] - V[(int64_t)j * d + c], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) { y[n] = acc; r[n] = bsum[i] - bsum[j]; }
+    }
+}
+// block n: s_emb[n] = sum_a sigma(-(r_a + y_n)), s_bias[n] = sum_b sigma(-(r_n + y_b)); the B*B softplus terms go to *loss
+__global__ void __launch_bounds__(256) vbpr_pair_kernel(const float* __restrict__ r, const float* __restrict__ y, int B, float* __restrict__ s_emb,
+                                                        float* __restrict__ s_bias, float* __restrict__ loss) {
+    __shared__ float red[3][8];
+    const int n = blockIdx.x;
+    const float yn = y[n], rn = r[n];
+    float se = 0.f, sb = 0.f, ls = 0.f;
+    for (int a = threadIdx.x; a < B; a += blockDim.x) {
+        const float x = r[a] + yn;                                        // column n of x
+        se += __fdividef(1.0f, 1.0f + __expf(x));
+        ls += fmaxf(-x, 0.f) + __logf(1.0f + __expf(-fabsf(x)));
+        sb += __fdividef(1.0f, 1.0f + __expf(rn + y[a]));                 // row n of x
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); ls += __shfl_xor_sync(0xffffffffu, ls, o); }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = se; red[1][threadIdx.x >> 5] = sb; red[2][threadIdx.x >> 5] = ls; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a0 += red[0][w]; a1 += red[1][w]; a2 += red[2][w]; }
+        s_emb[n] = a0; s_bias[n] = a1;
+        if (loss != nullptr) atomicAdd(loss, a2);
+    }
+}
+constexpr int64_t kPairwiseMaxBatch = 4096;        // the literal graph is O(B^2) per step
+
 struct VbprWs {
     StepWs s; float* wq; float* GE; float* Gc; size_t total;
     // tensor-core route (large batches, dense features): F^T built once per workspace, the pre-split B operands per step
     bool tc; int Mp; float* Ft; float* Bp_hi; float* Bp_lo; float* Bg_hi; float* Bg_lo; unsigned long long* ft_tag;
+    float* pair;             // cfg.pairwise: [4][B] floats r, y, s_emb, s_bias  + the triples drawn ahead when the sampler is fused [3][B] int32
 };
 
 // The content GEMMs go to the tensor cores when every item row is (potentially) touched each step -- the dense mode of
@@ -287,8 +329,9 @@ static size_t vbpr_ws_bytes(const tkr_vbpr_cfg* cfg, int64_t B) {
                align_up((size_t)cfg->d_feat * h * 4, 256) + align_up((size_t)cfg->d_feat * 4, 256);
     if (vbpr_tc_shape(cfg, B)) {
         const size_t Mp = align_up((size_t)cfg->base.n_items, 4), NP = (size_t)gemm3_np((int)h);
-        n += align_up((size_t)cfg->d_feat * Mp * 4, 1024) + 2 * align_up(NP * cfg->d_feat * 4, 1024) + 2 * align_up(NP * Mp * 4, 1024) + 1024;
+        n += align_up((size_t)cfg->d_feat * Mp * 4, 1024) + 2 * align_up(NP * cfg->d_feat * 4, 1024) + 2 * align_up(NP * Mp * 4, 1024) + 1024 + 1024;
     }
+    if (cfg->pairwise) n += align_up((size_t)7 * B * 4, 1024) + 1024;
     return n;
 }
 
@@ -311,8 +354,10 @@ static int vbpr_carve(const tkr_vbpr_cfg* cfg, int64_t B, void* ws, size_t ws_by
         out->Bp_hi = (float*)p; p += align_up(NP * cfg->d_feat * 4, 1024);
         out->Bp_lo = (float*)p; p += align_up(NP * cfg->d_feat * 4, 1024);
         out->Bg_hi = (float*)p; p += align_up(NP * Mp * 4, 1024);
-        out->Bg_lo = (float*)p;
+        out->Bg_lo = (float*)p; p += align_up(NP * Mp * 4, 1024);
     }
+    out->pair = nullptr;
+    if (cfg->pairwise) { p = (char*)align_up((size_t)(uintptr_t)p, 1024); out->pair = (float*)p; }
     out->total = need;
     return TKR_OK;
 }
@@ -322,6 +367,8 @@ static int vbpr_check(const tkr_vbpr_cfg* cfg, int64_t B) {
     if (int rc = bpr_check_cfg(&cfg->base, B)) return rc;
     TKR_CHECK_ARG(cfg->base.d % 2 == 0, "VBPR needs an even k (k/2 rating + k/2 content dims, vbpr.py:37-44), got %d", cfg->base.d);
     TKR_CHECK_ARG(cfg->d_feat > 0, "d_feat must be positive");
+    TKR_CHECK_ARG(!cfg->pairwise || B <= kPairwiseMaxBatch, "pairwise (the [B,B] graph of vbpr.py:61 as written) is O(B^2): batch %lld > %lld",
+                  (long long)B, (long long)kPairwiseMaxBatch);
     return TKR_OK;
 }
 
@@ -386,6 +433,7 @@ static int vbpr_run(int phase, int data_parallel, const tkr_vbpr_cfg* cfg, float
     TKR_CHECK_ARG(phase == VBPR_APPLY || (bsum && F), "bsum and F must not be NULL");
     TKR_CHECK_ARG(phase == VBPR_GRAD || cfg->base.optimizer == TKR_OPT_SGD || (msU && msV && msrb && msE && msc), "RMSProp needs every rms slot");
     TKR_CHECK_ARG(n_steps >= 0, "n_steps < 0");
+    TKR_CHECK_ARG(!(cfg->pairwise && data_parallel), "pairwise (x over all pairs of the batch) cannot be split over ranks");
     SamplerDev sd = {};
     if (phase != VBPR_APPLY) {
         if (u == nullptr) {
@@ -436,8 +484,24 @@ static int vbpr_run(int phase, int data_parallel, const tkr_vbpr_cfg* cfg, float
         float* lt = loss_out ? loss_out + t : nullptr;
         if (phase != VBPR_APPLY) {
             if (int rc = project()) return rc;
-            if (int rc = bpr_dispatch_grad(bc, U, V, bsum, u ? u + t * B : nullptr, u ? i + t * B : nullptr, u ? j + t * B : nullptr, B, sd,
-                                           first_draw + (uint64_t)t * (uint64_t)B, w.s, mode, ex, lt, st)) return rc;
+            const int32_t *ut = u ? u + t * B : nullptr, *it = u ? i + t * B : nullptr, *jt = u ? j + t * B : nullptr;
+            StepExtra ext = ex;
+            if (cfg->pairwise) {
+                float* pr = w.pair;                                       // r | y | s_emb | s_bias, then the staged triples
+                if (u == nullptr) {                                       // fused sampler: the same draws, made ahead (x needs all of them)
+                    int32_t* su = (int32_t*)(pr + 4 * B);
+                    if (int rc = tkr_bpr_sample(smp, first_draw + (uint64_t)t * (uint64_t)B, B, su, su + B, su + 2 * B, stream)) return rc;
+                    ut = su; it = su + B; jt = su + 2 * B;
+                }
+                int64_t xb = (B + 7) / 8;
+                if (xb > kNumSMs * 8) xb = kNumSMs * 8;
+                vbpr_xparts_kernel<<<(unsigned)xb, 256, 0, st>>>(U, V, bsum, ut, it, jt, (int)B, bc->d, pr, pr + B);
+                TKR_LAUNCH_CHECK();
+                vbpr_pair_kernel<<<(unsigned)B, 256, 0, st>>>(pr, pr + B, (int)B, pr + 2 * B, pr + 3 * B, lt);
+                TKR_LAUNCH_CHECK();
+                ext.s_emb = pr + 2 * B; ext.s_bias = pr + 3 * B;
+            }
+            if (int rc = bpr_dispatch_grad(bc, U, V, bsum, ut, it, jt, B, sd, first_draw + (uint64_t)t * (uint64_t)B, w.s, mode, ext, lt, st)) return rc;
             if (tc) {   // [dE | dc] += F^T . [W | wq] over all items (untouched rows of W are zero)
                 if (int rc = gemm3_build_b(w.s.GV, bc->d, h, w.wq, bc->n_items, w.Mp, h, w.Bg_hi, w.Bg_lo, st)) return rc;
                 if (int rc = gemm3_run(1, w.Ft, dF, bc->n_items, w.Mp, w.Bg_hi, w.Bg_lo, w.Mp, h, w.GE, h, 0, w.Gc, nullptr, tc_splits, st)) return rc;

@@ -25,8 +25,15 @@ from .bpr import BPR
 
 class VBPR(BPR):
     def __init__(self, k: int, d: int, lambda_u: float = 2.5e-3, lambda_i: float = 2.5e-3, lambda_j: float = 2.5e-4,
-                 lambda_b: float = 0, lambda_e: float = 0, lr: float = 1.0e-4, mode: str = 'l2', **engine_kw) -> None:
+                 lambda_b: float = 0, lambda_e: float = 0, lr: float = 1.0e-4, mode: str = 'l2', graph: str = 'reference',
+                 **engine_kw) -> None:
+        """``graph='reference'`` (default): the objective exactly as ``vbpr.py:59-72`` computes it -- the bias variables are
+        ``[n_items, 1]`` / ``[d, 1]``, so ``x_uij`` broadcasts to ``[B, B]`` (x[a, b] = r_a + y_b) and the loss sums over
+        all B*B entries (a defect of the reference; O(B^2), batch_size <= 4096).
+        ``graph='per-triple'``: x_n = r_n + y_n, the objective the code evidently means; any batch size."""
         super().__init__(k, lambda_u, lambda_i, lambda_j, lambda_b, lr, mode, **engine_kw)
+        assert graph in ('reference', 'per-triple')
+        self.graph = graph
         self.d = d
         self.le = lambda_e
         self.feat = None
@@ -34,7 +41,7 @@ class VBPR(BPR):
 
     def _engine_cfg(self):
         return topkrec.VbprCfg(self.n_users, self.n_items, self.k, self.d, self.lu, self.li, self.lj, self.lb, self.le,
-                               self.lr, self.mode, self.optimizer)
+                               self.lr, self.mode, self.optimizer, pairwise=self.graph == 'reference')
 
     def build_graph(self):
         """Device state per ``vbpr.py:37-48``: ur, uc, ir ~ N(0, 0.01); irb = 0; cem = 2/(d k); icb = 0."""
@@ -68,6 +75,8 @@ class VBPR(BPR):
         if epoch_sample_limit is not None:
             self.epoch_sample_limit = int(epoch_sample_limit)          # vbpr.py:83-84 has no int assert
         batch_limit = self.epoch_sample_limit // batch_size + 1
+        assert self.graph == 'per-triple' or batch_size <= 4096, \
+            "graph='reference' reproduces the reference's [B, B] objective (O(B^2) per step): use batch_size <= 4096 or graph='per-triple'"
         self.build_graph()
         st, h = self._state, self.k // 2
         if model_path is not None:

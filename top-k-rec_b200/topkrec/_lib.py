@@ -22,7 +22,7 @@ class tkr_bpr_cfg(C.Structure):
 
 
 class tkr_vbpr_cfg(C.Structure):
-    _fields_ = [("base", tkr_bpr_cfg), ("d_feat", C.c_int32), ("lambda_e", C.c_float)]
+    _fields_ = [("base", tkr_bpr_cfg), ("d_feat", C.c_int32), ("lambda_e", C.c_float), ("pairwise", C.c_int32)]
 
 
 class tkr_sampler(C.Structure):
@@ -66,6 +66,7 @@ def lib():
     L.tkr_bpr_grad.argtypes = [cfgp] + [vp] * 3 + [vp] * 3 + [i64, smpp, u64, vp, vp, sz, i32, vp]
     L.tkr_bpr_apply.argtypes = [cfgp] + [vp] * 6 + [i64, vp, sz, i32, vp]
     L.tkr_bpr_step.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp, sz, vp]
+    L.tkr_bpr_hogwild.argtypes = [cfgp] + [vp] * 3 + [vp] * 3 + [i64, i64, smpp, u64, vp, vp]
     L.tkr_bpr_step_host.argtypes = [cfgp] + [vp] * 6 + [vp] * 3 + [i64, i64, vp, vp, sz, vp, sz, vp]
     L.tkr_bpr_sample.argtypes = [smpp, u64, i64, vp, vp, vp, vp]
     L.tkr_bpr_dp_layout.argtypes = [cfgp, C.POINTER(C.c_int64)]
@@ -101,7 +102,7 @@ def lib():
     L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
     L.tkr_als_gram.argtypes = [vp, i32, vp, i64, C.c_float, C.c_float, vp, vp, sz, vp]
     L.tkr_als_solve_rows.argtypes = [C.POINTER(tkr_als_cfg), C.POINTER(tkr_als_plan), vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    for name in ("tkr_vbpr_grad", "tkr_vbpr_apply", "tkr_vbpr_workspace_layout", "tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    for name in ("tkr_bpr_hogwild", "tkr_vbpr_grad", "tkr_vbpr_apply", "tkr_vbpr_workspace_layout", "tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
@@ -170,9 +171,10 @@ class VbprCfg:
     """Host mirror of tkr_vbpr_cfg (single/vbpr.py:18 defaults); k must be even."""
 
     def __init__(self, n_users, n_items, k, d_feat, lambda_u=2.5e-3, lambda_i=2.5e-3, lambda_j=2.5e-4, lambda_b=0.0, lambda_e=0.0,
-                 lr=1.0e-4, mode="l2", optimizer="rmsprop"):
+                 lr=1.0e-4, mode="l2", optimizer="rmsprop", pairwise=False):
+        """pairwise=True: the graph exactly as the reference writes it (vbpr.py:61 broadcasts x to [B, B]; batch <= 4096)"""
         base = BprCfg(n_users, n_items, k, lambda_u, lambda_i, lambda_j, lambda_b, lr, mode, optimizer).c
-        self.c = tkr_vbpr_cfg(base, int(d_feat), float(lambda_e))
+        self.c = tkr_vbpr_cfg(base, int(d_feat), float(lambda_e), int(bool(pairwise)))
 
     @property
     def ptr(self):
@@ -295,6 +297,16 @@ def bpr_step(cfg: BprCfg, U, V, b, msU, msV, msb, u, i, j, batch, n_steps, ws, l
                                   _dev(u, i32, "u"), _dev(i, i32, "i"), _dev(j, i32, "j"), int(batch), int(n_steps),
                                   sampler.ptr if sampler is not None else None, int(first_draw),
                                   _dev(loss, f32, "loss"), ws.data_ptr(), ws.numel(), _stream()))
+
+
+def bpr_hogwild(cfg: BprCfg, U, V, b, u, i, j, batch, n_steps, loss=None, sampler=None, first_draw=0):
+    """tkr_bpr_hogwild: barrier-free plain-SGD steps, one kernel per step (no workspace, no slots; not bit-reproducible)"""
+    f32, i32 = torch.float32, torch.int32
+    _need_cuda(U, V, b)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_bpr_hogwild(cfg.ptr, _dev(U, f32, "U"), _dev(V, f32, "V"), _dev(b, f32, "b"), _dev(u, i32, "u"), _dev(i, i32, "i"),
+                                     _dev(j, i32, "j"), int(batch), int(n_steps), sampler.ptr if sampler is not None else None, int(first_draw),
+                                     _dev(loss, f32, "loss"), _stream()))
 
 
 def bpr_step_host(cfg: BprCfg, U, V, b, msU, msV, msb, u_host, i_host, j_host, batch, n_steps, loss_host, staging, ws):
