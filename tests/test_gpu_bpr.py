@@ -474,3 +474,39 @@ def test_bpr_class_numpy_sampler_matches_oracle_replay(mini):
     ref_loss = bpr_ref.bpr_train(st, ub.ravel(), ib.ravel(), jb.ravel(), 64, bpr_ref.BprCfg())
     assert _rel(m.fue, st["U"]) <= REL_TOL and _rel(m.fie, st["V"]) <= REL_TOL and _rel(m.fib.ravel(), st["b"]) <= REL_TOL
     assert np.allclose(m.losses, ref_loss, rtol=1e-4)
+
+
+def test_hogwild_sgd_equals_synchronous_sgd_without_row_conflicts_and_trains():
+    """tkr_bpr_hogwild (SURVEY 8(f) NEXT-4): with no row occurring twice in a batch the barrier-free update IS the synchronous
+    SGD step (old/methods/bpr.py:57-61) -- checked against the oracle; with conflicts it is only required to train."""
+    rng = np.random.default_rng(61)
+    nu, ni, d, B, steps = 4000, 9000, 128, 1024, 6
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    st["U"] *= 20; st["V"] *= 20
+    u = np.concatenate([rng.permutation(nu)[:B] for _ in range(steps)]).astype(np.int32)
+    ij = np.stack([rng.permutation(ni)[:2 * B] for _ in range(steps)])
+    i, j = ij[:, :B].ravel().astype(np.int32), ij[:, B:].ravel().astype(np.int32)          # every row at most once per batch
+    ocfg = bpr_ref.BprCfg(optimizer="sgd", lr=0.05, lambda_b=0.01)
+    cfg = topkrec.BprCfg(nu, ni, d, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lr, "l2", "sgd")
+    dst = _to_dev(st)
+    loss = torch.empty(steps, device="cuda")
+    topkrec.bpr_hogwild(cfg, dst["U"], dst["V"], dst["b"], torch.from_numpy(u).cuda(), torch.from_numpy(i).cuda(), torch.from_numpy(j).cuda(), B, steps, loss)
+    ref_loss = bpr_ref.bpr_train(st, u, i, j, B, ocfg)
+    for n in ("U", "V", "b"):
+        assert _rel(dst[n].cpu().numpy(), st[n]) <= REL_TOL, n
+    assert np.allclose(loss.cpu().numpy(), ref_loss, rtol=1e-4)
+    # heavy conflicts (a few popular rows): still descends
+    n_tr = 4096 * 60
+    u2 = rng.integers(0, 50, n_tr).astype(np.int32); i2 = rng.choice(200, n_tr).astype(np.int32); j2 = (200 + rng.integers(0, 200, n_tr)).astype(np.int32)
+    l2 = torch.empty(60, device="cuda")
+    topkrec.bpr_hogwild(cfg, dst["U"], dst["V"], dst["b"], torch.from_numpy(u2).cuda(), torch.from_numpy(i2).cuda(), torch.from_numpy(j2).cuda(), 4096, 60, l2)
+    l2 = l2.cpu().numpy()
+    assert np.isfinite(l2).all() and l2[-1] < 0.7 * l2[0]
+
+
+def test_bpr_class_hogwild_sampling_switch(mini):
+    import single
+    m = single.BPR(k=16, seed=3, lr=0.05)
+    m.load_training_data(os.path.join(mini, "uid"), os.path.join(mini, "vid"), os.path.join(mini, "f0tr.txt"))
+    m.train(sampling="user uniform hogwild", epochs=4, batch_size=64, epoch_sample_limit=2000)
+    assert np.isfinite(m.fue).all() and m.losses[-1] < m.losses[0]

@@ -78,7 +78,8 @@ def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, pairwise=F
     # export identity (vbpr.py:124-126): the engine state IS (fue, fie, fib)
     fue, fie, fib = bpr_ref.vbpr_export(st, F)
     assert _rel(got["U"], fue) <= REL_TOL and _rel(got["V"], fie) <= REL_TOL and _rel(got["bsum"], fib.ravel()) <= REL_TOL
-    core = ws[:_core_ws_bytes(cfg, B)]
+    plain = topkrec.VbprCfg(nu, ni, k, dF, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lambda_e, ocfg.lr, ocfg.mode, ocfg.optimizer)
+    core = ws[:_core_ws_bytes(plain, B)]          # (without the tensor-core and pairwise scratch regions, which stay non-zero)
     assert int(core.count_nonzero().item()) <= 4 * (min(B, nu) + min(2 * B, ni)) + 8, "accumulators must be re-zeroed (only the row lists may be stale)"
     return d
 

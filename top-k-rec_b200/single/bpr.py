@@ -33,7 +33,7 @@ class BPR(REC):
         self.lu, self.li, self.lj, self.lb = lambda_u, lambda_i, lambda_j, lambda_b
         self.lr = lr
         self.mode = mode
-        self.optimizer = optimizer            # 'rmsprop' (reference) | 'sgd' (old/methods/bpr.py)
+        self.optimizer = optimizer            # 'rmsprop' (reference) | 'sgd' (old/methods/bpr.py, batch-synchronous) | 'hogwild' (barrier-free SGD)
         self.sampler_backend = sampler        # 'device' (Philox, fused) | 'numpy' (reference RNG replay)
         self.seed = seed
         self.device = device
@@ -78,7 +78,7 @@ class BPR(REC):
     # ----------------------------------------------------------------- state
     def _engine_cfg(self):
         return topkrec.BprCfg(self.n_users, self.n_items, self.k, self.lu, self.li, self.lj, self.lb, self.lr,
-                              self.mode, self.optimizer)
+                              self.mode, 'sgd' if self.optimizer == 'hogwild' else self.optimizer)
 
     def build_graph(self):
         """Allocate and initialise the device state: the counterpart of the
@@ -134,7 +134,12 @@ class BPR(REC):
         assert isinstance(sampling, str)
         assert isinstance(epochs, int)
         assert isinstance(batch_size, int)
-        assert sampling == 'user uniform', "only 'user uniform' sampling exists (bpr.py:115-117)"
+        # 'user uniform' is the reference's only sampler (bpr.py:115-117); 'user uniform hogwild' keeps it and switches the
+        # update to barrier-free plain SGD (SURVEY 8(f) NEXT-4: one kernel per step, not bit-reproducible)
+        assert sampling in ('user uniform', 'user uniform hogwild'), "sampling must be 'user uniform' or 'user uniform hogwild'"
+        if sampling.endswith('hogwild'):
+            self.optimizer = 'hogwild'
+            sampling = 'user uniform'
         if epoch_sample_limit is not None:
             # the shipped train.py passes 10e5 (a float); accept integral floats (SURVEY D-1)
             assert float(epoch_sample_limit) == int(epoch_sample_limit), 'epoch_sample_limit must be integral'
@@ -189,7 +194,13 @@ class BPR(REC):
         while done < n_steps:
             n = min(chunk, n_steps - done)
             t1 = time.time()
-            if host_gen is None:
+            if host_gen is None and self.optimizer == 'hogwild':
+                loss = torch.empty(n, dtype=torch.float32, device=st['U'].device)
+                topkrec.bpr_hogwild(self._cfg, st['U'], st['V'], st['b'], None, None, None, batch_size, n, loss,
+                                    sampler=self._device_sampler(), first_draw=self._draws)
+                self._draws += n * batch_size
+                loss = loss.cpu().numpy()
+            elif host_gen is None:
                 loss = torch.empty(n, dtype=torch.float32, device=st['U'].device)
                 topkrec.bpr_step(self._cfg, st['U'], st['V'], st['b'], st['msU'], st['msV'], st['msb'], None, None, None,
                                  batch_size, n, ws, loss, sampler=self._device_sampler(), first_draw=self._draws)
