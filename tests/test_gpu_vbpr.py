@@ -80,7 +80,8 @@ def _run(nu, ni, k, dF, B, steps, seed, sparse_feat=False, hot=False, pairwise=F
     assert _rel(got["U"], fue) <= REL_TOL and _rel(got["V"], fie) <= REL_TOL and _rel(got["bsum"], fib.ravel()) <= REL_TOL
     plain = topkrec.VbprCfg(nu, ni, k, dF, ocfg.lambda_u, ocfg.lambda_i, ocfg.lambda_j, ocfg.lambda_b, ocfg.lambda_e, ocfg.lr, ocfg.mode, ocfg.optimizer)
     core = ws[:_core_ws_bytes(plain, B)]          # (without the tensor-core and pairwise scratch regions, which stay non-zero)
-    assert int(core.count_nonzero().item()) <= 4 * (min(B, nu) + min(2 * B, ni)) + 8, "accumulators must be re-zeroed (only the row lists may be stale)"
+    # (stale by design: the touched-row lists of the step kernels, and for small batches the projected-row list + the triples drawn ahead)
+    assert int(core.count_nonzero().item()) <= 4 * (min(B, nu) + min(2 * B, ni)) + 20 * B + 16, "accumulators must be re-zeroed (only row lists / staged triples may be stale)"
     return d
 
 
@@ -255,3 +256,10 @@ def test_vbpr_graph_as_written_fused_sampler_and_limits(mini):
     assert np.allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-5)
     with pytest.raises(topkrec.TkrError, match="O\\(B\\^2\\)"):
         topkrec.vbpr_workspace(cfg, 8192)
+
+
+def test_vbpr_small_batch_projects_only_touched_rows():
+    """B = 256 on a table of 3 000 items: only the <= 512 item rows of a batch are re-projected per step (the export is refreshed
+    for every row at the end); explicit triples and the fused sampler (triples drawn ahead) give the same result as the oracle"""
+    d = _run(700, 3000, 64, 300, 256, 12, seed=71, lambda_e=0.01, lambda_b=0.01)
+    assert d is not None
