@@ -109,6 +109,11 @@ __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restri
     float accq[RT] = {};
     // A chunk: TM rows x 32 k of F (row-major), transposed into As[k][row]; B chunk: 32 k x 64 n of E.  The next chunk's
     // global loads are issued before the current chunk is multiplied (register double buffer).
+    // split-K over blockIdx.z (row-list mode only: a few hundred rows would otherwise be a few long serial loops); the
+    // partial products are then added atomically onto rows the caller has zeroed / initialised to rb
+    const int kper = (((K + GK - 1) / GK + gridDim.z - 1) / gridDim.z) * GK;
+    const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
+    if (kbeg >= kend) return;
     float4 pa[AIT], pb[2];
     float pc = 0.f;
     auto fetch = [&](int k0) {
@@ -121,8 +126,8 @@ __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restri
             if (idx < NA && mi < M) {
                 const int m = rows ? __ldg(rows + mi) : mi;
                 const float* src = F + (int64_t)m * K + k;
-                if (vec && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src));
-                else { if (k < K) v.x = __ldg(src); if (k + 1 < K) v.y = __ldg(src + 1); if (k + 2 < K) v.z = __ldg(src + 2); if (k + 3 < K) v.w = __ldg(src + 3); }
+                if (vec && k + 3 < kend) v = __ldg(reinterpret_cast<const float4*>(src));
+                else { if (k < kend) v.x = __ldg(src); if (k + 1 < kend) v.y = __ldg(src + 1); if (k + 2 < kend) v.z = __ldg(src + 2); if (k + 3 < kend) v.w = __ldg(src + 3); }
             }
             pa[it] = v;
         }
@@ -132,17 +137,17 @@ __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restri
             const int kb = idx >> 4, n4 = (idx & 15) * 4;
             const int kk = k0 + kb, n = n0 + n4;
             float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kk < K) {
+            if (kk < kend) {
                 const float* src = E + (int64_t)kk * h + n;
                 if (vec && n + 3 < h) w = __ldg(reinterpret_cast<const float4*>(src));
                 else { if (n < h) w.x = __ldg(src); if (n + 1 < h) w.y = __ldg(src + 1); if (n + 2 < h) w.z = __ldg(src + 2); if (n + 3 < h) w.w = __ldg(src + 3); }
             }
             pb[it] = w;
         }
-        pc = (tid < GK && k0 + tid < K) ? __ldg(c + k0 + tid) : 0.f;
+        pc = (tid < GK && k0 + tid < kend) ? __ldg(c + k0 + tid) : 0.f;
     };
-    fetch(0);
-    for (int k0 = 0; k0 < K; k0 += GK) {
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += GK) {
 #pragma unroll
         for (int it = 0; it < AIT; ++it) {
             const int idx = tid + it * 256;
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restri
         }
         if (tid < GK) sm.vs[tid] = pc;
         __syncthreads();
-        if (k0 + GK < K) fetch(k0 + GK);
+        if (k0 + GK < kend) fetch(k0 + GK);
         gemm_chunk<RT>(sm, g, ty, tx, acc, accq);
         __syncthreads();
     }
@@ -164,12 +169,15 @@ __global__ void __launch_bounds__(256) vbpr_project_kernel(const float* __restri
     for (int e = tid; e < TM * GT; e += 256) {
         const int r = e >> 6, n = e & 63;
         const int mi = m0 + r, col = n0 + n;
-        if (mi < M && col < h) Vp[(int64_t)(rows ? __ldg(rows + mi) : mi) * ldv + h_off + col] = red[r][n];
+        if (mi < M && col < h) {
+            float* dst = Vp + (int64_t)(rows ? __ldg(rows + mi) : mi) * ldv + h_off + col;
+            if (gridDim.z > 1) atomicAdd(dst, red[r][n]); else *dst = red[r][n];
+        }
     }
     if (blockIdx.y == 0 && tid < TM && m0 + tid < M) {
         const int m = rows ? __ldg(rows + m0 + tid) : m0 + tid;
-        bsum[m] = rb[m] + redq[tid];
-        if (rows) row_flag[m] = 0;
+        if (gridDim.z > 1) atomicAdd(bsum + m, redq[tid]); else bsum[m] = rb[m] + redq[tid];
+        if (rows && blockIdx.z == 0) row_flag[m] = 0;
     }
 }
 
@@ -393,11 +401,17 @@ static int vbpr_check(const tkr_vbpr_cfg* cfg, int64_t B) {
 }
 
 // distinct item rows of a batch: first toucher of a row appends it (flag 0 -> 1)
+// (and prepares it for the split-K projection: content columns zeroed, bsum = rb)
 __global__ void __launch_bounds__(256) vbpr_touch_kernel(const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int B,
-                                                         int32_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ n) {
+                                                         int32_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ n,
+                                                         float* __restrict__ V, int ldv, int h, const float* __restrict__ rb, float* __restrict__ bsum) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * B; t += gridDim.x * blockDim.x) {
         const int r = t < B ? ib[t] : jb[t - B];
-        if (atomicExch(flag + r, 1) == 0) list[atomicAdd(n, 1)] = r;
+        if (atomicExch(flag + r, 1) == 0) {
+            list[atomicAdd(n, 1)] = r;
+            for (int c = 0; c < h; ++c) V[(int64_t)r * ldv + h + c] = 0.f;
+            bsum[r] = rb[r];
+        }
     }
 }
 
@@ -411,7 +425,14 @@ static void launch_project(const tkr_vbpr_cfg* cfg, const float* F, const float*
     if (rows != nullptr) rt = rt <= 1 ? 1 : rt <= 2 ? 2 : rt <= 4 ? 4 : 8;
     else if (rt < 8 || rt > 12) rt = 8;
     const unsigned gy = (unsigned)((h + GT - 1) / GT);
-#define TKR_PROJ(RT) vbpr_project_kernel<RT><<<dim3((unsigned)((M + 8 * RT - 1) / (8 * RT)), gy), 256, 0, st>>>(F, E, c, rb, cfg->base.n_items, h, cfg->d_feat, V, cfg->base.d, h, bsum, rows, n_rows_dev, row_flag)
+    // row lists: split K so that tiles x splits cover the chip about twice
+    unsigned gz = 1;
+    if (rows != nullptr) {
+        const int tiles = (M + 8 * rt - 1) / (8 * rt) * (int)gy, kchunks = (cfg->d_feat + GK - 1) / GK;
+        int z = (2 * kNumSMs + tiles - 1) / tiles;
+        gz = (unsigned)(z < 1 ? 1 : z > kchunks ? kchunks : z > 16 ? 16 : z);
+    }
+#define TKR_PROJ(RT) vbpr_project_kernel<RT><<<dim3((unsigned)((M + 8 * RT - 1) / (8 * RT)), gy, gz), 256, 0, st>>>(F, E, c, rb, cfg->base.n_items, h, cfg->d_feat, V, cfg->base.d, h, bsum, rows, n_rows_dev, row_flag)
     switch (rt) {
         case 1: TKR_PROJ(1); break;
         case 2: TKR_PROJ(2); break;
@@ -528,7 +549,7 @@ static int vbpr_run(int phase, int data_parallel, const tkr_vbpr_cfg* cfg, float
                     ut = w.trip; it = w.trip + B; jt = w.trip + 2 * B;
                 }
                 TKR_CUDA(cudaMemsetAsync(w.tcount, 0, 4, st));
-                vbpr_touch_kernel<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(it, jt, (int)B, w.tflag, w.tlist, w.tcount);
+                vbpr_touch_kernel<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(it, jt, (int)B, w.tflag, w.tlist, w.tcount, V, bc->d, h, rb, bsum);
                 TKR_LAUNCH_CHECK();
                 const int max_rows = (int)(2 * B < bc->n_items ? 2 * B : bc->n_items);
                 launch_project(cfg, F, E, c, rb, V, bsum, st, w.tlist, w.tcount, w.tflag, max_rows);
