@@ -401,17 +401,21 @@ static int vbpr_check(const tkr_vbpr_cfg* cfg, int64_t B) {
 }
 
 // distinct item rows of a batch: first toucher of a row appends it (flag 0 -> 1)
-// (and prepares it for the split-K projection: content columns zeroed, bsum = rb)
 __global__ void __launch_bounds__(256) vbpr_touch_kernel(const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int B,
-                                                         int32_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ n,
-                                                         float* __restrict__ V, int ldv, int h, const float* __restrict__ rb, float* __restrict__ bsum) {
+                                                         int32_t* __restrict__ flag, int32_t* __restrict__ list, int32_t* __restrict__ n) {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < 2 * B; t += gridDim.x * blockDim.x) {
         const int r = t < B ? ib[t] : jb[t - B];
-        if (atomicExch(flag + r, 1) == 0) {
-            list[atomicAdd(n, 1)] = r;
-            for (int c = 0; c < h; ++c) V[(int64_t)r * ldv + h + c] = 0.f;
-            bsum[r] = rb[r];
-        }
+        if (atomicExch(flag + r, 1) == 0) list[atomicAdd(n, 1)] = r;
+    }
+}
+// prepares the listed rows for the split-K projection: content columns zeroed, bsum = rb (one warp per row)
+__global__ void __launch_bounds__(256) vbpr_rows_init_kernel(const int32_t* __restrict__ list, const int32_t* __restrict__ n, float* __restrict__ V,
+                                                             int ldv, int h, const float* __restrict__ rb, float* __restrict__ bsum) {
+    const int lane = threadIdx.x & 31, cnt = *n;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < cnt; w += (gridDim.x * blockDim.x) >> 5) {
+        const int r = list[w];
+        for (int c = lane; c < h; c += 32) V[(int64_t)r * ldv + h + c] = 0.f;
+        if (lane == 0) bsum[r] = rb[r];
     }
 }
 
@@ -425,12 +429,12 @@ static void launch_project(const tkr_vbpr_cfg* cfg, const float* F, const float*
     if (rows != nullptr) rt = rt <= 1 ? 1 : rt <= 2 ? 2 : rt <= 4 ? 4 : 8;
     else if (rt < 8 || rt > 12) rt = 8;
     const unsigned gy = (unsigned)((h + GT - 1) / GT);
-    // row lists: split K so that tiles x splits cover the chip about twice
+    // row lists: split K so that tiles x splits cover the chip several times over (each block is a short latency-bound loop)
     unsigned gz = 1;
     if (rows != nullptr) {
         const int tiles = (M + 8 * rt - 1) / (8 * rt) * (int)gy, kchunks = (cfg->d_feat + GK - 1) / GK;
-        int z = (2 * kNumSMs + tiles - 1) / tiles;
-        gz = (unsigned)(z < 1 ? 1 : z > kchunks ? kchunks : z > 16 ? 16 : z);
+        int z = (8 * kNumSMs + tiles - 1) / tiles;
+        gz = (unsigned)(z < 1 ? 1 : z > kchunks ? kchunks : z > 32 ? 32 : z);
     }
 #define TKR_PROJ(RT) vbpr_project_kernel<RT><<<dim3((unsigned)((M + 8 * RT - 1) / (8 * RT)), gy, gz), 256, 0, st>>>(F, E, c, rb, cfg->base.n_items, h, cfg->d_feat, V, cfg->base.d, h, bsum, rows, n_rows_dev, row_flag)
     switch (rt) {
@@ -549,7 +553,9 @@ static int vbpr_run(int phase, int data_parallel, const tkr_vbpr_cfg* cfg, float
                     ut = w.trip; it = w.trip + B; jt = w.trip + 2 * B;
                 }
                 TKR_CUDA(cudaMemsetAsync(w.tcount, 0, 4, st));
-                vbpr_touch_kernel<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(it, jt, (int)B, w.tflag, w.tlist, w.tcount, V, bc->d, h, rb, bsum);
+                vbpr_touch_kernel<<<(unsigned)((2 * B + 255) / 256), 256, 0, st>>>(it, jt, (int)B, w.tflag, w.tlist, w.tcount);
+                TKR_LAUNCH_CHECK();
+                vbpr_rows_init_kernel<<<(unsigned)((2 * B + 7) / 8), 256, 0, st>>>(w.tlist, w.tcount, V, bc->d, h, rb, bsum);
                 TKR_LAUNCH_CHECK();
                 const int max_rows = (int)(2 * B < bc->n_items ? 2 * B : bc->n_items);
                 launch_project(cfg, F, E, c, rb, V, bsum, st, w.tlist, w.tcount, w.tflag, max_rows);
