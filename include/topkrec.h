@@ -406,6 +406,28 @@ int tkr_topk_exchange_merge(int64_t nu, int64_t nu_cap, int32_t k, const tkr_pee
                             int32_t* out_idx, float* out_score, void* stream);
 int tkr_topk_exchange_status(int64_t nu_cap, int32_t k, const tkr_peers* peers, void* stream);
 
+/* Item-sharded scoring as a RING: the sweep of a user batch over the whole item table is cut into one SEGMENT per GPU, and
+ * the running state of the sweep -- every row's threshold, candidate buffer and count (tkr_score_topk_tc_state_bytes) --
+ * travels from GPU to GPU; GPU g works on segment g of batch t - g while GPU g+1 works on batch t - g - 1.  Unlike independent
+ * per-shard top-k lists (tkr_topk_exchange_*), the per-row selection work -- which hardly depends on the sweep length -- is then
+ * paid once per batch instead of once per shard.  `first` = the sweep starts here (seeding), `last` = it ends here: only then
+ * are the lists sorted out, re-scored exactly against V_full (the keys carry global columns) with the error-bound certificate,
+ * and the uncertified rows re-done by the exact engine.  Results are bit-identical to tkr_score_topk on the whole table.
+ * The caller moves the state (a plain device-to-device copy into the next GPU's mapped buffer) and orders the segments with
+ * tkr_peer_signal_to / tkr_peer_wait_from (flag block of tkr_peer_flag_bytes() at a caller-chosen offset of the exchange
+ * buffer; slots 4..7 are free for callers); topkrec.dist.RingScorer does both. */
+size_t tkr_score_topk_tc_state_bytes(int64_t nu);
+size_t tkr_score_topk_tc_segment_workspace_bytes(int64_t nu, int64_t ni_shard, int64_t ni_full, int32_t d, int32_t k, int32_t has_bias);
+int tkr_score_topk_tc_segment(const float* U, int64_t nu, const float* V_shard, int64_t ni_shard, int32_t d, const float* bias_shard,
+                              const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset, void* state,
+                              int32_t first, int32_t last, const float* V_full, int64_t ni_full, const float* bias_full,
+                              int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
+                              int32_t items_prepared, void* stream);
+size_t tkr_peer_flag_bytes(void);
+int tkr_peer_signal_to(const tkr_peers* peers, size_t flag_off, int32_t slot, int32_t target, uint64_t epoch, void* stream);
+int tkr_peer_wait_from(const tkr_peers* peers, size_t flag_off, int32_t slot, int32_t source, uint64_t epoch, void* stream);
+int tkr_peer_status(const tkr_peers* peers, size_t flag_off, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -324,3 +324,30 @@ def test_tc_items_prepared_reuses_bf16_table():
         gi, gs = topkrec.score_topk(t(U[rows].copy()), Vd, 30, bd, t(ptr.copy()), idx_d, engine="tc", ws=ws, items_prepared=prepared)
         ri, rs = topk_ref.score_topk(U[rows], V, 30, b, ptr - ptr[0], i[ptr[0]:ptr[-1]])
         assert np.array_equal(gi.cpu().numpy(), ri) and np.array_equal(gs.cpu().numpy().view(np.uint32), rs.view(np.uint32))
+
+
+@pytest.mark.parametrize("nu,ni,d,bias,rated,cuts", [(18944, 65536, 128, False, 0, (0, 20000, 41000, 65536)), (19000, 40000, 64, True, 40, (0, 9000, 40000)),
+                                                    (18944, 30000, 200, False, 16, (0, 7000, 14000, 22000, 30000))])
+def test_score_topk_sweep_in_segments_equals_whole_sweep(nu, ni, d, bias, rated, cuts):
+    """tkr_score_topk_tc_segment: one sweep cut into segments over item shards, the rows' thresholds / candidate buffers carried
+    in the state from segment to segment (what travels from GPU to GPU in the ring) -- lists and score bits equal the oracle's
+    and the single-call engine's on the whole table"""
+    U, V, b, indptr, idx = _case(nu, ni, d, 30, seed=nu + ni + d, bias=bias, rated=rated)
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
+    Ud, Vd, bd, rp, ri = t(U), t(V), t(b), t(indptr), t(idx)
+    state = torch.zeros(topkrec.lib().tkr_score_topk_tc_state_bytes(nu), dtype=torch.uint8, device="cuda")
+    nfb = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = None
+    for s in range(len(cuts) - 1):
+        lo, hi = cuts[s], cuts[s + 1]
+        out = topkrec.score_topk_segment(Ud, Vd[lo:hi].contiguous(), 30, lo, state, s == 0, s == len(cuts) - 2, V_full=Vd,
+                                         bias_shard=None if bd is None else bd[lo:hi].contiguous(), bias_full=bd, rated_indptr=rp, rated_idx=ri, n_fallback=nfb)
+    gi, gs = out[0].cpu().numpy(), out[1].cpu().numpy()
+    wi, wsc = topkrec.score_topk(Ud, Vd, 30, bd, rp, ri, engine="tc")
+    assert np.array_equal(gi, wi.cpu().numpy()) and np.array_equal(gs.view(np.uint32), wsc.cpu().numpy().view(np.uint32))
+    rows = np.random.default_rng(1).choice(nu, 300, replace=False)
+    sub_ptr = None if indptr is None else np.concatenate([[0], np.cumsum(np.diff(indptr)[rows])]).astype(np.int64)
+    sub_idx = None if indptr is None else np.concatenate([idx[indptr[r]:indptr[r + 1]] for r in rows] + [np.zeros(0, np.int32)]).astype(np.int32)
+    oi, osc = topk_ref.score_topk(U[rows], V, 30, b, sub_ptr, sub_idx)
+    assert np.array_equal(gi[rows], oi) and np.array_equal(gs[rows].view(np.uint32), osc.view(np.uint32))
+    assert int(nfb.item()) <= nu // 100

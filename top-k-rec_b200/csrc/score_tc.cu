@@ -220,6 +220,12 @@ struct FilterParams {
     int seed_rank;           // 4 or 3: the row's seed threshold is the smallest of the column quarters' seed_rank-th largest chunk maxima
     int cap_trigger;         // a row's candidate buffer is compacted to its best KPRIME once it would exceed this many keys (<= CAP)
     float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
+    // A sweep may be one SEGMENT of a longer one that continues on another GPU (item-sharded ring, tkr_score_topk_tc_segment):
+    // resume = the rows' thresholds / candidate counts come from st_tau / st_cnt (candidates already in `cand`), no seeding;
+    // suspend = they are written back there at the end instead of sorting the lists out.
+    int resume, suspend;
+    float* st_tau;
+    int32_t* st_cnt;
     const int64_t* rated_indptr;
     const int32_t* rated_idx;
     uint64_t* cand;          // [n_splits][nu][CAP] scratch keys
@@ -447,8 +453,8 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     }
     for (int t = threadIdx.x; t < FM; t += F_THREADS) {
         const bool ok = row0 + t < p.nu;   // padded rows never collect
-        tau_sh[t] = ok ? -INFINITY : INFINITY;
-        if (row0 + t < p.nu && T0 == 0) p.out_tau0[(int64_t)split * p.nu + row0 + t] = -INFINITY;
+        tau_sh[t] = ok ? (p.resume ? p.st_tau[row0 + t] : -INFINITY) : INFINITY;
+        if (row0 + t < p.nu && T0 == 0 && !p.resume) p.out_tau0[(int64_t)split * p.nu + row0 + t] = -INFINITY;
         cnt_sh[t] = 0;
         rlo_sh[t] = (ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + t) : 0;
         rhi_sh[t] = (ok && p.rated_indptr) ? __ldg(p.rated_indptr + row0 + t + 1) : 0;
@@ -626,8 +632,9 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
         uint64_t* bufq = p.cand + ((size_t)split * p.nu + (size_t)row0 + (size_t)q * 32) * CAP;   // row r of the quarter at bufq + r*CAP
         uint64_t skey[4];
         int tail = 0;
-        int cnt_reg = 0;                                                  // lane r: candidates buffered for row r of the quarter
-        float tau_reg = row0 + q * 32 + lane < p.nu ? -INFINITY : INFINITY;   // lane r: its threshold (mirrored in tau_sh for the epilogue)
+        const bool my_row_ok = row0 + q * 32 + lane < p.nu;
+        int cnt_reg = (p.resume && my_row_ok) ? p.st_cnt[row0 + q * 32 + lane] : 0;   // lane r: candidates buffered for row r of the quarter
+        float tau_reg = my_row_ok ? (p.resume ? p.st_tau[row0 + q * 32 + lane] : -INFINITY) : INFINITY;   // lane r: its threshold (mirrored in tau_sh for the epilogue)
         bool tau_seeded = T0 == 0;
         long long dbg_idle = 0, dbg_busy = 0, dbg_n = 0, dbg_cmp = 0;
         for (;;) {
@@ -704,6 +711,13 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             if (lane == 0) sh_st_volatile_u32(tail_a, (uint32_t)tail);
             dbg_busy += tick<DBG>() - i1; dbg_n += n;
         }
+        if (p.suspend) {   // the sweep continues elsewhere: hand the rows' state back (their candidates are in `cand` already)
+            if (my_row_ok) {
+                if (!tau_seeded) tau_reg = fmaxf(tau_reg, __int_as_float(sh_ld_volatile(tau_a + 4u * (uint32_t)lane)));   // (no block ever arrived: seeds not picked up yet)
+                p.st_cnt[row0 + q * 32 + lane] = cnt_reg;
+                p.st_tau[row0 + q * 32 + lane] = tau_reg;
+            }
+        } else
         // final: sorted best-KPRIME list of every row of this quarter
         for (int r = 0; r < 32; ++r) {
             const int row = q * 32 + r;
@@ -964,18 +978,37 @@ extern "C" size_t tkr_score_topk_tc_workspace_bytes(int64_t nu, int64_t ni, int3
     return P.total + 1024;
 }
 
-extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
-                                 const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
-                                 int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
-                                 int32_t items_prepared, void* stream) {
-    TKR_CHECK_ARG(U && V && out_idx && out_score, "U, V and the outputs must not be NULL");
-    TKR_CHECK_ARG(nu >= 0 && ni >= 1 && d >= 1 && k >= 1, "bad nu/ni/d/k");
-    TKR_CHECK_ARG(rated_indptr == nullptr || rated_idx != nullptr, "rated_indptr without rated_idx");
-    TKR_CHECK_ARG(ni + col_offset < ((int64_t)1 << 31), "global column index exceeds int32");
-    if (nu == 0) return TKR_OK;
+namespace tkr {
+// state of a sweep that travels from GPU to GPU (tkr_score_topk_tc_segment): [cand nu*CAP u64 | tau nu f32 | cnt nu i32 | tau0 nu f32 | scal 16 u32]
+struct SegState { uint64_t* cand; float* tau; int32_t* cnt; float* tau0; unsigned int* scal; size_t total; };
+static SegState seg_state(void* state, int64_t nu) {
+    SegState S;
+    char* p = (char*)state;
+    size_t o = 0;
+    S.cand = (uint64_t*)(p + o); o += align_up((size_t)nu * CAP * 8, 256);
+    S.tau = (float*)(p + o); o += align_up((size_t)nu * 4, 256);
+    S.cnt = (int32_t*)(p + o); o += align_up((size_t)nu * 4, 256);
+    S.tau0 = (float*)(p + o); o += align_up((size_t)nu * 4, 256);
+    S.scal = (unsigned int*)(p + o); o += 256;
+    S.total = o;
+    return S;
+}
+// running maxima of the item norms / |bias| over the segments seen so far (non-negative floats: unsigned compare)
+__global__ void seg_scal_kernel(unsigned int* __restrict__ st, const unsigned int* __restrict__ mine, int first) {
+    if (threadIdx.x < 2) st[threadIdx.x] = first ? mine[threadIdx.x] : max(st[threadIdx.x], mine[threadIdx.x]);
+}
+
+// seg == nullptr: the whole pipeline on one shard (tkr_score_topk_tc).  Otherwise one segment of a sweep: first / last say
+// whether the sweep starts / ends here; only the last segment refines (against V_full, whose rows the keys' global columns
+// index) and re-does the uncertified rows.
+static int tc_run(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
+                  const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
+                  int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
+                  int32_t items_prepared, void* stream, const SegState* seg, int first, int last,
+                  const float* V_full, int64_t ni_full, const float* bias_full) {
     TcPlan P;
-    if (!tc_plan(nu, ni, d, k, bias != nullptr, &P))   // shape outside the tensor-core filter: the exact engine does it all
-        return tkr_score_topk(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, out_idx, out_score, ws, ws_bytes, stream);
+    if (!tc_plan(nu, ni, d, k, bias != nullptr, &P)) { set_error("score_topk_tc: shape outside the tensor-core filter"); return TKR_ERR_UNSUPPORTED; }
+    if (seg != nullptr && P.ns != 1) { set_error("score_topk_tc_segment needs user batches that fill the chip without item splits (>= %d rows)", kNumSMs * FM / 2); return TKR_ERR_UNSUPPORTED; }
     if (ws == nullptr || ws_bytes < P.total + 1024) { set_error("score_topk_tc workspace too small: have %zu, need %zu", ws_bytes, P.total + 1024); return TKR_ERR_WORKSPACE; }
     cudaStream_t st = (cudaStream_t)stream;
     char* w = (char*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
@@ -983,10 +1016,11 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     __nv_bfloat16* Vbf = (__nv_bfloat16*)(w + P.o_vbf);
     float* unorm = (float*)(w + P.o_unorm);
     unsigned int* scal = (unsigned int*)(w + P.o_scal);
-    uint64_t* cand = (uint64_t*)(w + P.o_cand);
+    uint64_t* cand = seg ? seg->cand : (uint64_t*)(w + P.o_cand);
     int32_t* sidx = (int32_t*)(w + P.o_sidx); float* sscore = (float*)(w + P.o_sscore);
     int32_t* midx = (int32_t*)(w + P.o_midx); float* mscore = (float*)(w + P.o_mscore);
     int32_t* fail = (int32_t*)(w + P.o_fail);
+    const bool do_tail = seg == nullptr || last;
 
     const int has_bias = bias != nullptr;
     // scal: [0] max item norm, [1] max |bias| (both belong to the prepared item table), [2] uncertified rows
@@ -998,16 +1032,20 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
         convert_rows_kernel<<<(unsigned)((ni + 7) / 8), 256, 0, st>>>(V, ni, d, P.dpad, bias, 0, has_bias, Vbf, nullptr, scal + 0, scal + 1);
         TKR_LAUNCH_CHECK();
     }
+    if (seg != nullptr) { seg_scal_kernel<<<1, 32, 0, st>>>(seg->scal, scal, first); TKR_LAUNCH_CHECK(); }
 
     CUtensorMap tmU, tmV;
     if (int rc = make_tmap(&tmU, Ubf, nu, P.dpad, FM)) return rc;
     if (int rc = make_tmap(&tmV, Vbf, ni, P.dpad, B_HALF)) return rc;
-    FilterParams fp;
+    FilterParams fp = {};
     fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.cps = P.cps; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
     fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
-    fp.seed_tiles = P.seed_tiles; fp.out_tau0 = (float*)(w + P.o_tau0);
+    fp.seed_tiles = (seg != nullptr && !first) ? 0 : P.seed_tiles;
+    fp.out_tau0 = seg ? seg->tau0 : (float*)(w + P.o_tau0);
+    fp.resume = (seg != nullptr && !first) ? 1 : 0; fp.suspend = (seg != nullptr && !last) ? 1 : 0;
+    fp.st_tau = seg ? seg->tau : nullptr; fp.st_cnt = seg ? seg->cnt : nullptr;
     // (tuning aids; measured on item shards of 2^17 .. 2^20 items, profiles/r02_filter_roles.txt: seeding on the 3rd largest
     // chunk maximum sends a handful of rows per batch to the exact fallback, which costs more than the hand-offs it saves,
     // and compacting at 96 keys is a wash -- the defaults stay 4 / CAP)
@@ -1027,28 +1065,84 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
     else TKR_FILTER_LAUNCH(1);
     TKR_LAUNCH_CHECK();
     if (fp.dbg != nullptr && g_filter_mode >= 2) return TKR_OK;   // ceiling probes: no lists were produced
+    if (!do_tail) return TKR_OK;                                 // the sweep continues on the next shard
     if (P.ns > 1)
         if (int rc = tkr_topk_merge(sidx, sscore, P.ns, nu, KPRIME, midx, mscore, stream)) return rc;
 
+    // exact re-scoring reads the table the keys' columns index: this shard's (col_offset), or -- at the end of a sweep
+    // over several shards -- the whole table
+    const float* Vr = seg ? V_full : V;
+    const float* br = seg ? bias_full : bias;
+    const int64_t cor = seg ? 0 : col_offset, nir = seg ? ni_full : ni;
+    const unsigned int* vmax = seg ? seg->scal + 0 : scal + 0;
+    const unsigned int* bmax = seg ? seg->scal + 1 : scal + 1;
     // |bf16 tensor-core score - exact fma-chain score| <= coef * |u| * |v|: two roundings to 8-bit significands
     // (2^-8 + 2^-18 on every product, Cauchy-Schwarz over the row) + fp32 accumulation slack on both sides.
     const float coef = 0.00390625f * 1.01f + (float)(d + 8) * 9.5367431640625e-7f;
     {
-        const int vec = (d % 4 == 0 && ((uintptr_t)V % 16) == 0 && ((uintptr_t)U % 16) == 0) ? 1 : 0;
+        const int vec = (d % 4 == 0 && ((uintptr_t)Vr % 16) == 0 && ((uintptr_t)U % 16) == 0) ? 1 : 0;
         const int rr = d <= 128 ? 16 : 8;                                // staged candidates per round
         const size_t rsmem = (size_t)8 * (d + 4) * 4 + (size_t)8 * KPRIME * 8 + (vec ? (size_t)8 * rr * (d + 4) * 4 : 0);
 #define TKR_REFINE(RR)                                                                                                            \
         do {                                                                                                                       \
             TKR_CUDA(cudaFuncSetAttribute(score_refine_kernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsmem));       \
-            score_refine_kernel<RR><<<(unsigned)((nu + 7) / 8), 256, rsmem, st>>>(U, V, nu, d, bias, col_offset, midx, mscore, unorm, scal + 0, scal + 1, \
-                (const float*)(w + P.o_tau0), P.ns, coef, k, vec, out_idx, out_score, fail, (int32_t*)(scal + 2));                 \
+            score_refine_kernel<RR><<<(unsigned)((nu + 7) / 8), 256, rsmem, st>>>(U, Vr, nu, d, br, cor, midx, mscore, unorm, vmax, bmax, \
+                fp.out_tau0, P.ns, coef, k, vec, out_idx, out_score, fail, (int32_t*)(scal + 2));                                  \
         } while (0)
         if (rr == 16) TKR_REFINE(16); else TKR_REFINE(8);
 #undef TKR_REFINE
     }
     TKR_LAUNCH_CHECK();
     // uncertified rows -> exact engine, driven by the device-side row list (no host round trip)
-    if (int rc = launch_exact_rows(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, fail, (const int32_t*)(scal + 2), out_idx, out_score, w + P.o_fb, P.fb_bytes, st)) return rc;
+    const size_t fb_need = exact_rows_workspace_bytes(nir, k);
+    char* fbp = w + P.o_fb;
+    size_t fbb = P.fb_bytes;
+    if (seg != nullptr) {   // the fallback scratch of a segment workspace follows the shard-sized plan (it must hold the whole table's splits)
+        fbp = w + align_up(P.total, 1024);
+        fbb = (size_t)((char*)ws + ws_bytes - fbp);
+    }
+    if (fb_need > fbb) { set_error("score_topk_tc: workspace was sized for a smaller item table (fallback needs %zu bytes, has %zu)", fb_need, fbb); return TKR_ERR_WORKSPACE; }
+    if (int rc = launch_exact_rows(U, nu, Vr, nir, d, br, rated_indptr, rated_idx, k, cor, fail, (const int32_t*)(scal + 2), out_idx, out_score, fbp, fbb, st)) return rc;
     if (n_fallback_rows != nullptr) TKR_CUDA(cudaMemcpyAsync(n_fallback_rows, scal + 2, 4, cudaMemcpyDeviceToDevice, st));
     return TKR_OK;
+}
+}  // namespace tkr
+
+extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int64_t ni, int32_t d, const float* bias,
+                                 const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset,
+                                 int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
+                                 int32_t items_prepared, void* stream) {
+    TKR_CHECK_ARG(U && V && out_idx && out_score, "U, V and the outputs must not be NULL");
+    TKR_CHECK_ARG(nu >= 0 && ni >= 1 && d >= 1 && k >= 1, "bad nu/ni/d/k");
+    TKR_CHECK_ARG(rated_indptr == nullptr || rated_idx != nullptr, "rated_indptr without rated_idx");
+    TKR_CHECK_ARG(ni + col_offset < ((int64_t)1 << 31), "global column index exceeds int32");
+    if (nu == 0) return TKR_OK;
+    TcPlan P;
+    if (!tc_plan(nu, ni, d, k, bias != nullptr, &P))   // shape outside the tensor-core filter: the exact engine does it all
+        return tkr_score_topk(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, out_idx, out_score, ws, ws_bytes, stream);
+    return tc_run(U, nu, V, ni, d, bias, rated_indptr, rated_idx, k, col_offset, out_idx, out_score, ws, ws_bytes, n_fallback_rows, items_prepared, stream,
+                  nullptr, 1, 1, nullptr, 0, nullptr);
+}
+
+// One SEGMENT of a tensor-core sweep over an item table sharded across GPUs (see include/topkrec.h).
+extern "C" size_t tkr_score_topk_tc_state_bytes(int64_t nu) { return nu > 0 ? seg_state(nullptr, nu).total : 0; }
+extern "C" size_t tkr_score_topk_tc_segment_workspace_bytes(int64_t nu, int64_t ni_shard, int64_t ni_full, int32_t d, int32_t k, int32_t has_bias) {
+    const size_t a = tkr_score_topk_tc_workspace_bytes(nu, ni_shard, d, k, has_bias);
+    return a + exact_rows_workspace_bytes(ni_full, k) + 4096;
+}
+extern "C" int tkr_score_topk_tc_segment(const float* U, int64_t nu, const float* V_shard, int64_t ni_shard, int32_t d, const float* bias_shard,
+                                         const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset, void* state,
+                                         int32_t first, int32_t last, const float* V_full, int64_t ni_full, const float* bias_full,
+                                         int32_t* out_idx, float* out_score, void* ws, size_t ws_bytes, int32_t* n_fallback_rows,
+                                         int32_t items_prepared, void* stream) {
+    TKR_CHECK_ARG(U && V_shard && state, "U, V_shard and state must not be NULL");
+    TKR_CHECK_ARG(nu >= 1 && ni_shard >= 1 && d >= 1 && k >= 1, "bad nu/ni/d/k");
+    TKR_CHECK_ARG(rated_indptr == nullptr || rated_idx != nullptr, "rated_indptr without rated_idx");
+    TKR_CHECK_ARG(!last || (V_full && out_idx && out_score && ni_full >= ni_shard), "the last segment needs V_full and the outputs");
+    TKR_CHECK_ARG((bias_shard == nullptr) == (!last || bias_full == nullptr) || !last, "bias_shard and bias_full must be given together");
+    TKR_CHECK_ARG(ni_shard + col_offset < ((int64_t)1 << 31), "global column index exceeds int32");
+    TKR_CHECK_ARG(((uintptr_t)state % 256) == 0, "state must be 256-byte aligned");
+    const SegState S = seg_state(state, nu);
+    return tc_run(U, nu, V_shard, ni_shard, d, bias_shard, rated_indptr, rated_idx, k, col_offset, out_idx, out_score, ws, ws_bytes, n_fallback_rows,
+                  items_prepared, stream, &S, first, last, V_full, ni_full, bias_full);
 }

@@ -46,6 +46,20 @@ __global__ void __launch_bounds__(256) topk_push_kernel(PeerView pv, const int32
     }
 }
 
+__global__ void peer_signal_one_kernel(PeerView pv, size_t flag_off, int slot, int target, uint32_t epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) { __threadfence_system(); st_release_sys(peer_flag(pv, target, flag_off, slot, pv.rank), epoch); }
+}
+__global__ void peer_wait_one_kernel(PeerView pv, size_t flag_off, int slot, int source, uint32_t epoch) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const uint64_t t0 = global_timer_ns();
+        const uint32_t* f = peer_flag(pv, pv.rank, flag_off, slot, source);
+        while ((int32_t)(ld_acquire_sys(f) - epoch) < 0) {
+            if (global_timer_ns() - t0 > kPeerTimeoutNs) { atomicExch(peer_error_word(pv, flag_off), 1u + (uint32_t)slot); break; }
+            __nanosleep(64);
+        }
+    }
+}
+
 int merge_lists_public(const int32_t* idx, const float* score, int n_lists, int64_t nu, int k, int32_t* out_idx, float* out_score, void* stream);
 
 }  // namespace tkr
@@ -103,5 +117,33 @@ extern "C" int tkr_topk_exchange_status(int64_t nu_cap, int32_t k, const tkr_pee
     TKR_CUDA(cudaMemcpyAsync(&err, pv.base[pv.rank] + L.flags + (size_t)kPeerSlots * TKR_MAX_PEERS * 4, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     TKR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     if (err != 0) { set_error("top-k exchange: a rank did not reach barrier %u within 20 s", err - 1); return TKR_ERR_CUDA; }
+    return TKR_OK;
+}
+
+// ---- point-to-point flags on a caller-laid-out exchange buffer (the ring of tkr_score_topk_tc_segment uses them) ----
+extern "C" size_t tkr_peer_flag_bytes(void) { return align_up(kPeerFlagBytes, 256); }
+extern "C" int tkr_peer_signal_to(const tkr_peers* peers, size_t flag_off, int32_t slot, int32_t target, uint64_t epoch, void* stream) {
+    PeerView pv;
+    if (int rc = peer_view_from(peers, &pv)) return rc;
+    TKR_CHECK_ARG(slot >= 0 && slot < kPeerSlots && target >= 0 && target < pv.world, "bad slot / target");
+    peer_signal_one_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, flag_off, slot, target, (uint32_t)epoch);
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
+}
+extern "C" int tkr_peer_wait_from(const tkr_peers* peers, size_t flag_off, int32_t slot, int32_t source, uint64_t epoch, void* stream) {
+    PeerView pv;
+    if (int rc = peer_view_from(peers, &pv)) return rc;
+    TKR_CHECK_ARG(slot >= 0 && slot < kPeerSlots && source >= 0 && source < pv.world, "bad slot / source");
+    peer_wait_one_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pv, flag_off, slot, source, (uint32_t)epoch);
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
+}
+extern "C" int tkr_peer_status(const tkr_peers* peers, size_t flag_off, void* stream) {
+    PeerView pv;
+    if (int rc = peer_view_from(peers, &pv)) return rc;
+    uint32_t err = 0;
+    TKR_CUDA(cudaMemcpyAsync(&err, pv.base[pv.rank] + flag_off + (size_t)kPeerSlots * TKR_MAX_PEERS * 4, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    TKR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    if (err != 0) { set_error("peer flag %u was not raised within 20 s", err - 1); return TKR_ERR_CUDA; }
     return TKR_OK;
 }

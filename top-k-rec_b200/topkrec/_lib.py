@@ -88,6 +88,13 @@ def lib():
     L.tkr_score_topk_host_device_bytes.argtypes = [i64, i64, i32, i32, i64]
     L.tkr_score_topk_host.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, vp, vp, vp, sz, vp]
     L.tkr_topk_merge.argtypes = [vp, vp, i32, i64, i32, vp, vp, vp]
+    L.tkr_score_topk_tc_state_bytes.restype = sz; L.tkr_score_topk_tc_state_bytes.argtypes = [i64]
+    L.tkr_score_topk_tc_segment_workspace_bytes.restype = sz; L.tkr_score_topk_tc_segment_workspace_bytes.argtypes = [i64, i64, i64, i32, i32, i32]
+    L.tkr_score_topk_tc_segment.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, i32, i64, vp, i32, i32, vp, i64, vp, vp, vp, vp, sz, vp, i32, vp]
+    L.tkr_peer_flag_bytes.restype = sz; L.tkr_peer_flag_bytes.argtypes = []
+    L.tkr_peer_signal_to.argtypes = [vp, sz, i32, i32, u64, vp]
+    L.tkr_peer_wait_from.argtypes = [vp, sz, i32, i32, u64, vp]
+    L.tkr_peer_status.argtypes = [vp, sz, vp]
     L.tkr_topk_exchange_bytes.restype = sz; L.tkr_topk_exchange_bytes.argtypes = [i64, i32, i32]
     L.tkr_topk_exchange_push.argtypes = [vp, vp, i64, i64, i32, vp, u64, vp]
     L.tkr_topk_exchange_merge.argtypes = [i64, i64, i32, vp, u64, vp, vp, vp]
@@ -102,7 +109,7 @@ def lib():
     L.tkr_als_gram_workspace_bytes.restype = sz; L.tkr_als_gram_workspace_bytes.argtypes = [i32]
     L.tkr_als_gram.argtypes = [vp, i32, vp, i64, C.c_float, C.c_float, vp, vp, sz, vp]
     L.tkr_als_solve_rows.argtypes = [C.POINTER(tkr_als_cfg), C.POINTER(tkr_als_plan), vp, vp, vp, vp, vp, vp, vp, sz, vp]
-    for name in ("tkr_bpr_hogwild", "tkr_vbpr_grad", "tkr_vbpr_apply", "tkr_vbpr_workspace_layout", "tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
+    for name in ("tkr_score_topk_tc_segment", "tkr_peer_signal_to", "tkr_peer_wait_from", "tkr_peer_status", "tkr_bpr_hogwild", "tkr_vbpr_grad", "tkr_vbpr_apply", "tkr_vbpr_workspace_layout", "tkr_topk_exchange_push", "tkr_topk_exchange_merge", "tkr_topk_exchange_status", "tkr_bpr_dp_layout", "tkr_bpr_dp_step", "tkr_bpr_dp_status", "tkr_als_gram", "tkr_als_solve_rows", "tkr_bpr_workspace_init", "tkr_bpr_workspace_layout", "tkr_bpr_workspace_set_hot_items", "tkr_bpr_grad", "tkr_bpr_apply", "tkr_bpr_step", "tkr_bpr_step_host", "tkr_bpr_sample", "tkr_vbpr_workspace_init", "tkr_vbpr_project", "tkr_vbpr_step", "tkr_score_topk",
                  "tkr_score_topk_tc", "tkr_score_topk_host", "tkr_topk_merge", "tkr_eval_hits", "tkr_dat_shape", "tkr_dat_read", "tkr_dat_write",
                  "tkr_ratings_parse"):
         getattr(L, name).restype = C.c_int
@@ -435,6 +442,32 @@ def score_topk(U, V, k, bias=None, rated_indptr=None, rated_idx=None, col_offset
             _check(lib().tkr_score_topk_tc(*args, _dev(n_fallback, torch.int32, "n_fallback"), int(bool(items_prepared)), _stream()))
         else:
             _check(lib().tkr_score_topk(*args, _stream()))
+    return out
+
+
+def score_topk_segment(U, V_shard, k, col_offset, state, first, last, V_full=None, bias_shard=None, bias_full=None, rated_indptr=None,
+                       rated_idx=None, out=None, ws=None, n_fallback=None, items_prepared=False):
+    """One segment of a tensor-core sweep over an item table cut into shards (tkr_score_topk_tc_segment): ``state`` (uint8 CUDA
+    tensor of tkr_score_topk_tc_state_bytes(nu)) carries thresholds and candidates from segment to segment; the last segment
+    returns (idx, score) for the whole table, bit-identical to ``score_topk`` on it."""
+    f32 = torch.float32
+    _need_cuda(U, V_shard, state)
+    nu, d = U.shape
+    ni = V_shard.shape[0]
+    ni_full = V_full.shape[0] if V_full is not None else 0
+    if last and out is None:
+        out = (torch.empty((nu, k), dtype=torch.int32, device=U.device), torch.empty((nu, k), dtype=f32, device=U.device))
+    need = lib().tkr_score_topk_tc_segment_workspace_bytes(nu, ni, max(ni_full, ni), d, k, int(bias_shard is not None))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=U.device)
+    if rated_indptr is not None and (rated_idx is None or rated_idx.numel() == 0):
+        rated_idx = torch.zeros(1, dtype=torch.int32, device=U.device)
+    with torch.cuda.device(U.device):
+        _check(lib().tkr_score_topk_tc_segment(_dev(U, f32, "U"), nu, _dev(V_shard, f32, "V_shard"), ni, d, _dev(bias_shard, f32, "bias_shard"),
+                                               _dev(rated_indptr, torch.int64, "rated_indptr"), _dev(rated_idx, torch.int32, "rated_idx"), int(k),
+                                               int(col_offset), state.data_ptr(), int(bool(first)), int(bool(last)), _dev(V_full, f32, "V_full"), ni_full,
+                                               _dev(bias_full, f32, "bias_full"), out[0].data_ptr() if out else None, out[1].data_ptr() if out else None,
+                                               ws.data_ptr(), ws.numel(), _dev(n_fallback, torch.int32, "n_fallback"), int(bool(items_prepared)), _stream()))
     return out
 
 
