@@ -1,0 +1,70 @@
+#!/usr/bin/env python3
+"""Item-sharded score + top-30 as a ring of sweep segments on N GPUs (torchrun): topkrec.dist.RingScorer against the unsharded
+engine (bit-identical lists and score bits required on the last rank, with and without a rated mask), then device-timed
+pipelined steps on the fixed 18 944-user x 1 M-item batch (d=128, k=30).
+usage: python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 profiles/ring_ngpu.py [users] [steps]"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [os.path.join(ROOT, "top-k-rec_b200"), ROOT]
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import topkrec  # noqa: E402
+from topkrec import dist as tdist  # noqa: E402
+
+
+def main():
+    nb = int(sys.argv[1]) if len(sys.argv) > 1 else 18944
+    K = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+    NI, D, k = 1 << 20, 128, 30
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    g = torch.Generator(device=dev); g.manual_seed(4)
+    Vfull = torch.randn(NI, D, device=dev, generator=g) * 0.1
+    bounds = tdist.ring_bounds(NI, world)
+    beg, end = bounds[rank]
+    V = Vfull[beg:end].contiguous()
+    last = rank == world - 1
+    if not last:
+        del Vfull
+        Vfull = None
+    gu = torch.Generator(device=dev); gu.manual_seed(3)
+    Ub = [torch.randn(nb, D, device=dev, generator=gu) * 0.1 for _ in range(4)]
+    ri = torch.sort(torch.randint(0, NI, (nb, 64), device=dev, generator=gu, dtype=torch.int32), dim=1).values.reshape(-1).contiguous()
+    rp = torch.arange(0, (nb + 1) * 64, 64, device=dev, dtype=torch.int64)
+    out = {"world": world, "users_per_step": nb, "items": NI, "d": D, "k": k, "shards": bounds}
+    ring = tdist.RingScorer(V, D, k, nb, beg, V_full=Vfull, device=dev)
+    ok = True
+    for t, masked in ((0, False), (1, True), (2, False), (3, True), (0, True)):
+        res = ring.submit(Ub[t], rp if masked else None, ri if masked else None)
+        ring.wait()
+        if last:
+            wi, wsc = topkrec.score_topk(Ub[t], Vfull, k, None, rp if masked else None, ri if masked else None, engine="tc")
+            ok = ok and bool(torch.equal(res[0], wi)) and bool(torch.equal(res[1].view(torch.int32), wsc.view(torch.int32)))
+    flag = torch.tensor([int(ok)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ring_equals_unsharded_bitwise"] = bool(flag.item())
+    for t in range(8):
+        ring.submit(Ub[t % 4])
+    ring.wait(); dist.barrier(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        ring.submit(Ub[t % 4])
+    ring.wait()
+    e1.record(); dist.barrier(); torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    out["ring"] = {"ms_per_step": float(ms.item()), "users_per_s": nb / (float(ms.item()) / 1e3), "steps": K,
+                   "fallback_rows_last_step": int(ring.nfb.item()) if last else None}
+    if last:
+        print(json.dumps(out))
+    ring.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
