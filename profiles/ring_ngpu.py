@@ -25,41 +25,40 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     g = torch.Generator(device=dev); g.manual_seed(4)
     Vfull = torch.randn(NI, D, device=dev, generator=g) * 0.1
-    bounds = tdist.ring_bounds(NI, world)
+    bounds = tdist.shard_bounds(NI, world)
     beg, end = bounds[rank]
     V = Vfull[beg:end].contiguous()
-    last = rank == world - 1
-    if not last:
-        del Vfull
-        Vfull = None
     gu = torch.Generator(device=dev); gu.manual_seed(3)
     Ub = [torch.randn(nb, D, device=dev, generator=gu) * 0.1 for _ in range(4)]
     ri = torch.sort(torch.randint(0, NI, (nb, 64), device=dev, generator=gu, dtype=torch.int32), dim=1).values.reshape(-1).contiguous()
     rp = torch.arange(0, (nb + 1) * 64, 64, device=dev, dtype=torch.int64)
-    out = {"world": world, "users_per_step": nb, "items": NI, "d": D, "k": k, "shards": bounds}
-    ring = tdist.RingScorer(V, D, k, nb, beg, V_full=Vfull, device=dev)
-    ok = True
-    for t, masked in ((0, False), (1, True), (2, False), (3, True), (0, True)):
-        res = ring.submit(Ub[t], rp if masked else None, ri if masked else None)
-        ring.wait()
-        if last:
-            wi, wsc = topkrec.score_topk(Ub[t], Vfull, k, None, rp if masked else None, ri if masked else None, engine="tc")
-            ok = ok and bool(torch.equal(res[0], wi)) and bool(torch.equal(res[1].view(torch.int32), wsc.view(torch.int32)))
-    flag = torch.tensor([int(ok)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-    out["ring_equals_unsharded_bitwise"] = bool(flag.item())
-    for t in range(8):
-        ring.submit(Ub[t % 4])
+    out = {"world": world, "users_per_step": nb, "items": NI, "d": D, "k": k}
+    ring = tdist.RingScorer(V, D, k, nb, beg, Vfull, device=dev)
+    # ---- correctness: 2 G + 3 batches (every rank owns some), odd ones masked; the owner compares with the unsharded engine
+    T = 2 * world + 3
+    batches = [Ub[t % 4] for t in range(T)]
+    rated = [(rp, ri) if t % 2 else (None, None) for t in range(T)]
+    bad = []
+
+    def check(t, idx, score):
+        wi, wsc = topkrec.score_topk(batches[t], Vfull, k, None, rated[t][0], rated[t][1], engine="tc")
+        if not (torch.equal(idx, wi) and torch.equal(score.view(torch.int32), wsc.view(torch.int32))):
+            bad.append(t)
+    ring.run(batches, rated, on_result=check)
+    ring.wait()
+    flag = torch.tensor([int(not bad)], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["ring_equals_unsharded_bitwise_on_every_owner"] = bool(flag.item())
+    ring.run([Ub[t % 4] for t in range(2 * world)])
     ring.wait(); dist.barrier(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for t in range(K):
-        ring.submit(Ub[t % 4])
+    ring.run([Ub[t % 4] for t in range(K)])
     ring.wait()
     e1.record(); dist.barrier(); torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1) / K], device=dev, dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    out["ring"] = {"ms_per_step": float(ms.item()), "users_per_s": nb / (float(ms.item()) / 1e3), "steps": K,
-                   "fallback_rows_last_step": int(ring.nfb.item()) if last else None}
+    out["ring"] = {"ms_per_step": float(ms.item()), "users_per_s": nb / (float(ms.item()) / 1e3), "steps": K}
+    last = rank == 0
     if last:
         print(json.dumps(out))
     ring.close()

@@ -146,102 +146,103 @@ class ShardedScorer:
         self.buf.close()
 
 
-def ring_bounds(n, world, first_w=0.9, last_w=0.75):
-    """Contiguous item shards for ``RingScorer``: the first rank also seeds (extra tiles) and the last also refines, so they
-    get proportionally fewer items and every ring stage takes about the same time."""
-    if world == 1:
-        return [(0, int(n))]
-    w = np.array([first_w] + [1.0] * (world - 2) + [last_w])
-    edges = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * n)]).astype(np.int64)
-    edges = (edges // 256) * 256                       # whole MMA tiles per shard
-    edges[-1] = n
-    return [(int(edges[r]), int(edges[r + 1])) for r in range(world)]
-
-
 class RingScorer:
     """Item-sharded filtered top-k as a RING of sweep segments (``tkr_score_topk_tc_segment``).
 
-    The sweep of a user batch over the whole item table is cut into one segment per GPU; the running state of the sweep
-    (every row's threshold, candidate buffer and count, ~1 KB per row) travels from rank to rank over NVLink, so rank r works
-    on segment r of batch t - r while rank r + 1 works on batch t - r - 1.  The per-row selection work of a sweep -- which
-    hardly depends on its length and is what bounds independent per-shard lists (``ShardedScorer``) -- is paid once per batch.
-    The last rank sorts the lists out, re-scores them exactly against the whole table and owns the results: bit-identical
-    to one GPU.  All ranks call ``submit`` with the same batches in the same order."""
+    The sweep of a user batch over the whole item table is cut into one segment per GPU (rank r always sweeps item shard r);
+    the running state of the sweep (every row's threshold, candidate buffer and count, ~1 KB per row) travels from rank to
+    rank over NVLink.  Unlike independent per-shard lists (``ShardedScorer``), the per-row selection work of a sweep -- which
+    hardly depends on its length -- is then paid once per batch instead of once per shard.  Batch t STARTS at rank
+    ``2 t mod G`` (the start of a sweep carries the threshold warm-up, the end the exact re-scoring: rotating them spreads
+    both over the ring) and moves one rank per time slot, so in slot tau it is at rank ``(tau + t) mod G`` -- distinct for
+    the G batches in flight.  The rank that holds a batch's last segment sorts its lists out, re-scores them exactly against
+    the whole table (every rank keeps ``V_full`` for that) and owns the result: bit-identical to one GPU.
+    All ranks call ``run`` with the same batches."""
 
     SLOT_READY, SLOT_FREE = 4, 5
 
-    def __init__(self, V_shard, d, k, user_batch, col_offset, V_full=None, bias_shard=None, bias_full=None, group=None, device=None):
+    def __init__(self, V_shard, d, k, user_batch, col_offset, V_full, bias_shard=None, bias_full=None, group=None, device=None):
         import topkrec
         from .peer import PeerBuffer, _RawCuda
         self.t, self.group = topkrec, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.last = self.rank == self.world - 1
         self.dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
-        if self.last and V_full is None:
-            raise ValueError("the last rank of the ring re-scores against the whole table: pass V_full")
         self.V, self.V_full, self.bias, self.bias_full = V_shard, V_full, bias_shard, bias_full
         self.d, self.k, self.nb, self.col_offset = int(d), int(k), int(user_batch), int(col_offset)
         L = topkrec.lib()
         self.sbytes = -(-L.tkr_score_topk_tc_state_bytes(self.nb) // 1024) * 1024
         self.flag_off = 2 * self.sbytes
-        ni_full = V_full.shape[0] if V_full is not None else V_shard.shape[0]
         with torch.cuda.device(self.dev):
             self.buf = PeerBuffer(self.flag_off + L.tkr_peer_flag_bytes(), group, self.dev)
-            self.ws = torch.empty(L.tkr_score_topk_tc_segment_workspace_bytes(self.nb, V_shard.shape[0], ni_full, self.d, self.k, int(bias_shard is not None)),
+            self.ws = torch.empty(L.tkr_score_topk_tc_segment_workspace_bytes(self.nb, V_shard.shape[0], V_full.shape[0], self.d, self.k, int(bias_shard is not None)),
                                   dtype=torch.uint8, device=self.dev)
             self.xfer = torch.cuda.Stream(self.dev)
             self.seg_done = [torch.cuda.Event() for _ in range(2)]
-            self.xfer_done = [torch.cuda.Event() for _ in range(2)]
+            self.slot_free = [torch.cuda.Event() for _ in range(2)]
             self.out = [(torch.empty((self.nb, k), dtype=torch.int32, device=self.dev), torch.empty((self.nb, k), dtype=torch.float32, device=self.dev))
-                        for _ in range(2)] if self.last else None
+                        for _ in range(2)]
             self.nfb = torch.zeros(1, dtype=torch.int32, device=self.dev)
             self.state = [self.buf.local[s * self.sbytes:(s + 1) * self.sbytes] for s in range(2)]
-            self.next_state = None
-            if not self.last:      # the next rank's state slots as tensors of THIS device (the mapping is a plain device pointer here)
-                nxt = self.buf.ptrs[self.rank + 1]
-                self.next_state = [torch.as_tensor(_RawCuda(nxt + s * self.sbytes, self.sbytes), device=self.dev) for s in range(2)]
-        self.epoch = 0
+            nxt = self.buf.ptrs[(self.rank + 1) % self.world]
+            self.next_state = [torch.as_tensor(_RawCuda(nxt + s * self.sbytes, self.sbytes), device=self.dev) for s in range(2)] if self.world > 1 else None
+        self.base = 0                 # time slots consumed by earlier run() calls (the flag epochs keep growing)
         self.prepared = False
         if self.world > 1:
             dist.barrier(group=group)
 
-    def submit(self, U, rated_indptr=None, rated_idx=None):
-        """Enqueue this rank's segment of one user batch.  Returns (idx, score) device views on the LAST rank (valid in stream
-        order on the current stream), None elsewhere."""
-        t, L = self.t, self.t.lib()
-        n = U.shape[0]
-        if n != self.nb:
-            raise ValueError("the ring scorer takes full batches of %d rows (pad the last one)" % self.nb)
-        self.epoch += 1
-        e, s = self.epoch, self.epoch & 1
+    def owner(self, t):
+        """rank that ends up with the lists of batch t"""
+        return (2 * t + self.world - 1) % self.world
+
+    def run(self, batches, rated=None, on_result=None):
+        """``batches``: sequence of user batches (device tensors [user_batch, d], the same on every rank); ``rated``: optional
+        sequence of (rated_indptr, rated_idx) per batch.  ``on_result(t, idx, score)`` is called (on the current stream, in
+        stream order) on the rank that owns batch t; the views are reused two slots later."""
+        t_, L, G, r = self.t, self.t.lib(), self.world, self.rank
+        T = len(batches)
         main = torch.cuda.current_stream(self.dev)
         peers = self.buf.peers_ptr
+        prev, nxt = (r - 1) % G, (r + 1) % G
         with torch.cuda.device(self.dev):
-            if self.rank > 0:
-                t._lib._check(L.tkr_peer_wait_from(peers, self.flag_off, self.SLOT_READY, self.rank - 1, e, main.cuda_stream))
-            elif e > 2:
-                main.wait_event(self.xfer_done[s])                       # the copy-out of batch e-2 has left this slot
-            out = self.out[s] if self.last else None
-            t.score_topk_segment(U, self.V, self.k, self.col_offset, self.state[s], self.rank == 0, self.last, V_full=self.V_full,
-                                 bias_shard=self.bias, bias_full=self.bias_full, rated_indptr=rated_indptr, rated_idx=rated_idx, out=out, ws=self.ws,
-                                 n_fallback=self.nfb if self.last else None, items_prepared=self.prepared)
-            self.prepared = True
-            if self.last:
-                if self.rank > 0:
-                    t._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_FREE, self.rank - 1, e, main.cuda_stream))
-                return out
-            self.seg_done[s].record(main)
-            with torch.cuda.stream(self.xfer):
-                self.xfer.wait_event(self.seg_done[s])
-                if e > 2:                                               # the next rank is done with what this slot held two batches ago
-                    t._lib._check(L.tkr_peer_wait_from(peers, self.flag_off, self.SLOT_FREE, self.rank + 1, e - 2, self.xfer.cuda_stream))
-                self.next_state[s].copy_(self.state[s], non_blocking=True)
-                t._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_READY, self.rank + 1, e, self.xfer.cuda_stream))
-                self.xfer_done[s].record(self.xfer)
-                if self.rank > 0:
-                    t._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_FREE, self.rank - 1, e, self.xfer.cuda_stream))
-        return None
+            for tau in range(T + G - 1):
+                e, s = self.base + tau + 1, (self.base + tau) & 1
+                # the batch of this rank in slot tau: t in (tau - G, tau] with (tau + t) % G == r
+                t = tau - ((tau + tau - r) % G)
+                if t < 0 or t >= T:
+                    # idle slot (pipeline fill / drain): only the predecessor's "your slot is free" is owed, in slot order
+                    if G > 1:
+                        t_._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_FREE, prev, e, self.xfer.cuda_stream))
+                    continue
+                p = tau - t
+                first, last = p == 0, p == G - 1
+                if first:
+                    main.wait_event(self.slot_free[s])                      # local slot s: its use two slots ago is over
+                else:
+                    t_._lib._check(L.tkr_peer_wait_from(peers, self.flag_off, self.SLOT_READY, prev, e, main.cuda_stream))
+                rp, ri = rated[t] if rated is not None else (None, None)
+                out = self.out[s] if last else None
+                t_.score_topk_segment(batches[t], self.V, self.k, self.col_offset, self.state[s], first, last, V_full=self.V_full, bias_shard=self.bias,
+                                      bias_full=self.bias_full, rated_indptr=rp, rated_idx=ri, out=out, ws=self.ws, n_fallback=self.nfb if last else None,
+                                      items_prepared=self.prepared)
+                self.prepared = True
+                if last and on_result is not None:
+                    on_result(t, out[0], out[1])
+                self.seg_done[s].record(main)
+                # everything that crosses to a neighbour goes through the transfer stream, in slot order: the "free" of slot tau is
+                # only raised once every earlier slot's state has left this rank
+                with torch.cuda.stream(self.xfer):
+                    self.xfer.wait_event(self.seg_done[s])
+                    if not last:
+                        # the state lands in the next rank's buffer of time slot tau + 1: free once that rank is done with slot tau - 1
+                        if self.base + tau >= 1:
+                            t_._lib._check(L.tkr_peer_wait_from(peers, self.flag_off, self.SLOT_FREE, nxt, e - 1, self.xfer.cuda_stream))
+                        self.next_state[(self.base + tau + 1) & 1].copy_(self.state[s], non_blocking=True)
+                        t_._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_READY, nxt, e + 1, self.xfer.cuda_stream))
+                    self.slot_free[s].record(self.xfer)
+                    if G > 1:
+                        t_._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_FREE, prev, e, self.xfer.cuda_stream))
+        self.base += T + G - 1
 
     def wait(self):
         main = torch.cuda.current_stream(self.dev)
