@@ -693,8 +693,10 @@ def score_sweep(dev, nb, NI, k, peaks, reps=5):
 
 def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src):
     """score + top-30: 1M items (sharded over the ranks), d=128, user batches of --score-users (the SAME batch at every N:
-    strong scaling of one step).  N > 1: topkrec.dist.ShardedScorer -- peer-memory exchange by user slice, pipelined over
-    batches; each rank ends with the final lists of its slice, checked bit for bit against the unsharded engine."""
+    strong scaling of one step).  N > 1: topkrec.dist.RingScorer -- one sweep per batch cut into a segment per GPU, the per-row
+    filter state travelling rank to rank over NVLink, G batches in flight; the owner of every batch checks its lists and score
+    bits against the unsharded engine.  --score-dist exchange: topkrec.dist.ShardedScorer (independent shard lists + peer-memory
+    exchange by user slice), kept as the route the ring is measured against."""
     import torch
     import topkrec
     from topkrec import dist as tdist
@@ -707,7 +709,32 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
     Ub = [torch.randn(nb, D, device=dev, generator=gu) * 0.1 for _ in range(4)]
     eng = args.score_engine
     check = None
-    if world > 1:
+    sc = None
+    how = "one GPU"
+    if world > 1 and args.score_dist == "ring" and eng == "tc":
+        # ring of sweep segments: rank r sweeps item shard r, the rows' thresholds / candidate buffers travel rank to rank over
+        # NVLink, the rank holding a batch's last segment re-scores exactly against the full table and owns the lists
+        how = "ring of sweep segments (topkrec.dist.RingScorer): per-row filter state copied rank to rank over NVLink, G batches in flight"
+        sc = tdist.RingScorer(V, D, k, nb, beg, Vfull, device=dev)
+        T0 = 2 * world + 1
+        bad = []
+
+        def check_owner(t, idx, score):
+            wi, wsc = topkrec.score_topk(Ub[t % 4], Vfull, k, engine="tc")
+            if not (torch.equal(idx, wi) and torch.equal(score.view(torch.int32), wsc.view(torch.int32))):
+                bad.append(t)
+        sc.run([Ub[t % 4] for t in range(T0)], on_result=check_owner)
+        sc.wait()
+        ok = torch.tensor([int(not bad)], device=dev)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+        check = {"ring_lists_and_score_bits_equal_unsharded_on_every_owner": bool(ok.item()), "batches_checked": T0}
+        torch.cuda.empty_cache()
+
+        def run_steps(n):
+            sc.run([Ub[t % 4] for t in range(n)])
+            sc.wait()
+    elif world > 1:
+        how = "independent per-shard lists, candidates exchanged by user slice over peer memory (topkrec.dist.ShardedScorer)"
         sc = tdist.ShardedScorer(end - beg, D, k, nb, beg, engine=eng, device=dev)
         oi, osc = sc.submit(Ub[0], V)
         sc.wait()
@@ -718,36 +745,36 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
         check = {"sharded_lists_and_score_bits_equal_unsharded_on_every_rank": bool(ok.item())}
         del Vfull, wi, wsc
         torch.cuda.empty_cache()
-        step, finish = (lambda t: sc.submit(Ub[t % 4], V)), sc.wait
+
+        def run_steps(n):
+            for t in range(n):
+                sc.submit(Ub[t % 4], V)
+            sc.wait()
     else:
         need = topkrec.lib().tkr_score_topk_tc_workspace_bytes(nb, NI, D, k, 0) if eng == "tc" else topkrec.lib().tkr_score_topk_workspace_bytes(nb, NI, D, k)
         wsb = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
         nfb = torch.zeros(1, dtype=torch.int32, device=dev)
         state = {"prepared": False}   # the evaluator scores many user batches against one item table: BF16 items converted once
 
-        def step(t):
-            prep = state["prepared"] and eng == "tc"
-            state["prepared"] = True
-            return topkrec.score_topk(Ub[t % 4], V, k, col_offset=beg, engine=eng, ws=wsb, n_fallback=nfb if eng == "tc" else None, items_prepared=prep)
-        finish = lambda: None  # noqa: E731
-    for t in range(4):
-        step(t)
-    finish()
+        def run_steps(n):
+            for t in range(n):
+                prep = state["prepared"] and eng == "tc"
+                state["prepared"] = True
+                topkrec.score_topk(Ub[t % 4], V, k, col_offset=beg, engine=eng, ws=wsb, n_fallback=nfb if eng == "tc" else None, items_prepared=prep)
+    run_steps(2 * world + 2)
     barrier()
     # >= 1 s of steps whatever --steps says (a step is ~4 ms / N)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = 8 * world
     e0.record()
-    for t in range(8):
-        step(t)
-    finish(); e1.record(); barrier()
-    K = int(max(args.score_steps, min(2000, 1000.0 / (max_over_ranks(e0.elapsed_time(e1)) / 8))))
+    run_steps(n0)
+    e1.record(); barrier()
+    K = int(max(args.score_steps, min(4000, 1000.0 / (max_over_ranks(e0.elapsed_time(e1)) / n0))))
     K = int(max_over_ranks(float(K)))
     topkrec.reset_launch_count()
     with ClockSampler(dev.index) as clk:
         e0.record()
-        for t in range(K):
-            step(t)
-        finish()
+        run_steps(K)
         e1.record()
         barrier()
     ms = max_over_ranks(e0.elapsed_time(e1)) / K
@@ -765,7 +792,7 @@ def bench_score(args, rank, world, dev, barrier, max_over_ranks, peaks, peak_src
                         "unit": "TFLOP/s", "frac": flops / world / (ms / 1e3) / 1e12 / peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]),
                         "frac_of_burst_peak": flops / world / (ms / 1e3) / 1e12 / peaks["bf16_tflops"], "traffic": profile_traffic("score_topk"),
                         "note": "per GPU: FLOP = 2*nu*(ni/world)*d over the whole step (convert + filter + merge + refine + fallback [+ exchange])"},
-           "scaling": "strong: the same %d-user batch at every N; item columns sharded over the GPUs, candidates exchanged by user slice over peer memory" % nb}
+           "scaling": "strong: the same %d-user batch at every N; item columns sharded over the GPUs -- %s" % (nb, how)}
     if world == 1 and eng == "tc":
         out["rows_redone_by_exact_fallback_last_step"] = int(nfb.item())
     if check is not None:
@@ -819,6 +846,8 @@ def main():
     ap.add_argument("--score-engine", default="tc", choices=["tc", "exact"])
     ap.add_argument("--score-items", type=int, default=1 << 20)
     ap.add_argument("--score-steps", type=int, default=5)
+    ap.add_argument("--score-dist", default="ring", choices=["ring", "exchange"],
+                    help="N > 1: ring of sweep segments (RingScorer, default) or independent shard lists + peer exchange (ShardedScorer)")
     ap.add_argument("--no-hot-items", action="store_true", help="do not privatise the most popular item rows (tkr_bpr_workspace_set_hot_items)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-score", action="store_true")

@@ -159,6 +159,44 @@ def _worker_slices(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_ring(rank, world, port, q):
+    """the ring of sweep segments (topkrec.dist.RingScorer) on gloo: the running state of a batch's sweep -- here its running
+    top-k lists -- travels rank to rank in the slot order of ``ring_slot``; rank r always sweeps item shard r; the rank that
+    holds the last segment (``ring_owner``) ends with the unsharded lists.  Per-segment compute injected from the oracle."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n, ni, d, k, T = 19, 157, 8, 10, 5
+    V = rng.standard_normal((ni, d)).astype(np.float32); V[100] = V[3]
+    batches = [rng.standard_normal((n, d)).astype(np.float32) for _ in range(T)]
+    beg, end = tdist.shard_bounds(ni, world)[rank]
+    prev, nxt = (rank - 1) % world, (rank + 1) % world
+    ok, owned, pending = True, [], []
+    for tau in range(T + world - 1):
+        slot = tdist.ring_slot(tau, rank, world, T)
+        if slot is None:
+            continue
+        t, p = slot
+        ok = ok and (2 * t + p) % world == rank                         # batch t started at rank 2t mod G, one rank per slot
+        li, ls = topk_ref.score_topk(batches[t], V[beg:end], k, col_offset=beg)
+        if p > 0:
+            st = torch.empty((2, n, k), dtype=torch.int32)
+            dist.recv(st, src=prev, tag=t)
+            li, ls = topk_ref.topk_merge(np.stack([st[0].numpy(), li]), np.stack([st[1].view(torch.float32).numpy(), ls]))
+        if p < world - 1:
+            pending.append(dist.isend(torch.stack([torch.from_numpy(li), torch.from_numpy(ls).view(torch.int32)]), dst=nxt, tag=t))
+        else:
+            wi, ws = topk_ref.score_topk(batches[t], V, k)
+            ok = ok and tdist.ring_owner(t, world) == rank and np.array_equal(li, wi) and np.array_equal(ls, ws)
+            owned.append(t)
+    for h in pending:
+        h.wait()
+    seen = torch.zeros(T); seen[owned] = 1
+    dist.all_reduce(seen)
+    q.put((rank, bool(ok and bool((seen == 1).all()))))
+    dist.destroy_process_group()
+
+
 class _CpuSide:
     def __init__(self, indptr, idx):
         self.indptr, self.idx = indptr, idx
@@ -213,7 +251,7 @@ def _worker_als(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp, _worker_dp_owner, _worker_slices, _worker_als])
+@pytest.mark.parametrize("worker", [_worker_topk, _worker_dp, _worker_dp_owner, _worker_slices, _worker_ring, _worker_als])
 def test_world2_gloo(worker):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -225,6 +263,29 @@ def test_world2_gloo(worker):
     for p in procs:
         p.join(30)
     assert res == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("G", [1, 2, 3, 4, 8])
+def test_ring_schedule(G):
+    """every slot holds at most one batch per rank; a batch visits G consecutive ranks in G consecutive slots, segment p at
+    rank (2t + p) mod G; owners rotate over the ring"""
+    T = 2 * G + 3
+    visits = {}
+    for tau in range(T + G - 1):
+        here = [tdist.ring_slot(tau, r, G, T) for r in range(G)]
+        ts = [s[0] for s in here if s is not None]
+        assert len(ts) == len(set(ts))
+        for r, s in enumerate(here):
+            if s is not None:
+                visits.setdefault(s[0], []).append((tau, r, s[1]))
+    assert sorted(visits) == list(range(T))
+    for t, v in visits.items():
+        assert [x[0] for x in v] == list(range(t, t + G)) and [x[2] for x in v] == list(range(G))
+        assert [x[1] for x in v] == [(2 * t + p) % G for p in range(G)] and v[-1][1] == tdist.ring_owner(t, G)
+    if G > 1 and G % 2 == 0:
+        assert {tdist.ring_owner(t, G) for t in range(T)} == set(range(1, G, 2)) or G == 2
+    if G % 2 == 1:
+        assert {tdist.ring_owner(t, G) for t in range(T)} == set(range(G))
 
 
 def test_shard_bounds():

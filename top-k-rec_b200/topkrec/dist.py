@@ -146,6 +146,22 @@ class ShardedScorer:
         self.buf.close()
 
 
+def ring_slot(tau, rank, world, n_batches):
+    """Schedule of the ring of sweep segments: the batch rank ``rank`` works on in time slot ``tau`` and which segment of that
+    batch's sweep it is.  Batch t starts at rank ``2 t mod world`` in slot t and moves one rank per slot, so in slot tau it sits
+    at rank ``(tau + t) mod world`` -- distinct for the ``world`` batches in flight.  Returns ``(t, p)`` with p in
+    [0, world) the segment number (0 = first, world-1 = last), or ``None`` for an idle slot (pipeline fill / drain)."""
+    t = tau - ((2 * tau - rank) % world)
+    if t < 0 or t >= n_batches:
+        return None
+    return t, tau - t
+
+
+def ring_owner(t, world):
+    """rank that sweeps the last segment of batch t and ends up with its lists"""
+    return (2 * t + world - 1) % world
+
+
 class RingScorer:
     """Item-sharded filtered top-k as a RING of sweep segments (``tkr_score_topk_tc_segment``).
 
@@ -193,7 +209,7 @@ class RingScorer:
 
     def owner(self, t):
         """rank that ends up with the lists of batch t"""
-        return (2 * t + self.world - 1) % self.world
+        return ring_owner(t, self.world)
 
     def run(self, batches, rated=None, on_result=None):
         """``batches``: sequence of user batches (device tensors [user_batch, d], the same on every rank); ``rated``: optional
@@ -207,14 +223,13 @@ class RingScorer:
         with torch.cuda.device(self.dev):
             for tau in range(T + G - 1):
                 e, s = self.base + tau + 1, (self.base + tau) & 1
-                # the batch of this rank in slot tau: t in (tau - G, tau] with (tau + t) % G == r
-                t = tau - ((tau + tau - r) % G)
-                if t < 0 or t >= T:
+                slot = ring_slot(tau, r, G, T)
+                if slot is None:
                     # idle slot (pipeline fill / drain): only the predecessor's "your slot is free" is owed, in slot order
                     if G > 1:
                         t_._lib._check(L.tkr_peer_signal_to(peers, self.flag_off, self.SLOT_FREE, prev, e, self.xfer.cuda_stream))
                     continue
-                p = tau - t
+                t, p = slot
                 first, last = p == 0, p == G - 1
                 if first:
                     main.wait_event(self.slot_free[s])                      # local slot s: its use two slots ago is over
