@@ -303,6 +303,9 @@ void tkr_debug_set_filter_tuning(int32_t seed_rank, int32_t cap_trigger);
 void tkr_debug_set_vbpr_tc_mode(int32_t mode);
 /* experiments on the 3xTF32 GEMM: bit 0 = overwrite the A tile with its TF32-exact part, bit 1 = three separate products */
 void tkr_debug_set_gemm3_flags(int32_t flags);
+/* ALS factorisation variant: 0 = default (blocked 16-column rounds for d > 192, four-column rounds below), 1 = blocked at every
+ * width, 2 = the per-column / four-column loops at every width (als_solve.cu) */
+void tkr_debug_set_als_factor(int32_t mode);
 void tkr_debug_set_seed_div(int32_t div);          /* seed fraction of a sweep = 1/div (default 12); tuning aid */
 int32_t tkr_debug_filter_max_pairs(int32_t d);   /* resident CTA pairs of the filter kernel on the current device */
 

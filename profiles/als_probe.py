@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
 """ALS half-step timing probe (BASELINE configs[3] shape: 480 189 users x 17 770 items, d=256, Zipf item popularity).
-usage: python profiles/als_probe.py [scale=0.1] [d=256] [seg=4096] [mean_pos=208]"""
+usage: python profiles/als_probe.py [scale=0.1] [d=256] [seg=4096] [mean_pos=208] [factor=0]
+factor: tkr_debug_set_als_factor (0 default, 1 blocked rounds at every width, 2 per-column / four-column loops)"""
 import os
 import sys
 import time
@@ -28,6 +29,7 @@ def main():
     d = int(sys.argv[2]) if len(sys.argv) > 2 else 256
     seg = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
     mean_pos = int(sys.argv[4]) if len(sys.argv) > 4 else 208
+    topkrec.lib().tkr_debug_set_als_factor(int(sys.argv[5]) if len(sys.argv) > 5 else 0)
     n_users, n_items = int(480189 * scale), 17770
     t0 = time.time()
     users, items = synth(n_users, n_items, mean_pos)

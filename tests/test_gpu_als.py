@@ -131,6 +131,19 @@ def test_user_and_item_steps_match_oracle(d, seg, init):
     assert abs(float(lr.sum()) - loss_ref) <= 1e-5 * (abs(loss_ref) + a * u_idx.size)      # terms of size a*nnz cancel in the item loss
 
 
+@pytest.mark.parametrize("d,seg", [(12, 16), (64, 33), (100, 4096), (128, 100), (192, 64), (200, 4096), (256, 48)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_both_factorisations_at_every_width(d, seg, mode):
+    """the blocked 16-column rounds (default at d > 192) and the per-column / four-column loops (default below) are both held to
+    the oracle at every width: tkr_debug_set_als_factor 1 = blocked everywhere, 2 = the loops everywhere"""
+    L = topkrec.lib()
+    L.tkr_debug_set_als_factor(mode)
+    try:
+        test_user_and_item_steps_match_oracle(d, seg, "uniform")
+    finally:
+        L.tkr_debug_set_als_factor(0)
+
+
 def test_split_rows_are_deterministic_and_agree_with_fused():
     rng = np.random.default_rng(5)
     d = 96

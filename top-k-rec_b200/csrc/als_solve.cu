@@ -21,6 +21,7 @@
 //     x^T B x = x^T rhs - ridge |x|^2 for the solved x, so the matrix is not needed again.
 #include "common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace tkr {
 namespace als {
@@ -44,7 +45,19 @@ template <int NB> struct Geo {
     static constexpr int NP = DP / 4;                  // 4-column panels of the factor
     static constexpr int PACKED = DP * DP / 2 + 2 * DP;// floats of the factor: panel p keeps a float4 per row 4p..DP-1
     static constexpr int PART = NBLK * 4096 + DP;      // floats per partial slot
-    static constexpr size_t SMEM = (size_t)(PACKED + STAGES * KC * DP + 4 * DP + 2 * DP + 16 + 64 + 3 * DP) * sizeof(float);
+    // blocked factorisation (factor_solve_blocked): panels of PW columns, panel p keeps rows PW*p..DP-1 of its columns k-major
+    // (column k of the panel = pitch(p) consecutive floats; the +4 keeps 16-byte alignment and spreads the banks of the
+    // back substitution's column walks)
+    static constexpr int PW = 16;
+    static constexpr int NPAN = DP / PW;
+    __host__ __device__ static constexpr int pitch(int p) { return DP - PW * p + 4; }
+    __host__ __device__ static constexpr int panel_off(int p) { return PW * (p * (DP + 4) - PW * (p * (p - 1) / 2)); }
+    static constexpr int BLOCKED = panel_off(NPAN);    // floats of the blocked factor
+    static constexpr int FACTOR = PACKED > BLOCKED ? PACKED : BLOCKED;
+    static constexpr int MT_PITCH = DP + 4;            // raw M of the current panel, k-major, in the (free) gather stages
+    static constexpr int NTB = NT;                     // threads of a blocked-variant block (warp 0 doubles as the pivot warp)
+    static constexpr int MAXREG_B = MAXREG;
+    static constexpr size_t SMEM = (size_t)(FACTOR + STAGES * KC * DP + 4 * DP + 2 * DP + 16 + 64 + 3 * DP + PW * PW + PW) * sizeof(float);
 };
 
 struct RowArgs {
@@ -68,6 +81,15 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void named_barrier(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// compile-time loop: f(std::integral_constant<int, B>{}) ... f(<E - 1>) -- register arrays indexed by the loop variable stay
+// in registers whatever the unroller decides
+template <int B, int E, class F> __device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
 }
 
 // thread -> tile geometry
@@ -141,7 +163,7 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], fl
     for (int s = 0; s < STAGES - 1; ++s) { issue(s); fetch_idx(s + 1); }
     for (int64_t c = 0; c < nchunks; ++c) {
         cp_async_wait<STAGES - 2>();
-        __syncthreads();
+        named_barrier(3, G::NT);                 // the NT tile threads (a blocked-variant block has one more warp, which is not here)
         issue(c + STAGES - 1);
         fetch_idx(c + STAGES);
         const float* buf = stage + (c % STAGES) * KC * G::DP;
@@ -164,7 +186,7 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], fl
         }
     }
     cp_async_wait<0>();
-    __syncthreads();
+    named_barrier(3, G::NT);
 }
 
 template <int NB>
@@ -225,10 +247,11 @@ __device__ __forceinline__ void row_loss(const RowArgs& p, int row, int64_t n, b
 
 template <int NB> struct Smem {
     using G = Geo<NB>;
-    float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep;
+    float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep; float* ldiag; float* dinv;
     __device__ explicit Smem(float* base) {
-        M = base; stage = M + G::PACKED;     // PACKED * 4 bytes is a multiple of 16 for every DP
+        M = base; stage = M + G::FACTOR;     // FACTOR * 4 bytes is a multiple of 16 for every DP
         raw = stage + STAGES * KC * G::DP; zs = raw + 4 * G::DP; xs = zs + G::DP; d44 = xs + G::DP; red = d44 + 16; keep = red + 64;
+        ldiag = keep + 3 * G::DP; dinv = ldiag + G::PW * G::PW;
     }
 };
 
@@ -457,6 +480,262 @@ __device__ __forceinline__ void factor_solve_columns(float (&acc)[Geo<NB>::TR][8
     }
 }
 
+// Blocked right-looking A = L D L^T, PW = 16 columns per round (the default at NB = 4), the matrix staying in the threads'
+// register tiles.  Round p, columns [16p, 16p + 16):
+//   publish  the tile owners of the panel's columns store them k-major into the panel's slot of the factor   -- barrier --
+//   panel    threads 16p..DP-1 take one matrix ROW each (16 registers).  The warp holding the diagonal block factors it with
+//            shuffles (row i at lane i: pivot, L[i][j], the rank-1 update of a_i[c] by the value of lane c), forward-solves
+//            the panel's right-hand-side entries and publishes L (straight into the factor), 1/D and y          -- named barrier --
+//            every row below solves its 16 entries against that block on its own (120 FMA, no communication), stores
+//            L (into the factor: this IS what back substitution walks) and raw M = L D (transient), takes its share of
+//            the forward substitution                                                                  -- barrier --
+//   update   every live tile applies the rank-16 update at the gather loop's density (64 FFMA per 4 LDS.128); 32-row / 32-column
+//            halves of a tile that the factorisation has passed are skipped (warp-uniform), and so is the upper-triangle
+//            quarter of the diagonal blocks.  Entries the factorisation has passed hold garbage from here on: never read.
+// Three barriers per 16 columns instead of one per column, and the serial part of a column is a shuffle + an FMA of one warp
+// instead of a store / barrier / load round trip of 20.  Back substitution runs panel by panel the same way (the diagonal
+// block inside one warp, everybody else one 16-term dot product per panel).
+template <int NB, int CG>
+__device__ __forceinline__ void blocked_publish(const float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, int p) {
+    using G = Geo<NB>;
+    if (t.J == (p >> 2) && (t.tx >> 2) == (p & 1)) {
+        const int pitch = G::pitch(p);
+        float* base = sm.M + G::panel_off(p) + (t.tx & 3) * 4 * pitch - G::PW * p;
+#pragma unroll
+        for (int rg = 0; rg < 2; ++rg) {
+            const int r = t.r0 + rg * 32;
+            if (r >= G::PW * p) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    *reinterpret_cast<float4*>(base + kk * pitch + r) =
+                        make_float4(acc[rg * 4 + 0][CG * 4 + kk], acc[rg * 4 + 1][CG * 4 + kk], acc[rg * 4 + 2][CG * 4 + kk], acc[rg * 4 + 3][CG * 4 + kk]);
+            }
+        }
+    }
+}
+
+template <int NB, bool R0, bool C0, bool DIAG>
+__device__ __forceinline__ void blocked_update(float (&acc)[Geo<NB>::TR][8], const float* __restrict__ lrow, int pitch, const float* __restrict__ mcol) {
+    using G = Geo<NB>;
+#pragma unroll 4
+    for (int k = 0; k < G::PW; ++k) {
+        const float4 l1 = *reinterpret_cast<const float4*>(lrow + k * pitch + 32);
+        const float4 m1 = *reinterpret_cast<const float4*>(mcol + k * G::MT_PITCH + 32);
+        const float lv1[4] = {l1.x, l1.y, l1.z, l1.w}, mv1[4] = {m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[4 + i][4 + j] = fmaf(-lv1[i], mv1[j], acc[4 + i][4 + j]);
+        if (C0) {
+            const float4 m0 = *reinterpret_cast<const float4*>(mcol + k * G::MT_PITCH);
+            const float mv0[4] = {m0.x, m0.y, m0.z, m0.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[4 + i][j] = fmaf(-lv1[i], mv0[j], acc[4 + i][j]);
+            if (R0) {
+                const float4 l0 = *reinterpret_cast<const float4*>(lrow + k * pitch);
+                const float lv0[4] = {l0.x, l0.y, l0.z, l0.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(-lv0[i], mv0[j], acc[i][j]);
+                if (!DIAG) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][4 + j] = fmaf(-lv0[i], mv1[j], acc[i][4 + j]);
+                }
+            }
+        } else if (R0) {
+            const float4 l0 = *reinterpret_cast<const float4*>(lrow + k * pitch);
+            const float lv0[4] = {l0.x, l0.y, l0.z, l0.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][4 + j] = fmaf(-lv0[i], mv1[j], acc[i][4 + j]);
+        }
+    }
+}
+
+// the 16 x 16 diagonal block of round p, factored inside the pivot warp (warp 0): row i at lane i, everything by shuffles
+template <int NB>
+__device__ __forceinline__ void blocked_pivot(const Smem<NB>& sm, int p) {
+    using G = Geo<NB>;
+    constexpr int PW = G::PW;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int pitch = G::pitch(p);
+    float* const Lp = sm.M + G::panel_off(p) - PW * p;       // Lp[k * pitch + r] = entry (r, 16p + k)
+    const int i = threadIdx.x & 31;
+    const bool dg = i < PW;
+    const int r = PW * p + (dg ? i : 0);
+    float a[PW];
+#pragma unroll
+    for (int k = 0; k < PW; ++k) a[k] = Lp[k * pitch + r];
+    float zi = sm.zs[r];
+    static_for<0, PW>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        const float dj = __shfl_sync(FULL, a[j], j);
+        float inv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dj));
+        inv = fmaf(fmaf(-dj, inv, 1.f), inv, inv);            // one Newton step: within an ulp of 1 / D[j]
+        const float lij = a[j] * inv;                         // L[i][j] (rows i > j; garbage in the others, never read)
+        const float yj = __shfl_sync(FULL, zi, j);
+        if (i == j) { sm.dinv[j] = inv; sm.raw[r] = inv; sm.zs[r] = zi; }   // lane j: 1 / D[j], and its y is final
+        zi = fmaf(-lij, yj, zi);                              // (lanes i <= j: already published)
+        // rank-1 update of the trailing block, all lanes unconditionally: entries right of the diagonal of a row are never
+        // read (lane c's a[j] with c > j is a lower entry), so no predicates; the shuffles go first, then the FMAs
+        float m[PW];
+        static_for<j + 1, PW>([&](auto cc) { constexpr int c = decltype(cc)::value; m[c] = __shfl_sync(FULL, a[j], c); });   // raw M[c][j]
+        static_for<j + 1, PW>([&](auto cc) { constexpr int c = decltype(cc)::value; a[c] = fmaf(-lij, m[c], a[c]); });
+        if (dg) Lp[j * pitch + r] = lij;                      // the factor: column j, rows contiguous (read by the rows below and
+    });                                                       // by back substitution, rows > j only)
+}
+
+// threads that meet at barrier 2 of round p: the warps with rows below the diagonal block and the pivot warp
+template <int NB> __device__ __forceinline__ int blocked_b2_count(int p) {
+    const int ws = (Geo<NB>::PW * (p + 1)) >> 5;
+    return (ws < Geo<NB>::DP / 32 ? Geo<NB>::DP - 32 * ws : 0) + (ws > 0 ? 32 : 0);
+}
+
+// a round of the pivot warp once its own tiles (block (0, 0)) are finished: rounds 4 and later.  The register tiles are not
+// live in this loop, so the factorisation of the diagonal block has the whole register budget.
+template <int NB>
+__device__ __forceinline__ void blocked_round_pivot(const Smem<NB>& sm, int p) {
+    using G = Geo<NB>;
+    named_barrier(4, G::NT);                                  // the panel's columns are published
+    blocked_pivot<NB>(sm, p);
+    named_barrier(2, blocked_b2_count<NB>(p));
+    named_barrier(4, G::NT);                                  // L and M of the panel are in shared memory
+}
+
+// a round of the tile threads: rows below the diagonal block (threads 16p+16 .. DP-1, one row each), then the rank-16 update.
+// PIVOT: warp 0 in rounds 0..3, when it still holds live tiles and factors the diagonal block as well.
+template <int NB, bool PIVOT>
+__device__ __forceinline__ void blocked_round(float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, int p, float& z) {
+    using G = Geo<NB>;
+    constexpr int PW = G::PW;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pitch = G::pitch(p);
+    float* const Mt = sm.stage;
+    float* const Lp = sm.M + G::panel_off(p) - PW * p;       // Lp[k * pitch + r] = entry (r, 16p + k)
+    named_barrier(4, G::NT);                                  // the panel's columns are published
+    const int ws = (PW * (p + 1)) >> 5;
+    if (PIVOT) blocked_pivot<NB>(sm, p);
+    if (warp >= ws && tid < G::DP) {
+        const int i = tid - PW * p;                           // >= 16: a row below the diagonal block
+        float a[PW];
+#pragma unroll
+        for (int k = 0; k < PW; ++k) a[k] = Lp[k * pitch + tid];
+        named_barrier(2, blocked_b2_count<NB>(p));
+        if (i >= PW) {
+            // M[r][j] = A[r][j] - sum_{q < j} M[r][q] L[j][q], right-looking: once M[r][q] is final it leaves all the later
+            // entries (independent FMAs); column q of the diagonal block's L is read from the factor itself, uniformly
+            static_for<0, PW - 1>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                static_for<(q + 1) / 4, PW / 4>([&](auto jb) {
+                    constexpr int j0 = decltype(jb)::value * 4;
+                    const float4 l = *reinterpret_cast<const float4*>(Lp + q * pitch + PW * p + j0);
+                    if constexpr (j0 + 0 > q) a[j0 + 0] = fmaf(-a[q], l.x, a[j0 + 0]);
+                    if constexpr (j0 + 1 > q) a[j0 + 1] = fmaf(-a[q], l.y, a[j0 + 1]);
+                    if constexpr (j0 + 2 > q) a[j0 + 2] = fmaf(-a[q], l.z, a[j0 + 2]);
+                    if constexpr (j0 + 3 > q) a[j0 + 3] = fmaf(-a[q], l.w, a[j0 + 3]);
+                });
+            });
+            float zz = z;
+#pragma unroll
+            for (int k4 = 0; k4 < PW / 4; ++k4) {
+                const float4 iv = *reinterpret_cast<const float4*>(sm.dinv + k4 * 4);
+                const float4 yv = *reinterpret_cast<const float4*>(sm.zs + PW * p + k4 * 4);
+                const float ivv[4] = {iv.x, iv.y, iv.z, iv.w}, yvv[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = k4 * 4 + e;
+                    const float l = a[k] * ivv[e];
+                    zz = fmaf(-l, yvv[e], zz);
+                    Lp[k * pitch + tid] = l;
+                    Mt[k * G::MT_PITCH + tid] = a[k];
+                }
+            }
+            z = zz;
+            if (i < 2 * PW) sm.zs[tid] = zz;                  // rows of the next diagonal block hand their right-hand side to the pivot warp
+        }
+    } else if (PIVOT) {
+        named_barrier(2, blocked_b2_count<NB>(p));
+    }
+    named_barrier(4, G::NT);                                  // L and M of the panel are in shared memory
+    const int pe = PW * p + PW - 1;
+    if (t.I * 64 + 63 > pe && t.J * 64 + 63 > pe) {
+        const bool r0live = t.I * 64 + 31 > pe, c0live = t.J * 64 + 31 > pe;     // c0live implies r0live (I >= J)
+        const float* lrow = Lp + t.r0;
+        const float* mcol = Mt + t.c0;
+        if (c0live) {
+            if (t.I == t.J) blocked_update<NB, true, true, true>(acc, lrow, pitch, mcol);
+            else blocked_update<NB, true, true, false>(acc, lrow, pitch, mcol);
+        } else if (r0live) blocked_update<NB, true, false, false>(acc, lrow, pitch, mcol);
+        else blocked_update<NB, false, false, false>(acc, lrow, pitch, mcol);
+    }
+    if (p + 1 < G::NPAN) {                                    // CG of blocked_publish: which 32-column half of the block holds the panel
+        if (((p + 1) >> 1) & 1) blocked_publish<NB, 1>(acc, t, sm, p + 1);
+        else blocked_publish<NB, 0>(acc, t, sm, p + 1);
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void factor_solve_blocked(float (&acc)[Geo<NB>::TR][8], const Tile& t, const Smem<NB>& sm, float z, float& x) {
+    using G = Geo<NB>;
+    constexpr int PW = G::PW;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int NP0 = G::NPAN < 4 ? G::NPAN : 4;            // rounds in which block (0, 0) -- the pivot warp's own tiles -- is live
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid < G::DP) sm.zs[tid] = z;                          // the right-hand side: rows of a diagonal block are read by the pivot warp
+    blocked_publish<NB, 0>(acc, t, sm, 0);
+    if (warp == 0) {
+#pragma unroll 1
+        for (int p = 0; p < NP0; ++p) blocked_round<NB, true>(acc, t, sm, p, z);
+#pragma unroll 1
+        for (int p = NP0; p < G::NPAN; ++p) blocked_round_pivot<NB>(sm, p);
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < G::NPAN; ++p) blocked_round<NB, false>(acc, t, sm, p, z);
+    }
+    __syncthreads();                                          // y (zs) and 1/D (raw) of the last panel
+    // back substitution: x = L^-T D^-1 y, panel by panel from the bottom
+    if (tid < G::DP) {
+        float w = sm.zs[tid] * sm.raw[tid];
+#pragma unroll 1
+        for (int p = G::NPAN - 1; p >= 0; --p) {
+            const int wd = (PW * p) >> 5, lb = (PW * p) & 31;
+            if (warp == wd) {
+                const int i = tid - PW * p;
+                const bool mine = i >= 0 && i < PW;
+                const float* col = sm.M + G::panel_off(p) + (mine ? i : 0) * G::pitch(p);    // col[q] = L[16p + q][16p + i]
+                float lc[PW];
+#pragma unroll
+                for (int q = 0; q < PW; ++q) lc[q] = col[q];
+                static_for<0, PW - 1>([&](auto qc) {
+                    constexpr int q = PW - 1 - decltype(qc)::value;     // 15 .. 1
+                    const float xq = __shfl_sync(FULL, w, lb + q);
+                    if (mine && i < q) w = fmaf(-lc[q], xq, w);
+                });
+                if (mine) sm.xs[tid] = w;
+            }
+            named_barrier(1, G::DP);
+            if (tid < PW * p) {
+                const int pc = tid >> 4;
+                const float* col = sm.M + G::panel_off(pc) + (tid & 15) * G::pitch(pc) + PW * (p - pc);
+#pragma unroll
+                for (int q4 = 0; q4 < PW / 4; ++q4) {
+                    const float4 l = *reinterpret_cast<const float4*>(col + q4 * 4);
+                    const float4 xv = *reinterpret_cast<const float4*>(sm.xs + PW * p + q4 * 4);
+                    w = fmaf(-l.w, xv.w, fmaf(-l.z, xv.z, fmaf(-l.y, xv.y, fmaf(-l.x, xv.x, w))));
+                }
+            }
+        }
+        x = w;
+    }
+}
+
 // Build A from the accumulated Gram, factor it (A = L D L^T, in registers, four columns per round), solve, write the
 // row and its loss.  One round for columns j0..j0+3:
 //   A  the thread holding the 4x4 diagonal block factors it and publishes 1/D and the six L entries; threads j0..j0+3
@@ -465,21 +744,23 @@ __device__ __forceinline__ void factor_solve_columns(float (&acc)[Geo<NB>::TR][8
 //      row each: M into a transient buffer, L into the factor, which back substitution reads later)      -- barrier --
 //   C  every tile to the right/below applies the rank-4 update from L (its rows) and M (its columns); the right-hand
 //      side does the same (forward substitution rides along).
-template <int NB>
+template <int NB, bool BLK>
 __device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n, float (&acc)[Geo<NB>::TR][8], float ssum, const Tile& t,
                                            const Smem<NB>& sm) {
     using G = Geo<NB>;
     const int tid = threadIdx.x, d = p.d;
+    if (tid < G::NT) {
 #pragma unroll
-    for (int i = 0; i < G::TR; ++i) {
-        const int r = row_pos<NB>(t.r0, i);
+        for (int i = 0; i < G::TR; ++i) {
+            const int r = row_pos<NB>(t.r0, i);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = reg_pos(t.c0, j);
-            float v;
-            if (r < d && c < d) v = fmaf(p.amb, acc[i][j], __ldg(p.base + (size_t)r * d + c)) + (r == c ? p.ridge : 0.f);
-            else v = (r == c) ? 1.f : 0.f;
-            acc[i][j] = v;
+            for (int j = 0; j < 8; ++j) {
+                const int c = reg_pos(t.c0, j);
+                float v;
+                if (r < d && c < d) v = fmaf(p.amb, acc[i][j], __ldg(p.base + (size_t)r * d + c)) + (r == c ? p.ridge : 0.f);
+                else v = (r == c) ? 1.f : 0.f;
+                acc[i][j] = v;
+            }
         }
     }
     float pr = 0.f, z = 0.f;
@@ -489,7 +770,8 @@ __device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n,
     }
     if (tid < G::DP) { sm.keep[tid] = z; sm.keep[G::DP + tid] = pr; sm.keep[2 * G::DP + tid] = ssum; }   // read back for the loss
     float x = 0.f;
-    if constexpr (NB == 4) factor_solve_columns<NB>(acc, t, sm, z, x);
+    if constexpr (BLK) factor_solve_blocked<NB>(acc, t, sm, z, x);
+    else if constexpr (NB == 4) factor_solve_columns<NB>(acc, t, sm, z, x);
     else factor_solve_panels<NB>(acc, t, sm, z, x);
     if (tid < G::DP) {
         if (tid < d) p.X[(size_t)row * d + tid] = x;
@@ -512,8 +794,8 @@ __device__ __forceinline__ void loss_only_row(const RowArgs& p, int row, float* 
 }
 
 // kernel 1: one block per segment
-template <int NB>
-__global__ void __launch_bounds__(Geo<NB>::NT) __maxnreg__(Geo<NB>::MAXREG) als_segment_kernel(const RowArgs p) {
+template <int NB, bool BLK>
+__global__ void __launch_bounds__(BLK ? Geo<NB>::NTB : Geo<NB>::NT) __maxnreg__(BLK ? Geo<NB>::MAXREG_B : Geo<NB>::MAXREG) als_segment_kernel(const RowArgs p) {
     using G = Geo<NB>;
     extern __shared__ __align__(16) float smem_raw[];
     Smem<NB> sm(smem_raw);
@@ -523,40 +805,44 @@ __global__ void __launch_bounds__(Geo<NB>::NT) __maxnreg__(Geo<NB>::MAXREG) als_
         if (p.loss_rows) loss_only_row<NB>(p, row, sm.red);
         return;
     }
-    for (int e = tid; e < STAGES * KC * G::DP; e += G::NT) sm.stage[e] = 0.f;   // pad columns stay zero
+    for (int e = tid; e < STAGES * KC * G::DP; e += blockDim.x) sm.stage[e] = 0.f;   // pad columns stay zero
     __syncthreads();
-    const Tile t = tile_of<NB>(tid);
+    const bool tile_thread = tid < G::NT;                   // (a blocked-variant block has one more warp: the pivot warp)
+    const Tile t = tile_of<NB>(tile_thread ? tid : 0);
     float acc[G::TR][8];
 #pragma unroll
     for (int i = 0; i < G::TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float ssum = 0.f;
-    gram_accumulate<NB>(acc, ssum, t, p.Y, p.d, p.idx + p.seg_off[seg], len, sm.stage);
+    if (tile_thread) gram_accumulate<NB>(acc, ssum, t, p.Y, p.d, p.idx + p.seg_off[seg], len, sm.stage);
     if (slot >= 0) {
-        store_partial<NB>(acc, ssum, p.partial + (size_t)slot * G::PART);
+        if (tile_thread) store_partial<NB>(acc, ssum, p.partial + (size_t)slot * G::PART);
         return;
     }
-    finish_row<NB>(p, row, len, acc, ssum, t, sm);
+    if (BLK) __syncthreads();                               // the gather stages are free (the pivot warp was not in the gather's barriers)
+    finish_row<NB, BLK>(p, row, len, acc, ssum, t, sm);
 }
 
 // kernel 2: one block per split row: ordered sum of its partial slots, then the same finish
-template <int NB>
-__global__ void __launch_bounds__(Geo<NB>::NT) __maxnreg__(Geo<NB>::MAXREG) als_multi_kernel(const RowArgs p) {
+template <int NB, bool BLK>
+__global__ void __launch_bounds__(BLK ? Geo<NB>::NTB : Geo<NB>::NT) __maxnreg__(BLK ? Geo<NB>::MAXREG_B : Geo<NB>::MAXREG) als_multi_kernel(const RowArgs p) {
     using G = Geo<NB>;
     extern __shared__ __align__(16) float smem_raw[];
     Smem<NB> sm(smem_raw);
     const int m = blockIdx.x, tid = threadIdx.x;
     const int row = p.multi_row[m], slot0 = p.multi_slot0[m], ns = p.multi_nslots[m];
-    const Tile t = tile_of<NB>(tid);
+    const bool tile_thread = tid < G::NT;
+    const Tile t = tile_of<NB>(tile_thread ? tid : 0);
     float acc[G::TR][8];
 #pragma unroll
     for (int i = 0; i < G::TR; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float ssum = 0.f;
-    for (int s = 0; s < ns; ++s) add_partial<NB>(acc, ssum, p.partial + (size_t)(slot0 + s) * G::PART, tid / G::TPB, tid % G::TPB, true);
-    finish_row<NB>(p, row, p.multi_total[m], acc, ssum, t, sm);
+    if (tile_thread)
+        for (int s = 0; s < ns; ++s) add_partial<NB>(acc, ssum, p.partial + (size_t)(slot0 + s) * G::PART, tid / G::TPB, tid % G::TPB, true);
+    finish_row<NB, BLK>(p, row, p.multi_total[m], acc, ssum, t, sm);
 }
 
 // shared Gram: out[d,d] = scale * sum of n_slots partial matrices + ridge * I  (one 64-thread block per 64x64 block)
@@ -593,23 +879,32 @@ template <int NB> static int set_attr() {
     int dev = 0;
     TKR_CUDA(cudaGetDevice(&dev));
     if (done_dev != dev) {
-        TKR_CUDA(cudaFuncSetAttribute(als_segment_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
-        TKR_CUDA(cudaFuncSetAttribute(als_multi_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
+        TKR_CUDA(cudaFuncSetAttribute(als_segment_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
+        TKR_CUDA(cudaFuncSetAttribute(als_multi_kernel<NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
+        TKR_CUDA(cudaFuncSetAttribute(als_segment_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
+        TKR_CUDA(cudaFuncSetAttribute(als_multi_kernel<NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<NB>::SMEM));
         done_dev = dev;
     }
     return TKR_OK;
 }
 
+// factorisation variant (tkr_debug_set_als_factor): 0 = default (blocked at NB = 4, four-column rounds below), 1 = blocked
+// everywhere, 2 = the per-column / four-column loops everywhere.  A process global like the other tkr_debug_* switches.
+int g_als_factor = 0;
+
 template <int NB> static int launch_rows(const RowArgs& p, int64_t n_segs, int64_t n_multi, cudaStream_t st) {
     using G = Geo<NB>;
     int rc = set_attr<NB>();
     if (rc) return rc;
+    const bool blk = g_als_factor == 1 || (g_als_factor == 0 && NB == 4);
     if (n_segs > 0) {
-        als_segment_kernel<NB><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);
+        if (blk) als_segment_kernel<NB, true><<<(unsigned)n_segs, G::NTB, G::SMEM, st>>>(p);
+        else als_segment_kernel<NB, false><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);
         TKR_LAUNCH_CHECK();
     }
     if (n_multi > 0) {
-        als_multi_kernel<NB><<<(unsigned)n_multi, G::NT, G::SMEM, st>>>(p);
+        if (blk) als_multi_kernel<NB, true><<<(unsigned)n_multi, G::NTB, G::SMEM, st>>>(p);
+        else als_multi_kernel<NB, false><<<(unsigned)n_multi, G::NT, G::SMEM, st>>>(p);
         TKR_LAUNCH_CHECK();
     }
     return TKR_OK;
@@ -619,7 +914,7 @@ template <int NB> static int launch_gram(const RowArgs& p, int64_t n_segs, int d
     using G = Geo<NB>;
     int rc = set_attr<NB>();
     if (rc) return rc;
-    als_segment_kernel<NB><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);
+    als_segment_kernel<NB, false><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);     // every segment is a partial slot: no solve
     TKR_LAUNCH_CHECK();
     als_gram_reduce_kernel<NB><<<G::NBLK, G::TPB, 0, st>>>(p.partial, (int)n_segs, d, scale, ridge, out);
     TKR_LAUNCH_CHECK();
@@ -642,6 +937,8 @@ constexpr int kGramSegs = 2 * kNumSMs;
 }  // namespace tkr
 
 using namespace tkr;
+
+extern "C" void tkr_debug_set_als_factor(int32_t mode) { als::g_als_factor = mode; }
 
 extern "C" size_t tkr_als_partial_bytes(int32_t d, int64_t n_slots) {
     if (d < 1 || d > 256 || n_slots < 0) return 0;
