@@ -750,16 +750,29 @@ __device__ __forceinline__ void finish_row(const RowArgs& p, int row, int64_t n,
     using G = Geo<NB>;
     const int tid = threadIdx.x, d = p.d;
     if (tid < G::NT) {
+        const bool vec = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(p.base) & 15) == 0;
 #pragma unroll
         for (int i = 0; i < G::TR; ++i) {
             const int r = row_pos<NB>(t.r0, i);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int c = reg_pos(t.c0, j);
-                float v;
-                if (r < d && c < d) v = fmaf(p.amb, acc[i][j], __ldg(p.base + (size_t)r * d + c)) + (r == c ? p.ridge : 0.f);
-                else v = (r == c) ? 1.f : 0.f;
-                acc[i][j] = v;
+            for (int h = 0; h < 2; ++h) {
+                const int c = t.c0 + h * 32;                  // four consecutive columns
+                if (vec && r < d && c + 3 < d) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.base + (size_t)r * d + c));
+                    acc[i][h * 4 + 0] = fmaf(p.amb, acc[i][h * 4 + 0], b4.x) + (r == c + 0 ? p.ridge : 0.f);
+                    acc[i][h * 4 + 1] = fmaf(p.amb, acc[i][h * 4 + 1], b4.y) + (r == c + 1 ? p.ridge : 0.f);
+                    acc[i][h * 4 + 2] = fmaf(p.amb, acc[i][h * 4 + 2], b4.z) + (r == c + 2 ? p.ridge : 0.f);
+                    acc[i][h * 4 + 3] = fmaf(p.amb, acc[i][h * 4 + 3], b4.w) + (r == c + 3 ? p.ridge : 0.f);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int cc = c + j;
+                        float v;
+                        if (r < d && cc < d) v = fmaf(p.amb, acc[i][h * 4 + j], __ldg(p.base + (size_t)r * d + cc)) + (r == cc ? p.ridge : 0.f);
+                        else v = (r == cc) ? 1.f : 0.f;
+                        acc[i][h * 4 + j] = v;
+                    }
+                }
             }
         }
     }
@@ -888,15 +901,15 @@ template <int NB> static int set_attr() {
     return TKR_OK;
 }
 
-// factorisation variant (tkr_debug_set_als_factor): 0 = default (blocked at NB = 4, four-column rounds below), 1 = blocked
-// everywhere, 2 = the per-column / four-column loops everywhere.  A process global like the other tkr_debug_* switches.
+// factorisation variant (tkr_debug_set_als_factor): 0 = default = 1 = the blocked 16-column rounds, 2 = the per-column (NB = 4) /
+// four-column loops of round 1 (kept as the reference point the blocked rounds are measured against).  A process global like the other tkr_debug_* switches.
 int g_als_factor = 0;
 
 template <int NB> static int launch_rows(const RowArgs& p, int64_t n_segs, int64_t n_multi, cudaStream_t st) {
     using G = Geo<NB>;
     int rc = set_attr<NB>();
     if (rc) return rc;
-    const bool blk = g_als_factor == 1 || (g_als_factor == 0 && NB == 4);
+    const bool blk = g_als_factor != 2;
     if (n_segs > 0) {
         if (blk) als_segment_kernel<NB, true><<<(unsigned)n_segs, G::NTB, G::SMEM, st>>>(p);
         else als_segment_kernel<NB, false><<<(unsigned)n_segs, G::NT, G::SMEM, st>>>(p);
