@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) bpr_count_kernel(const int32_t* __restric
 // the 32 row gathers run through the whole warp one triple after the other, software-pipelined so the
 // 128-bit gathers of triple t+1 are in flight while triple t is reduced and scattered.
 template <int VW, int NCH, bool L1, bool SAMPLE, bool INPLACE>
-__global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_kernel(
+__global__ void __launch_bounds__(256, NCH == 1 ? (INPLACE ? 2 : 4) : 1) bpr_grad_kernel(
     tkr_bpr_cfg cfg, const float* __restrict__ U, const float* __restrict__ V, const float* __restrict__ b,
     const int32_t* __restrict__ ub, const int32_t* __restrict__ ib, const int32_t* __restrict__ jb, int64_t B,
     SamplerDev smp, uint64_t first_draw, StepWs ws, int mode, int tpw, StepExtra ex, float* __restrict__ loss_out,
@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
         const float bdiff = valid ? __ldg(b + i) - __ldg(b + j) : 0.f;
         const float bi = valid ? __ldg(ex.b_reg + i) : 0.f, bj = valid ? __ldg(ex.b_reg + j) : 0.f;   // regularised bias
         float x_mine = 0.f, s_mine = 0.f;
-        const bool pairwise = ex.s_emb != nullptr;                       // (VBPR as written: weights precomputed per triple)
+        // (VBPR as written: weights precomputed per triple; Hogwild: -lr * gradient straight onto the rows.  Neither exists on the
+        // in-place streaming route, whose instantiation must not pay for the tests: INPLACE makes both compile-time false.)
+        const bool pairwise = !INPLACE && ex.s_emb != nullptr;
+        const bool hogwild = !INPLACE && mode == MODE_HOGWILD;
         const float se_mine = (pairwise && valid) ? __ldg(ex.s_emb + n) : 0.f;
         // MODE_COUNT: bit 0/1/2 = the u / i / j row of this triple occurs once in the batch -> updated in place
         int hs_i = 0, hs_j = 0;        // privatised slot + 1 of the item rows (0 = cold)
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
                         p.v[e] = fmaf(-s, cur.u[c].v[e], reg_grad<L1>(cur.i[c].v[e], lam_i[c]));                      // gV_i
                         q.v[e] = fmaf(s, cur.u[c].v[e], reg_grad<L1>(cur.j[c].v[e], lam_j[c]));                       // gV_j
                     }
-                    if (mode == MODE_HOGWILD) {
+                    if (hogwild) {
 #pragma unroll
                         for (int e = 0; e < VW; ++e) { a.v[e] *= -cfg.lr; p.v[e] *= -cfg.lr; q.v[e] *= -cfg.lr; }
                     }
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
         }
         // lane-parallel scalar tail: lane t finishes triple t
         if (valid) {
-            if (mode == MODE_COUNT || mode == MODE_HOGWILD) {
+            if (mode == MODE_COUNT || hogwild) {
                 // the counts are the touched flags / nothing to flag
             } else if (mode == MODE_DENSE) {
                 ws.cntU[u] = 1; ws.tchV[i] = 1.0f; ws.tchV[j] = 1.0f;
@@ -266,7 +269,7 @@ __global__ void __launch_bounds__(256, (NCH == 1 && !INPLACE) ? 4 : 1) bpr_grad_
                 if (atomicAdd(ws.cntV + j, 1) == 0) ws.listV[atomicAdd(ws.n_touched + 1, 1)] = j;
             }
             if (pairwise) s_mine = __ldg(ex.s_bias + n);           // the bias / wq path of the [B, B] graph sums over the other index
-            const float gsc = mode == MODE_HOGWILD ? -cfg.lr : 1.0f;
+            const float gsc = hogwild ? -cfg.lr : 1.0f;
             const float gbi = gsc * (-s_mine + reg_grad<L1>(bi, cfg.lambda_b)), gbj = gsc * (s_mine + reg_grad<L1>(bj, cfg.lambda_b));
             if (hs_i) { sh_red_add(hot_b + hs_i - 1, gbi); hot_dirty[hs_i - 1] = 1.f; } else atomicAdd(ws.Gb + i, gbi);
             if (hs_j) { sh_red_add(hot_b + hs_j - 1, gbj); hot_dirty[hs_j - 1] = 1.f; } else atomicAdd(ws.Gb + j, gbj);
