@@ -26,10 +26,14 @@
 namespace tkr {
 namespace als {
 
-constexpr int KC = 16;      // rows per stage
-constexpr int STAGES = 3;
+constexpr int KC_ALIGN = 32; // slices of the shared Gram's row list are multiples of this (>= every Geo<NB>::KC)
 
 template <int NB> struct Geo {
+    // gather pipeline: rows per stage x stages.  The per-stage bookkeeping (indices, cp.async issue, barrier) is ~290
+    // instructions per warp, a fifth of a 16-row stage's FMA work: at NB = 4 two stages of 32 rows measured 3 % (user rows) to
+    // 7 % (item rows) faster than three of 16; at NB = 3 they measured 5 % slower, at NB <= 2 the same -- so 16 x 3 there.
+    static constexpr int KC = NB == 4 ? 32 : 16;
+    static constexpr int STAGES = NB == 4 ? 2 : 3;
     static constexpr int DP = 64 * NB;                 // padded width
     static constexpr int NBLK = NB * (NB + 1) / 2;     // lower-triangular 64x64 blocks
     // rows of a thread's register tile (columns: always 8).  16 x 8 tiles on 320 threads would halve the shared-memory
@@ -69,6 +73,7 @@ struct RowArgs {
     float* partial; double* loss_rows;
     float a, amb, ridge, lreg;
     int d, solve_empty, item_loss;
+    int full_diag;              // 1: the upper-triangle quarter of the diagonal blocks is wanted too (the shared Gram's reduce kernel)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -115,13 +120,13 @@ template <int NB> __device__ __forceinline__ int row_pos(int r0, int i) { return
 // acc += sum over rows list[0..n) of y y^T (this thread's tile); ssum += column tid of the same rows.
 template <int NB>
 __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], float& ssum, const Tile& t, const float* __restrict__ Y,
-                                                int d, const int32_t* __restrict__ list, int64_t n, float* stage) {
+                                                int d, const int32_t* __restrict__ list, int64_t n, float* stage, bool lower_only) {
     using G = Geo<NB>;
-    constexpr int EPT = (KC * (G::DP / 4) + G::NT - 1) / G::NT;   // 16-byte pieces of a stage per thread (upper bound)
+    constexpr int EPT = (G::KC * (G::DP / 4) + G::NT - 1) / G::NT;   // 16-byte pieces of a stage per thread (upper bound)
     const int tid = threadIdx.x;
     const bool vec = (d & 3) == 0 && ((reinterpret_cast<uintptr_t>(Y) & 15) == 0);
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    const int64_t nchunks = (n + KC - 1) / KC;
+    const int64_t nchunks = (n + G::KC - 1) / G::KC;
     // vector path: piece e = tid + i*NT of every stage is (row e / q, floats 4*(e % q)..+3); the row's index is fetched
     // one stage ahead of its cp.async so the gather never waits on the index load
     int prow[EPT], pcol[EPT], pidx[EPT];
@@ -129,22 +134,22 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], fl
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
         const int e = tid + i * G::NT;
-        prow[i] = (vec && e < KC * q) ? e / q : KC;
+        prow[i] = (vec && e < G::KC * q) ? e / q : G::KC;
         pcol[i] = (e - prow[i] * q) * 4;
         pidx[i] = 0;
     }
     auto fetch_idx = [&](int64_t c) {
         if (vec && c < nchunks) {
-            const int rows = (int)min((int64_t)KC, n - c * KC);
+            const int rows = (int)min((int64_t)G::KC, n - c * G::KC);
 #pragma unroll
             for (int i = 0; i < EPT; ++i)
-                if (prow[i] < rows) pidx[i] = list[c * KC + prow[i]];
+                if (prow[i] < rows) pidx[i] = list[c * G::KC + prow[i]];
         }
     };
     auto issue = [&](int64_t c) {
         if (c < nchunks) {
-            const int rows = (int)min((int64_t)KC, n - c * KC);
-            const uint32_t buf = stage_s + (uint32_t)((c % STAGES) * KC * G::DP) * 4u;
+            const int rows = (int)min((int64_t)G::KC, n - c * G::KC);
+            const uint32_t buf = stage_s + (uint32_t)((c % G::STAGES) * G::KC * G::DP) * 4u;
             if (vec) {
 #pragma unroll
                 for (int i = 0; i < EPT; ++i)
@@ -152,7 +157,7 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], fl
             } else {
                 for (int e = tid; e < rows * d; e += G::NT) {
                     const int r = e / d, cc = e - r * d;
-                    cp_async4(buf + (uint32_t)(r * G::DP + cc) * 4u, Y + (size_t)list[c * KC + r] * d + cc);
+                    cp_async4(buf + (uint32_t)(r * G::DP + cc) * 4u, Y + (size_t)list[c * G::KC + r] * d + cc);
                 }
             }
         }
@@ -160,30 +165,37 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[Geo<NB>::TR][8], fl
     };
     fetch_idx(0);
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) { issue(s); fetch_idx(s + 1); }
+    for (int s = 0; s < G::STAGES - 1; ++s) { issue(s); fetch_idx(s + 1); }
     for (int64_t c = 0; c < nchunks; ++c) {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<G::STAGES - 2>();
         named_barrier(3, G::NT);                 // the NT tile threads (a blocked-variant block has one more warp, which is not here)
-        issue(c + STAGES - 1);
-        fetch_idx(c + STAGES);
-        const float* buf = stage + (c % STAGES) * KC * G::DP;
-        const int rows = (int)min((int64_t)KC, n - c * KC);
+        issue(c + G::STAGES - 1);
+        fetch_idx(c + G::STAGES);
+        const float* buf = stage + (c % G::STAGES) * G::KC * G::DP;
+        const int rows = (int)min((int64_t)G::KC, n - c * G::KC);
+        // lower_only: a diagonal block whose upper-triangle quarter (rows 0..31 x columns 32..63 of the block) nobody reads
+        // -- every solve; not the shared Gram, whose reduce kernel writes the full matrix.  Two of a scheduler's five warps
+        // then issue 48 instead of 64 FFMA per gathered row.
+        auto rank1 = [&](auto lo) {
+            constexpr bool LO = decltype(lo)::value;
 #pragma unroll 2
-        for (int k = 0; k < rows; ++k) {
-            const float* y = buf + k * G::DP;
-            const float4 b0 = *reinterpret_cast<const float4*>(y + t.c0), b1 = *reinterpret_cast<const float4*>(y + t.c0 + 32);
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            for (int k = 0; k < rows; ++k) {
+                const float* y = buf + k * G::DP;
+                const float4 b0 = *reinterpret_cast<const float4*>(y + t.c0), b1 = *reinterpret_cast<const float4*>(y + t.c0 + 32);
+                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int gi = 0; gi < G::TR / 4; ++gi) {
-                const float4 a4 = *reinterpret_cast<const float4*>(y + t.r0 + gi * G::RS);
-                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+                for (int gi = 0; gi < G::TR / 4; ++gi) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(y + t.r0 + gi * G::RS);
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[gi * 4 + i][j] = fmaf(av[i], bv[j], acc[gi * 4 + i][j]);
+                        for (int j = 0; j < (LO && gi == 0 ? 4 : 8); ++j) acc[gi * 4 + i][j] = fmaf(av[i], bv[j], acc[gi * 4 + i][j]);
+                }
+                if (tid < G::DP) ssum += y[tid];
             }
-            if (tid < G::DP) ssum += y[tid];
-        }
+        };
+        if (lower_only) rank1(std::true_type{}); else rank1(std::false_type{});
     }
     cp_async_wait<0>();
     named_barrier(3, G::NT);
@@ -250,7 +262,7 @@ template <int NB> struct Smem {
     float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep; float* ldiag; float* dinv;
     __device__ explicit Smem(float* base) {
         M = base; stage = M + G::FACTOR;     // FACTOR * 4 bytes is a multiple of 16 for every DP
-        raw = stage + STAGES * KC * G::DP; zs = raw + 4 * G::DP; xs = zs + G::DP; d44 = xs + G::DP; red = d44 + 16; keep = red + 64;
+        raw = stage + G::STAGES * G::KC * G::DP; zs = raw + 4 * G::DP; xs = zs + G::DP; d44 = xs + G::DP; red = d44 + 16; keep = red + 64;
         ldiag = keep + 3 * G::DP; dinv = ldiag + G::PW * G::PW;
     }
 };
@@ -818,7 +830,7 @@ __global__ void __launch_bounds__(BLK ? Geo<NB>::NTB : Geo<NB>::NT) __maxnreg__(
         if (p.loss_rows) loss_only_row<NB>(p, row, sm.red);
         return;
     }
-    for (int e = tid; e < STAGES * KC * G::DP; e += blockDim.x) sm.stage[e] = 0.f;   // pad columns stay zero
+    for (int e = tid; e < G::STAGES * G::KC * G::DP; e += blockDim.x) sm.stage[e] = 0.f;   // pad columns stay zero
     __syncthreads();
     const bool tile_thread = tid < G::NT;                   // (a blocked-variant block has one more warp: the pivot warp)
     const Tile t = tile_of<NB>(tile_thread ? tid : 0);
@@ -828,7 +840,7 @@ __global__ void __launch_bounds__(BLK ? Geo<NB>::NTB : Geo<NB>::NT) __maxnreg__(
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     float ssum = 0.f;
-    if (tile_thread) gram_accumulate<NB>(acc, ssum, t, p.Y, p.d, p.idx + p.seg_off[seg], len, sm.stage);
+    if (tile_thread) gram_accumulate<NB>(acc, ssum, t, p.Y, p.d, p.idx + p.seg_off[seg], len, sm.stage, t.I == t.J && !p.full_diag);
     if (slot >= 0) {
         if (tile_thread) store_partial<NB>(acc, ssum, p.partial + (size_t)slot * G::PART);
         return;
@@ -973,8 +985,8 @@ extern "C" int tkr_als_gram(const float* Y, int32_t d, const int32_t* rows, int6
         return TKR_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int n_segs = (int)std::min<int64_t>(als::kGramSegs, std::max<int64_t>(1, (n_rows + als::KC - 1) / als::KC));
-    const int64_t per = ((n_rows + n_segs - 1) / n_segs + als::KC - 1) / als::KC * als::KC;
+    const int n_segs = (int)std::min<int64_t>(als::kGramSegs, std::max<int64_t>(1, (n_rows + als::KC_ALIGN - 1) / als::KC_ALIGN));
+    const int64_t per = ((n_rows + n_segs - 1) / n_segs + als::KC_ALIGN - 1) / als::KC_ALIGN * als::KC_ALIGN;
     char* w = (char*)ws;
     als::RowArgs p = {};
     p.partial = (float*)w; w += tkr_als_partial_bytes(d, als::kGramSegs);
@@ -982,9 +994,9 @@ extern "C" int tkr_als_gram(const float* Y, int32_t d, const int32_t* rows, int6
     int32_t* seg_row = (int32_t*)w; w += (size_t)als::kGramSegs * 4;
     int32_t* seg_len = (int32_t*)w; w += (size_t)als::kGramSegs * 4;
     int32_t* seg_slot = (int32_t*)w;
-    als::gram_plan_kernel<<<(n_segs + 127) / 128, 128, 0, st>>>(n_rows, n_segs, std::max<int64_t>(per, als::KC), seg_row, seg_off, seg_len, seg_slot);
+    als::gram_plan_kernel<<<(n_segs + 127) / 128, 128, 0, st>>>(n_rows, n_segs, std::max<int64_t>(per, als::KC_ALIGN), seg_row, seg_off, seg_len, seg_slot);
     TKR_LAUNCH_CHECK();
-    p.Y = Y; p.idx = rows; p.d = d;
+    p.Y = Y; p.idx = rows; p.d = d; p.full_diag = 1;
     p.seg_row = seg_row; p.seg_off = seg_off; p.seg_len = seg_len; p.seg_slot = seg_slot;
     switch (als::nb_of(d)) {
         case 1: return als::launch_gram<1>(p, n_segs, d, scale, ridge, out, st);
