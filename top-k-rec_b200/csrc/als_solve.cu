@@ -583,8 +583,8 @@ __device__ __forceinline__ void blocked_pivot(const Smem<NB>& sm, int p) {
     const int r = PW * p + (dg ? i : 0);
     float a[PW];
 #pragma unroll
-    for (int k = 0; k < PW; ++k) a[k] = Lp[k * pitch + r];
-    float zi = sm.zs[r];
+    for (int k = 0; k < PW; ++k) a[k] = dg ? Lp[k * pitch + r] : 1.f;     // (lanes 16..31 only take part in the shuffles)
+    float zi = dg ? sm.zs[r] : 0.f;
     static_for<0, PW>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         const float dj = __shfl_sync(FULL, a[j], j);
@@ -638,7 +638,7 @@ __device__ __forceinline__ void blocked_round(float (&acc)[Geo<NB>::TR][8], cons
         const int i = tid - PW * p;                           // >= 16: a row below the diagonal block
         float a[PW];
 #pragma unroll
-        for (int k = 0; k < PW; ++k) a[k] = Lp[k * pitch + tid];
+        for (int k = 0; k < PW; ++k) a[k] = i >= PW ? Lp[k * pitch + tid] : 0.f;     // (rows of the diagonal block are the pivot warp's)
         named_barrier(2, blocked_b2_count<NB>(p));
         if (i >= PW) {
             // M[r][j] = A[r][j] - sum_{q < j} M[r][q] L[j][q], right-looking: once M[r][q] is final it leaves all the later
