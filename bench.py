@@ -415,11 +415,12 @@ def dp_consistency(engine, st, dev, world):
 
 def bpr_sweep(cfg, st, smp, dev):
     """Other operating points of the same path on C2 (device-timed, >= 1 s each): the reference's own batch size 256
-    (bpr.py:103; persistent multi-step cluster kernel), 2^16, and 2^20 with the sampler fused into the step."""
+    (bpr.py:103; persistent multi-step cluster kernel), 64 and 1024 (dataflow multi-step kernel), 2^16, and 2^20 with the
+    sampler fused into the step."""
     import torch
     import topkrec
     out = []
-    for B, fused, n_steps in ((256, False, 4096), (256, True, 4096), (1 << 16, False, 64), (1 << 20, True, 8)):
+    for B, fused, n_steps in ((64, False, 4096), (256, False, 4096), (256, True, 4096), (1024, False, 1024), (1 << 16, False, 64), (1 << 20, True, 8)):
         ws = topkrec.bpr_workspace(cfg, B, dev)
         topkrec.bpr_set_hot_items(cfg, B, ws, topkrec.popular_items(smp.pos_idx, N_ITEMS))
         loss = torch.zeros(n_steps, dtype=torch.float32, device=dev)
@@ -434,7 +435,8 @@ def bpr_sweep(cfg, st, smp, dev):
         reps = int(max(3, min(400, 1000.0 / one)))
         ms = device_time_ms(run, reps, 0) / n_steps
         out.append({"batch_size": B, "fused_sampler": fused, "us_per_step": 1e3 * ms, "triples_per_sec": B / (ms / 1e3), "timed_seconds": ms * n_steps * reps / 1e3,
-                    "route": "persistent cluster kernel, %d steps per launch" % n_steps if B <= 1024 else "bpr_grad_kernel + bpr_apply_kernel per step",
+                    "route": ("dataflow multi-step kernel (row-level version words, no grid barriers)" if B <= 64 or 256 < B <= 1024 else
+                              "persistent cluster kernel, %d steps per launch" % n_steps if B <= 256 else "bpr_grad_kernel + bpr_apply_kernel per step"),
                     "algorithmic_gbs": algorithmic_bytes_per_triple(D) * B / (ms / 1e3) / 1e9})
     return out
 

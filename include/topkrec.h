@@ -288,9 +288,10 @@ void tkr_debug_set_filter_counters(long long* dev_buf);
 /* tkr_bpr_step path choice: -1 automatic (default), 0 never / 1 always (when legal) take the counting path that
  * updates rows occurring once in a batch in place; both paths follow the same step semantics. */
 void tkr_debug_set_count_mode(int32_t mode);
-/* tkr_bpr_step route for small batches: -1 automatic (default: the persistent cluster kernel -- many steps per launch --
- * for batches <= 256), 0 never (two launches per step), 1 whenever legal (batches <= 1024, d <= 256); both routes follow
- * the same step semantics. */
+/* tkr_bpr_step route for small batches (<= 1024 triples, d <= 256), many steps per launch: -1 automatic (default: the dataflow
+ * kernel -- row-level version words, no grid-wide barriers -- for batches <= 64 and 257..1024, the cluster kernel with two grid
+ * barriers per step for 65..256), 0 never (two launches per step), 1 the cluster kernel whenever legal, 2 the dataflow kernel
+ * whenever legal; all routes follow the same step semantics. */
 void tkr_debug_set_persist_mode(int32_t mode);
 /* profiling aid: device int64[8] receiving warp 0's cycles per phase of the persistent kernel (gather+gradient, slot
  * prefetch, barrier 1, update, barrier 2, steps); NULL (default) disables it */

@@ -21,12 +21,12 @@ out = []
 for (nu, ni, d) in ((70000, 10000, 128), (70000, 10000, 50)):
     st = {k: torch.from_numpy(v).to(dev) for k, v in bench.init_state_np(nu, ni, d).items()}
     cfg = topkrec.BprCfg(nu, ni, d)
-    for B in (64, 256, 512):
+    for B in (64, 256, 512, 1024):
         n_steps = 2048
         ws = topkrec.bpr_workspace(cfg, B, dev)
         loss = torch.zeros(n_steps, device=dev)
         trip = topkrec.bpr_sample(smp, 0, B * n_steps, dev)
-        for mode, name in ((1, "persistent"), (0, "two_kernel")):
+        for mode, name in ((2, "dataflow"), (1, "persistent"), (0, "two_kernel")):
             L.tkr_debug_set_persist_mode(mode)
             for fused in (False, True):
                 t3 = (None, None, None) if fused else trip

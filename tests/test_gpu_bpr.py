@@ -169,6 +169,25 @@ def persistent_route():
     _set_persist(-1)
 
 
+@pytest.fixture
+def dataflow_route():
+    """force the dataflow multi-step kernel (tkr_debug_set_persist_mode 2): no grid-wide barriers, every triple waits only for
+    the rows it reads (version words), the last occurrence of a row in a step applies its update"""
+    _set_persist(2)
+    yield
+    _set_persist(-1)
+
+
+@pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 100), (900, 700, 256, 1024, 6), (2000, 1500, 200, 700, 7), (50, 40, 7, 1, 30), (300, 200, 128, 97, 9),
+                                   (300, 200, 128, 256, 300), (40, 12, 64, 256, 40), (70000, 10000, 128, 256, 64)])
+def test_bpr_step_dataflow_kernel_matches_oracle(dataflow_route, shape):
+    """same parity bar as the other two routes: popular items (a row touched in every step: the serial chain of the version
+    words), tiny tables (every row occurs many times per step, i == j triples), chunks of more than 256 steps (two launches),
+    ragged batch sizes, a single triple, the C2 table sizes"""
+    nu, ni, d, B, steps = shape
+    _run_case(nu, ni, d, B, steps, seed=57 + d + B, item_skew=ni >= 200)
+
+
 @pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 100), (900, 700, 256, 1024, 6), (2000, 1500, 200, 700, 7), (50, 40, 7, 1, 30), (300, 200, 128, 97, 9)])
 def test_bpr_step_persistent_kernel_matches_oracle(persistent_route, shape):
     """persistent cluster kernel (default for B <= 1024, d <= 256): one triple per warp (B <= 256) and the list path

@@ -21,11 +21,19 @@ struct StepWs {            // views into the caller's workspace
     int32_t* hot_ids;      // [TKR_MAX_HOT] item id of slot s (-1 = unused)
     int32_t* stage;        // batches <= kPersistMaxBatch: 3 x kStageTriples ids sampled ahead for the persistent kernel (else NULL)
     uint32_t* sync;        // ... and the persistent kernel's barrier words: [0] arrival counter, [1] its value at the end of the last launch
+    char* flow;            // scratch of the dataflow multi-step kernel (bpr_flow_bytes; NULL for batches > kPersistMaxBatch)
 };
 
 constexpr int64_t kPersistMaxBatch = 1024;     // batches up to this size CAN take the persistent multi-step kernel (bpr_persist.cu)
 constexpr int64_t kPersistAutoBatch = 256;     // ... and up to this size do by default (one triple per warp of the cluster)
 constexpr int64_t kStageTriples = 1 << 16;
+constexpr int64_t kFlowTriples = 1 << 18;      // triples per launch of the dataflow multi-step kernel (bpr_flow_steps)
+// automatic choice between the two multi-step kernels (profiles/r02w_probe_b256.txt, C2 tables, us per step dataflow / cluster /
+// two launches: B=64 5.3 / 6.2 / 13.7, B=256 7.7 / 6.1 / 14.7, B=512 9.6 / 17.7 / 15.0, B=1024 11.8 / 28.7 / 16.3): the cluster
+// kernel's two grid barriers cost the same whatever the batch, the dataflow kernel's per-step chain grows with the number of
+// occurrences of the most popular rows
+constexpr int64_t kFlowSmallBatch = 64;        // batches up to this size ...
+constexpr int64_t kFlowLargeBatch = 256;       // ... and above this one (up to kPersistMaxBatch) take the dataflow kernel
 
 // VBPR rides on the same kernels with concatenated rows U' = [ur|uc], V' = [ir | F.E]:
 //   item_cols  leading columns of an item row that are parameters (regularised, updated); the rest is the
@@ -63,6 +71,9 @@ int bpr_dispatch_grad(const tkr_bpr_cfg* cfg, const float* U, const float* V, co
                       float* msU = nullptr, float* msV = nullptr);   // the slots are only needed by MODE_COUNT
 extern int g_persist_mode;
 bool bpr_persist_legal(const tkr_bpr_cfg* cfg, int64_t B);
+size_t bpr_flow_bytes(const tkr_bpr_cfg* cfg);
+int bpr_flow_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
+                   const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const StepWs& ws, float* loss, cudaStream_t st);
 int bpr_persist_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
                       const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const StepWs& ws, float* loss, cudaStream_t st);
 void bpr_launch_apply(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb,

@@ -18,6 +18,7 @@
 // step of the same launch.  Used by tkr_bpr_step for batches up to 1024 triples and d <= 256 (wider rows / larger
 // batches keep the two-kernel route, which is bandwidth- rather than latency-bound there).
 #include "bpr_device.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace tkr {
 
@@ -374,7 +375,295 @@ int bpr_persist_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, floa
 #undef TKR_P
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Dataflow variant: the same synchronous-step semantics WITHOUT grid-wide barriers.  A synchronous step only orders work
+// through the rows it touches: an occurrence of row r in step t must read r as the last EARLIER step touching r left it,
+// and r's single update of step t must see every occurrence of r in step t.  Both orders are local to the row:
+//   * a pre-pass sorts the chunk's 3 B S row references by (row, step) and gives every reference the previous step that
+//     touches its row (prev) and the number of occurrences of the row in its own step (n_occ);
+//   * warps take triples in (step, index) order from a ticket counter.  A triple waits until the version words of its three
+//     rows have reached prev (usually long since), gathers, adds its gradients to the rows' accumulators, fences, and
+//     arrives on the rows' counters; the LAST arriver of a row (count == n_occ) -- which still holds the pre-step row in
+//     registers -- applies the optimiser, re-zeroes accumulator and counter, fences, and publishes version = step.
+// Steps overlap as far as their rows allow; what serialises is the chain of a row touched in consecutive steps (the most
+// popular items).  A triple only ever waits for smaller tickets, which running warps hold: no residency assumption.
+// (kFlowTriples, bpr_internal.cuh: triples per chunk; the staged sampler draws kStageTriples ahead, explicit triples come 4x as many)
+constexpr size_t kFlowTmpBytes = (size_t)4 << 20;             // cub radix-sort scratch (checked at run time)
+
+struct FlowWs {
+    uint32_t* ctl;        // [0] ticket counter, [1] global step number of the chunk's first step, [2] steps of the running chunk
+    int32_t* ver;         // [n_users + n_items] global step number + 1 of the row's last update by this kernel
+    uint64_t* keys_a; uint64_t* keys_b;
+    int2* meta;           // [3 * triples] (prev step within the chunk or -1, occurrences of the row in the triple's step)
+    void* tmp;
+};
+size_t bpr_flow_bytes(const tkr_bpr_cfg* cfg) {
+    return 256 + align_up(((size_t)cfg->n_users + cfg->n_items) * 4, 256) + 3 * align_up((size_t)3 * kFlowTriples * 8, 256) + kFlowTmpBytes;
+}
+static FlowWs flow_carve(const tkr_bpr_cfg* cfg, char* p) {
+    FlowWs f;
+    f.ctl = (uint32_t*)p; p += 256;
+    f.ver = (int32_t*)p; p += align_up(((size_t)cfg->n_users + cfg->n_items) * 4, 256);
+    f.keys_a = (uint64_t*)p; p += align_up((size_t)3 * kFlowTriples * 8, 256);
+    f.keys_b = (uint64_t*)p; p += align_up((size_t)3 * kFlowTriples * 8, 256);
+    f.meta = (int2*)p; p += align_up((size_t)3 * kFlowTriples * 8, 256);
+    f.tmp = p;
+    return f;
+}
+
+__global__ void flow_begin_kernel(uint32_t* ctl, uint32_t n_steps) { ctl[1] += ctl[2]; ctl[2] = n_steps; ctl[0] = 0; }
+
+// key = row (users first, then items) : step : reference (3 * index + slot)
+__global__ void __launch_bounds__(256) flow_keys_kernel(const int32_t* __restrict__ u, const int32_t* __restrict__ i, const int32_t* __restrict__ j,
+                                                        int B, int64_t n_refs, uint32_t nu, uint64_t* __restrict__ keys) {
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (e >= n_refs) return;
+    const int64_t n = e / 3;
+    const int s = (int)(e - n * 3);
+    const uint32_t row = s == 0 ? (uint32_t)u[n] : nu + (uint32_t)(s == 1 ? i[n] : j[n]);
+    const uint64_t t = (uint64_t)(n / B), w = (uint64_t)(n % B);
+    keys[e] = ((uint64_t)row << 28) | (t << 12) | (w * 3 + (uint64_t)s);
+}
+__global__ void __launch_bounds__(256) flow_meta_kernel(const uint64_t* __restrict__ keys, int64_t n_refs, int B, int2* __restrict__ meta) {
+    const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= n_refs) return;
+    const uint64_t k = keys[p], grp = k >> 12;                // (row, step)
+    int64_t lo = p, hi = p;
+    while (lo > 0 && (keys[lo - 1] >> 12) == grp) --lo;
+    while (hi + 1 < n_refs && (keys[hi + 1] >> 12) == grp) ++hi;
+    int prev = -1;
+    if (lo > 0 && (keys[lo - 1] >> 28) == (k >> 28)) prev = (int)((keys[lo - 1] >> 12) & 0xffffu);
+    const int64_t t = (int64_t)((k >> 12) & 0xffffu), ws = (int64_t)(k & 0xfffu);
+    meta[t * 3 * B + ws] = make_int2(prev, (int)(hi - lo + 1));
+}
+
+// lanes 0..2 poll the version words of the triple's three rows at once (relaxed loads: the rows are read with ld.cg, issued
+// after the poll has seen the version, and the writer fenced between its stores and the version -- an acquire here would only
+// add an L1 invalidation per poll); the warp goes on when all three have arrived
+__device__ __forceinline__ void flow_wait3(const int32_t* p, int32_t need, bool waits) {
+    constexpr unsigned FULL = 0xffffffffu;
+    uint32_t spins = 0;
+    bool ok = !waits;
+    while (true) {
+        if (!ok) {
+            int32_t v;
+            asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+            ok = v - need >= 0;
+        }
+        if (__all_sync(FULL, ok)) break;
+        if (++spins > (1u << 22)) __trap();                   // a protocol bug traps instead of hanging the GPU
+    }
+}
+__device__ __forceinline__ void flow_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// One triple, whole warp, for the dataflow kernel: as persist_grad, but a row that occurs ONCE in its step (`direct` bit 0 / 1 / 2
+// for the u / i / j row; the pre-pass knows) skips the accumulator round trip altogether -- its gradient is complete in this
+// warp's registers, so the optimiser is applied and the row (and its slot) stored right here: no red, no counter, no re-read.
+template <int VW, int NCH, bool L1>
+__device__ __forceinline__ void flow_grad(const tkr_bpr_cfg& cfg, Row<VW, NCH>& ru, Row<VW, NCH>& ri, Row<VW, NCH>& rj, Row<VW, NCH>& mu, Row<VW, NCH>& mi,
+                                          Row<VW, NCH>& mj, float bi, float bj, float mbi, float mbj, int u, int i, int j, const StepWs& ws, float* __restrict__ U,
+                                          float* __restrict__ V, float* __restrict__ b, float* __restrict__ msU, float* __restrict__ msV, float* __restrict__ msb,
+                                          int d, int lane, int direct, bool rms, bool want_reg, float& x_out, float& reg_out) {
+    constexpr unsigned FULL = 0xffffffffu;
+    float x = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k)
+#pragma unroll
+        for (int q = 0; q < VW; ++q) x = fmaf(ru.c[k].v[q], ri.c[k].v[q] - rj.c[k].v[q], x);
+    x = warp_sum(x) + __shfl_sync(FULL, bi - bj, 0);
+    const float s = __fdividef(1.0f, 1.0f + __expf(x));
+    float reg = 0.f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int off = (k * 32 + lane) * VW;
+        if (off < d) {
+            Vec<VW> a, p, q;
+#pragma unroll
+            for (int e = 0; e < VW; ++e) {
+                a.v[e] = fmaf(-s, ri.c[k].v[e] - rj.c[k].v[e], reg_grad<L1>(ru.c[k].v[e], cfg.lambda_u));
+                p.v[e] = fmaf(-s, ru.c[k].v[e], reg_grad<L1>(ri.c[k].v[e], cfg.lambda_i));
+                q.v[e] = fmaf(s, ru.c[k].v[e], reg_grad<L1>(rj.c[k].v[e], cfg.lambda_j));
+                if (want_reg) reg += reg_val<L1>(ru.c[k].v[e], cfg.lambda_u) + reg_val<L1>(ri.c[k].v[e], cfg.lambda_i) + reg_val<L1>(rj.c[k].v[e], cfg.lambda_j);
+            }
+            if (direct & 1) {
+#pragma unroll
+                for (int e = 0; e < VW; ++e) opt_update(cfg, a.v[e], ru.c[k].v[e], mu.c[k].v[e]);
+                ru.c[k].store(U + (int64_t)u * d + off);
+                if (rms) mu.c[k].store(msU + (int64_t)u * d + off);
+            } else a.red_add(ws.GU + (int64_t)u * d + off);
+            if (direct & 2) {
+#pragma unroll
+                for (int e = 0; e < VW; ++e) opt_update(cfg, p.v[e], ri.c[k].v[e], mi.c[k].v[e]);
+                ri.c[k].store(V + (int64_t)i * d + off);
+                if (rms) mi.c[k].store(msV + (int64_t)i * d + off);
+            } else p.red_add(ws.GV + (int64_t)i * d + off);
+            if (direct & 4) {
+#pragma unroll
+                for (int e = 0; e < VW; ++e) opt_update(cfg, q.v[e], rj.c[k].v[e], mj.c[k].v[e]);
+                rj.c[k].store(V + (int64_t)j * d + off);
+                if (rms) mj.c[k].store(msV + (int64_t)j * d + off);
+            } else q.red_add(ws.GV + (int64_t)j * d + off);
+        }
+    }
+    if (lane == 0) {
+        const float gbi = -s + reg_grad<L1>(bi, cfg.lambda_b), gbj = s + reg_grad<L1>(bj, cfg.lambda_b);
+        if (direct & 2) { opt_update(cfg, gbi, bi, mbi); b[i] = bi; if (rms) msb[i] = mbi; } else atomicAdd(ws.Gb + i, gbi);
+        if (direct & 4) { opt_update(cfg, gbj, bj, mbj); b[j] = bj; if (rms) msb[j] = mbj; } else atomicAdd(ws.Gb + j, gbj);
+    }
+    x_out = x;
+    reg_out = reg;
+}
+
+template <int VW, int NCH, bool L1>
+__global__ void __launch_bounds__(256, 2)
+bpr_flow_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, float* __restrict__ b, float* __restrict__ msU,
+                float* __restrict__ msV, float* __restrict__ msb, const int32_t* __restrict__ ub, const int32_t* __restrict__ ib,
+                const int32_t* __restrict__ jb, int B, int n_steps, StepWs ws, FlowWs fw, float* __restrict__ loss_out) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int d = cfg.d;
+    const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
+    const bool want_loss = loss_out != nullptr;
+    const int total = n_steps * B;
+    const int32_t base = (int32_t)__ldcg(fw.ctl + 1);
+    int32_t* const verU = fw.ver;
+    int32_t* const verV = fw.ver + cfg.n_users;
+    int n_next = 0;
+    if (lane == 0) n_next = (int)atomicAdd(fw.ctl, 1u);
+    n_next = __shfl_sync(FULL, n_next, 0);
+    while (n_next < total) {
+        const int n = n_next;
+        const int u = __ldg(ub + n), i = __ldg(ib + n), j = __ldg(jb + n);
+        const int2 du = __ldg(fw.meta + (int64_t)n * 3), di = __ldg(fw.meta + (int64_t)n * 3 + 1), dj = __ldg(fw.meta + (int64_t)n * 3 + 2);
+        if (lane == 0) n_next = (int)atomicAdd(fw.ctl, 1u);  // the next ticket's round trip hides behind this triple
+        const int t = n / B;
+        // the rows as the last earlier step touching them left them: lane 0 / 1 / 2 <-> the u / i / j row
+        const int2 dm = lane == 0 ? du : lane == 1 ? di : dj;
+        int32_t* const my_ver = lane == 0 ? verU + u : verV + (lane == 1 ? i : j);
+        int32_t* const my_cnt = lane == 0 ? ws.cntU + u : ws.cntV + (lane == 1 ? i : j);
+        flow_wait3(my_ver, base + dm.x + 1, lane < 3 && dm.x >= 0);
+        // rows that occur once in their step are updated in place by this warp (bit 0 / 1 / 2 <-> u / i / j)
+        const int direct = (int)(du.y == 1) | (int)(di.y == 1) << 1 | (int)(dj.y == 1) << 2;
+        Row<VW, NCH> ru, ri, rj, mu, mi, mj;
+        ru.load_cg(U + (int64_t)u * d, d, lane);
+        ri.load_cg(V + (int64_t)i * d, d, lane);
+        rj.load_cg(V + (int64_t)j * d, d, lane);
+        if (rms) {
+            if (direct & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
+            if (direct & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
+            if (direct & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
+        }
+        float bi = 0.f, bj = 0.f, mbi = 0.f, mbj = 0.f, x_t = 0.f, reg_t = 0.f;
+        if (lane == 0) {
+            bi = __ldcg(b + i); bj = __ldcg(b + j);
+            if (rms && (direct & 2)) mbi = __ldcg(msb + i);
+            if (rms && (direct & 4)) mbj = __ldcg(msb + j);
+        }
+        flow_grad<VW, NCH, L1>(cfg, ru, ri, rj, mu, mi, mj, bi, bj, mbi, mbj, u, i, j, ws, U, V, b, msU, msV, msb, d, lane, direct, rms, want_loss, x_t, reg_t);
+        if (want_loss) persist_loss<L1>(cfg, x_t, reg_t, bi, bj, lane, loss_out + t);
+        flow_fence();                                         // this warp's gradient contributions / in-place updates are performed ...
+        __syncwarp();
+        const bool is_direct = lane < 3 && ((direct >> lane) & 1);
+        if (is_direct) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_ver), "r"(base + t + 1) : "memory");   // ... before their versions
+        bool last = false;                                    // ... and before it arrives on the other rows' counters (one round trip;
+        if (lane < 3 && !is_direct) last = atomicAdd(my_cnt, 1) == dm.y - 1;   //  i == j: two arrivals on one row, either can be the last)
+        const int claim = (int)(__ballot_sync(FULL, last) & 7u);
+        if (claim) {
+            flow_fence();                                     // every occurrence's contribution is visible to the last arriver
+            Row<VW, NCH> gu_, gi_, gj_;
+            float gbi = 0.f, gbj = 0.f;
+            if (rms) {
+                if (claim & 1) mu.load_cg(msU + (int64_t)u * d, d, lane);
+                if (claim & 2) mi.load_cg(msV + (int64_t)i * d, d, lane);
+                if (claim & 4) mj.load_cg(msV + (int64_t)j * d, d, lane);
+            }
+            if (claim & 1) gu_.load_cg(ws.GU + (int64_t)u * d, d, lane);
+            if (claim & 2) gi_.load_cg(ws.GV + (int64_t)i * d, d, lane);
+            if (claim & 4) gj_.load_cg(ws.GV + (int64_t)j * d, d, lane);
+            if (lane == 0) {
+                if (claim & 2) { gbi = __ldcg(ws.Gb + i); if (rms) mbi = __ldcg(msb + i); }
+                if (claim & 4) { gbj = __ldcg(ws.Gb + j); if (rms) mbj = __ldcg(msb + j); }
+            }
+            if (claim & 1) {
+                persist_apply_loaded<VW, NCH>(cfg, ru, mu, gu_, U + (int64_t)u * d, msU + (int64_t)u * d, ws.GU + (int64_t)u * d, d, lane, rms);
+                if (lane == 0) ws.cntU[u] = 0;
+            }
+            if (claim & 2) {
+                persist_apply_loaded<VW, NCH>(cfg, ri, mi, gi_, V + (int64_t)i * d, msV + (int64_t)i * d, ws.GV + (int64_t)i * d, d, lane, rms);
+                if (lane == 0) { opt_update(cfg, gbi, bi, mbi); b[i] = bi; if (rms) msb[i] = mbi; ws.Gb[i] = 0.f; ws.cntV[i] = 0; }
+            }
+            if (claim & 4) {
+                persist_apply_loaded<VW, NCH>(cfg, rj, mj, gj_, V + (int64_t)j * d, msV + (int64_t)j * d, ws.GV + (int64_t)j * d, d, lane, rms);
+                if (lane == 0) { opt_update(cfg, gbj, bj, mbj); b[j] = bj; if (rms) msb[j] = mbj; ws.Gb[j] = 0.f; ws.cntV[j] = 0; }
+            }
+            flow_fence();                                     // rows, slots, re-zeroed accumulators and counters first, then the version
+            __syncwarp();
+            if (lane < 3 && ((claim >> lane) & 1)) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_ver), "r"(base + t + 1) : "memory");
+        }
+        n_next = __shfl_sync(FULL, n_next, 0);
+    }
+}
+
+template <int VW, int NCH, bool L1>
+static int launch_flow_l1(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
+                          const int32_t* i, const int32_t* j, int B, int n_steps, const StepWs& ws, const FlowWs& fw, float* loss, cudaStream_t st) {
+    auto kern = bpr_flow_kernel<VW, NCH, L1>;
+    static int per_sm = -1;                                    // per instantiation; decided once (benign race: same answer)
+    if (per_sm < 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, 256, 0) != cudaSuccess || n < 1) n = 1;
+        (void)cudaGetLastError();
+        per_sm = n;
+    }
+    int64_t blocks = (int64_t)kNumSMs * per_sm;
+    const int64_t need = ((int64_t)n_steps * B + 7) / 8;
+    if (blocks > need) blocks = need;
+    kern<<<(unsigned)blocks, 256, 0, st>>>(*cfg, U, V, b, msU, msV, msb, u, i, j, B, n_steps, ws, fw, loss);
+    TKR_LAUNCH_CHECK();
+    return TKR_OK;
+}
+template <int VW, int NCH>
+static int launch_flow(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
+                       const int32_t* i, const int32_t* j, int B, int n_steps, const StepWs& ws, const FlowWs& fw, float* loss, cudaStream_t st) {
+    if (cfg->l1) return launch_flow_l1<VW, NCH, true>(cfg, U, V, b, msU, msV, msb, u, i, j, B, n_steps, ws, fw, loss, st);
+    return launch_flow_l1<VW, NCH, false>(cfg, U, V, b, msU, msV, msb, u, i, j, B, n_steps, ws, fw, loss, st);
+}
+
+// n_steps consecutive steps of B explicit triples each (n_steps * B <= kFlowTriples): pre-pass + one launch
+int bpr_flow_steps(const tkr_bpr_cfg* cfg, float* U, float* V, float* b, float* msU, float* msV, float* msb, const int32_t* u,
+                   const int32_t* i, const int32_t* j, int64_t B, int64_t n_steps, const StepWs& ws, float* loss, cudaStream_t st) {
+    if (n_steps <= 0) return TKR_OK;
+    if (ws.flow == nullptr || n_steps * B > kFlowTriples || n_steps > 65536 || 3 * B > 4096) {
+        set_error("internal: dataflow step kernel called with %lld steps of %lld triples", (long long)n_steps, (long long)B);
+        return TKR_ERR_INVALID;
+    }
+    const FlowWs fw = flow_carve(cfg, ws.flow);
+    const int64_t n_refs = 3 * n_steps * B;
+    flow_begin_kernel<<<1, 1, 0, st>>>(fw.ctl, (uint32_t)n_steps);
+    flow_keys_kernel<<<(unsigned)((n_refs + 255) / 256), 256, 0, st>>>(u, i, j, (int)B, n_refs, (uint32_t)cfg->n_users, fw.keys_a);
+    TKR_LAUNCH_CHECK();
+    int row_bits = 1;
+    while (((int64_t)1 << row_bits) < (int64_t)cfg->n_users + cfg->n_items) ++row_bits;
+    cub::DoubleBuffer<uint64_t> keys(fw.keys_a, fw.keys_b);
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, (int)n_refs, 12, 28 + row_bits, st);
+    if (e != cudaSuccess || tmp_bytes > kFlowTmpBytes) { set_error("dataflow step kernel: radix sort scratch of %zu bytes (cuda: %s)", tmp_bytes, cudaGetErrorString(e)); return TKR_ERR_CUDA; }
+    e = cub::DeviceRadixSort::SortKeys(fw.tmp, tmp_bytes, keys, (int)n_refs, 12, 28 + row_bits, st);
+    if (e != cudaSuccess) { set_error("dataflow step kernel: radix sort failed: %s", cudaGetErrorString(e)); return TKR_ERR_CUDA; }
+    flow_meta_kernel<<<(unsigned)((n_refs + 255) / 256), 256, 0, st>>>(keys.Current(), n_refs, (int)B, fw.meta);
+    TKR_LAUNCH_CHECK();
+    const int d = cfg->d;
+    const int vw = d % 4 == 0 ? 4 : d % 2 == 0 ? 2 : 1;
+    const int nch = (d + 32 * vw - 1) / (32 * vw);
+#define TKR_F(VW, NCH) return launch_flow<VW, NCH>(cfg, U, V, b, msU, msV, msb, u, i, j, (int)B, (int)n_steps, ws, fw, loss, st)
+    if (vw == 4) { if (nch == 1) TKR_F(4, 1); else TKR_F(4, 2); }
+    if (vw == 2) { if (nch == 1) TKR_F(2, 1); else TKR_F(2, 2); }
+    if (nch == 1) TKR_F(1, 1); else TKR_F(1, 2);
+#undef TKR_F
+}
+
 }  // namespace tkr
 
 extern "C" void tkr_debug_set_persist_counters(long long* dev_buf) { tkr::g_persist_dbg = dev_buf; }
-extern "C" void tkr_debug_set_persist_mode(int32_t m) { tkr::g_persist_mode = m < -1 || m > 1 ? -1 : m; }
+extern "C" void tkr_debug_set_persist_mode(int32_t m) { tkr::g_persist_mode = m < -1 || m > 2 ? -1 : m; }

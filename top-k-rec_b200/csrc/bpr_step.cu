@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(256) bpr_apply_kernel(tkr_bpr_cfg cfg, float* 
     }
 }
 
-struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, hotV, stage, total; };
+struct WsLayout { size_t GU, cntU, listU, n_touched, GV, Gb, tchV, cntV, listV, hotV, stage, flow, total; };
 
 WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     WsLayout L;
@@ -407,6 +407,7 @@ WsLayout ws_layout(const tkr_bpr_cfg* cfg, int64_t B) {
     L.hotV = take(ni * 4 + TKR_MAX_HOT * 4);
     // small batches (persistent multi-step kernel): room for kStageTriples sampled triples, drawn a chunk of steps ahead
     L.stage = take(B <= kPersistMaxBatch ? 256 + (size_t)3 * kStageTriples * 4 : 0);   // (+ the kernel's barrier words)
+    L.flow = take(B <= kPersistMaxBatch ? bpr_flow_bytes(cfg) : 0);
     L.total = o;
     return L;
 }
@@ -423,6 +424,7 @@ int bpr_carve(const tkr_bpr_cfg* cfg, int64_t B, void* ws, size_t ws_bytes, Step
     out->hot_slot = (int32_t*)(p + L.hotV); out->hot_ids = out->hot_slot + cfg->n_items;
     out->sync = B <= kPersistMaxBatch ? (uint32_t*)(p + L.stage) : nullptr;
     out->stage = B <= kPersistMaxBatch ? (int32_t*)(p + L.stage + 256) : nullptr;
+    out->flow = B <= kPersistMaxBatch ? p + L.flow : nullptr;
     return TKR_OK;
 }
 
@@ -664,8 +666,12 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
     // Small batches (the reference's batch_size = 256, bpr.py:103): the persistent cluster kernel runs many steps per
     // launch.  With the fused sampler the triples of a chunk of steps are drawn into the workspace first (same draws).
     // (automatic choice: up to one triple per warp of the cluster; between 257 and 1024 triples the two-launch route is still faster)
-    if (g_persist_mode != 0 && mode != MODE_COUNT && bpr_persist_legal(cfg, B) && B <= (g_persist_mode == 1 ? kPersistMaxBatch : kPersistAutoBatch)) {
-        const int64_t chunk = u ? n_steps : kStageTriples / B;
+    if (g_persist_mode != 0 && mode != MODE_COUNT && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch) {
+        // two multi-step kernels: the dataflow kernel (bpr_flow_steps: no grid-wide barriers, every triple waits only for the rows
+        // it reads) and the cluster kernel with two barriers per step (bpr_persist_steps).  g_persist_mode 2 / 1 force one of them,
+        // -1 picks by batch size (bpr_internal.cuh)
+        const bool flow = g_persist_mode == 2 || (g_persist_mode == -1 && (B <= kFlowSmallBatch || B > kFlowLargeBatch));
+        const int64_t chunk = flow ? (u ? kFlowTriples : kStageTriples) / B : (u ? n_steps : kStageTriples / B);
         for (int64_t t = 0; t < n_steps; t += chunk) {
             const int64_t ns = n_steps - t < chunk ? n_steps - t : chunk;
             const int32_t *ut = u ? u + t * B : w.stage, *it = u ? i + t * B : w.stage + kStageTriples, *jt = u ? j + t * B : w.stage + 2 * kStageTriples;
@@ -675,7 +681,8 @@ extern "C" int tkr_bpr_step(const tkr_bpr_cfg* cfg, float* U, float* V, float* b
                 sample_kernel<<<(unsigned)blocks, 256, 0, st>>>(sd, first_draw + (uint64_t)t * (uint64_t)B, ns * B, w.stage, w.stage + kStageTriples, w.stage + 2 * kStageTriples);
                 TKR_LAUNCH_CHECK();
             }
-            if (int rc = bpr_persist_steps(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, ns, w, loss_out ? loss_out + t : nullptr, st)) return rc;
+            if (flow) { if (int rc = bpr_flow_steps(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, ns, w, loss_out ? loss_out + t : nullptr, st)) return rc; }
+            else if (int rc = bpr_persist_steps(cfg, U, V, b, msU, msV, msb, ut, it, jt, B, ns, w, loss_out ? loss_out + t : nullptr, st)) return rc;
         }
         return TKR_OK;
     }
@@ -706,7 +713,7 @@ extern "C" int tkr_bpr_step_host(const tkr_bpr_cfg* cfg, float* U, float* V, flo
     int32_t* di = (int32_t*)p; p += align_up(n * 4, 256);
     int32_t* dj = (int32_t*)p; p += align_up(n * 4, 256);
     float* dl = (float*)p;
-    if (n_steps == 1 || (g_persist_mode != 0 && bpr_persist_legal(cfg, B) && B <= (g_persist_mode == 1 ? kPersistMaxBatch : kPersistAutoBatch))) {
+    if (n_steps == 1 || (g_persist_mode != 0 && bpr_persist_legal(cfg, B) && B <= kPersistMaxBatch)) {
         TKR_CUDA(cudaMemcpyAsync(du, u_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(di, i_host, n * 4, cudaMemcpyHostToDevice, st));
         TKR_CUDA(cudaMemcpyAsync(dj, j_host, n * 4, cudaMemcpyHostToDevice, st));
