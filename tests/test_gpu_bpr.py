@@ -254,6 +254,36 @@ def test_bpr_step_persistent_fused_sampler_chunks(mini):
     _assert_ws_clean(cfg, B, ws)
 
 
+@pytest.mark.parametrize("B,steps", [(48, 3000), (512, 300)])
+def test_bpr_step_dataflow_fused_sampler_chunks(mini, B, steps):
+    """fused sampler + dataflow kernel (the automatic choice at these batch sizes): the staged draws cross the 65 536-triple
+    buffer twice, every chunk gets its own pre-pass and launch, the version words carry over; equal to sampling up front (which
+    takes the 2^18-triple chunks of explicit triples) and to the two-launch route"""
+    tr_users, tr_data, indptr, idx, nu, ni = _mini_tables(mini)
+    rng = np.random.default_rng(46)
+    d, first = 64, 4321
+    st = bpr_ref.new_state(nu, ni, d, rng)
+    smp = topkrec.Sampler(tr_users, indptr, idx, ni, seed=78)
+    cfg = topkrec.BprCfg(nu, ni, d)
+    ws = topkrec.bpr_workspace(cfg, B)
+    a, b2, c = _to_dev(st), _to_dev(st), _to_dev(st)
+    la = torch.empty(steps, device="cuda"); lb = torch.empty(steps, device="cuda"); lc = torch.empty(steps, device="cuda")
+    topkrec.bpr_step(cfg, a["U"], a["V"], a["b"], a["msU"], a["msV"], a["msb"], None, None, None, B, steps, ws, la, sampler=smp, first_draw=first)
+    u, i, j = topkrec.bpr_sample(smp, first, B * steps)
+    topkrec.bpr_step(cfg, b2["U"], b2["V"], b2["b"], b2["msU"], b2["msV"], b2["msb"], u, i, j, B, steps, ws, lb)
+    _set_persist(0)
+    try:
+        topkrec.bpr_step(cfg, c["U"], c["V"], c["b"], c["msU"], c["msV"], c["msb"], u, i, j, B, steps, ws, lc)
+    finally:
+        _set_persist(-1)
+    for n in a:
+        assert _rel(a[n].cpu().numpy(), b2[n].cpu().numpy()) <= 2e-6, n
+        assert _rel(a[n].cpu().numpy(), c[n].cpu().numpy()) <= REL_TOL, n
+    assert np.allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-5)
+    assert np.allclose(la.cpu().numpy(), lc.cpu().numpy(), rtol=1e-4)
+    _assert_ws_clean(cfg, B, ws)
+
+
 @pytest.mark.parametrize("shape", [(3000, 800, 50, 256, 40), (5000, 1000, 128, 1 << 15, 4), (7, 5, 128, 512, 8), (900, 700, 256, 4096, 5),
                                    (400, 300, 33, 64, 10)])
 def test_bpr_step_hot_items_match_oracle(shape):
