@@ -288,6 +288,17 @@ def test_ring_schedule(G):
         assert {tdist.ring_owner(t, G) for t in range(T)} == set(range(G))
 
 
+def test_ring_shard_bounds():
+    assert tdist.ring_shard_bounds(1 << 20, 8) == tdist.shard_bounds(1 << 20, 8)          # equal shards by default (measured best)
+    assert tdist.ring_shard_bounds(1 << 20, 3, 0.05) == tdist.shard_bounds(1 << 20, 3)    # odd rings rotate every role: no skew
+    for G, tail in ((2, 0.03), (4, 0.03), (8, 0.04), (8, -0.02)):
+        b = tdist.ring_shard_bounds(1 << 20, G, tail)
+        assert b[0][0] == 0 and b[-1][1] == 1 << 20 and all(b[r][1] == b[r + 1][0] for r in range(G - 1))
+        assert all(e % 256 == 0 for _, e in b)
+        even, odd = b[0][1] - b[0][0], b[1][1] - b[1][0]
+        assert (even > odd) == (tail > 0)
+
+
 def test_shard_bounds():
     assert tdist.shard_bounds(10, 3) == [(0, 4), (4, 7), (7, 10)]
     assert tdist.shard_bounds(1 << 20, 8)[-1] == (7 << 17, 1 << 20)

@@ -61,7 +61,7 @@ template <int NB> struct Geo {
     static constexpr int MT_PITCH = DP + 4;            // raw M of the current panel, k-major, in the (free) gather stages
     static constexpr int NTB = NT;                     // threads of a blocked-variant block (warp 0 doubles as the pivot warp)
     static constexpr int MAXREG_B = MAXREG;
-    static constexpr size_t SMEM = (size_t)(FACTOR + STAGES * KC * DP + 4 * DP + 2 * DP + 16 + 64 + 3 * DP + PW * PW + PW) * sizeof(float);
+    static constexpr size_t SMEM = (size_t)(FACTOR + STAGES * KC * DP + 4 * DP + 2 * DP + 16 + 64 + 3 * DP + PW) * sizeof(float);
 };
 
 struct RowArgs {
@@ -259,11 +259,11 @@ __device__ __forceinline__ void row_loss(const RowArgs& p, int row, int64_t n, b
 
 template <int NB> struct Smem {
     using G = Geo<NB>;
-    float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep; float* ldiag; float* dinv;
+    float* M; float* stage; float* raw; float* zs; float* xs; float* d44; float* red; float* keep; float* dinv;
     __device__ explicit Smem(float* base) {
         M = base; stage = M + G::FACTOR;     // FACTOR * 4 bytes is a multiple of 16 for every DP
         raw = stage + G::STAGES * G::KC * G::DP; zs = raw + 4 * G::DP; xs = zs + G::DP; d44 = xs + G::DP; red = d44 + 16; keep = red + 64;
-        ldiag = keep + 3 * G::DP; dinv = ldiag + G::PW * G::PW;
+        dinv = keep + 3 * G::DP;              // [PW] 1 / D of the round's diagonal block
     }
 };
 

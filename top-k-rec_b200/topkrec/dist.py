@@ -157,6 +157,29 @@ def ring_slot(tau, rank, world, n_batches):
     return t, tau - t
 
 
+def ring_shard_bounds(n, world, tail_cost=0.0):
+    """Item shards for ``RingScorer``: equal by default.  With an even number of ranks the sweeps START on the even ranks
+    (threshold warm-up) and END on the odd ones (merge + exact re-scoring), so the two groups could be given shards of different
+    lengths (odd ranks shorter by the fraction delta = tail_cost * world / 2, even ranks longer; negative: the other way round) --
+    measured at 8 GPUs (profiles/r02z_ring_skew_8gpu_*.json): 0.712 ms per batch with equal shards, 0.749 / 0.765 / 0.785 at
+    tail_cost 0.02 / 0.03 / 0.04 and 0.716 / 0.727 / 0.738 at -0.01 / -0.02 / -0.03: a slot lasts as long as its LONGEST shard
+    on either side, neither role carries a visible fixed cost.  Kept for other shapes (few users per batch make the re-scoring
+    relatively dearer).  Bounds are multiples of 256 items (the filter's tile width)."""
+    world = int(world)
+    if world < 2 or world % 2 == 1 or tail_cost == 0:
+        return shard_bounds(n, world)
+    delta = max(-0.5, min(0.5, 0.5 * tail_cost * world))
+    w = [1.0 + delta if r % 2 == 0 else 1.0 - delta for r in range(world)]
+    tot, acc, bounds, beg = sum(w), 0.0, [], 0
+    for r in range(world):
+        acc += w[r]
+        end = int(n) if r == world - 1 else min(int(n), int(round(n * acc / tot / 256.0)) * 256)
+        end = max(end, beg)
+        bounds.append((beg, end))
+        beg = end
+    return bounds
+
+
 def ring_owner(t, world):
     """rank that sweeps the last segment of batch t and ends up with its lists"""
     return (2 * t + world - 1) % world
