@@ -604,19 +604,20 @@ def als_points(dev, fp32_peak, d=256, n_users=480189 // 8, n_items=17770, mean_p
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     tu = ti = 0.0
     topkrec.reset_launch_count()
-    for r in range(reps + 1):
-        ev[0].record()
-        l_u, l_i = iteration()
-        ev[2].record(); torch.cuda.synchronize()
-        if r:                                                       # first iteration = warm-up
-            tu += ev[0].elapsed_time(ev[1]) / reps; ti += ev[1].elapsed_time(ev[2]) / reps
+    with ClockSampler(dev.index) as clk:                            # (this section follows >= 1 s of tensor-pipe work: the clocks say in what state)
+        for r in range(reps + 1):
+            ev[0].record()
+            l_u, l_i = iteration()
+            ev[2].record(); torch.cuda.synchronize()
+            if r:                                                   # first iteration = warm-up
+                tu += ev[0].elapsed_time(ev[1]) / reps; ti += ev[1].elapsed_time(ev[2]) / reps
     launches = topkrec.launch_count() // (reps + 1)
     fl_gram = 2.0 * nnz * d * d
     fl_u, fl_i = fl_gram + n_users * (2.0 / 3.0) * d ** 3, fl_gram + n_items * (2.0 / 3.0) * d ** 3
     out = {"config": "WMF/CER ALS, %d users (1/8 of 480 189: one GPU's share of the 8-GPU run) x %d items, d=%d, %d positives (Zipf items), a=1 b=0.01" % (n_users, n_items, d, nnz),
            "user_step_ms": tu, "item_step_ms": ti, "iteration_ms": tu + ti, "user_rows_per_sec": n_users / (tu / 1e3),
            "item_rows_per_sec": n_items / (ti / 1e3), "positives_per_sec": 2 * nnz / ((tu + ti) / 1e3),
-           "loss": float(l_u.sum()) + float(l_i.sum()), "gpu_launches_per_iteration": launches, "dtype": "f32",
+           "loss": float(l_u.sum()) + float(l_i.sum()), "gpu_launches_per_iteration": launches, "dtype": "f32", "clocks": clk.summary(),
            "roofline": {"bound": "fp32 fma pipe", "achieved": (fl_u + fl_i) / ((tu + ti) / 1e3) / 1e12, "peak": fp32_peak,
                         "peak_source": "measured live: cuBLAS SGEMM 8192^3, TF32 off", "unit": "TFLOP/s",
                         "frac": (fl_u + fl_i) / ((tu + ti) / 1e3) / 1e12 / fp32_peak,
