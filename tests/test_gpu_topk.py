@@ -327,11 +327,13 @@ def test_tc_items_prepared_reuses_bf16_table():
 
 
 @pytest.mark.parametrize("nu,ni,d,bias,rated,cuts", [(18944, 65536, 128, False, 0, (0, 20000, 41000, 65536)), (19000, 40000, 64, True, 40, (0, 9000, 40000)),
-                                                    (18944, 30000, 200, False, 16, (0, 7000, 14000, 22000, 30000))])
+                                                    (18944, 30000, 200, False, 16, (0, 7000, 14000, 22000, 30000)),
+                                                    (18944, 100000, 64, True, 24, (0, 25000, 60000, 100000))])
 def test_score_topk_sweep_in_segments_equals_whole_sweep(nu, ni, d, bias, rated, cuts):
     """tkr_score_topk_tc_segment: one sweep cut into segments over item shards, the rows' thresholds / candidate buffers carried
     in the state from segment to segment (what travels from GPU to GPU in the ring) -- lists and score bits equal the oracle's
-    and the single-call engine's on the whole table"""
+    and the single-call engine's on the whole table.  Tables of >= 65 536 items: the first segment seeds its thresholds on a
+    sample of the WHOLE table (BF16 copy in the segment workspace), with and without a bias column"""
     U, V, b, indptr, idx = _case(nu, ni, d, 30, seed=nu + ni + d, bias=bias, rated=rated)
     t = lambda a: None if a is None else torch.from_numpy(a).cuda()  # noqa: E731
     Ud, Vd, bd, rp, ri = t(U), t(V), t(b), t(indptr), t(idx)

@@ -217,6 +217,8 @@ struct FilterParams {
     int64_t nu, ni, col_offset;
     int kb, cps, stages, tiles_per_split;   // K chunks of 64, chunks per smem stage, ring depth
     int seed_tiles;          // tiles of each sweep (evenly spread) scanned first in seed mode (0 = off)
+    int seed_ext;            // 1: the seed tiles come from ANOTHER table (tensor map tmS: the whole item table, of which this sweep's own
+    int seed_ext_stride;     //    table is the first shard), every seed_ext_stride-th tile of it
     int seed_rank;           // 4 or 3: the row's seed threshold is the smallest of the column quarters' seed_rank-th largest chunk maxima
     int cap_trigger;         // a row's candidate buffer is compacted to its best KPRIME once it would exceed this many keys (<= CAP)
     float* out_tau0;         // [n_splits][nu] seed threshold of each row (-inf when seeding is off)
@@ -397,7 +399,7 @@ __device__ __noinline__ float sel_compact(uint64_t* buf, int n, int lane, const 
 
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F_THREADS, 1)
-score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV, FilterParams p) {
+score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS, FilterParams p) {
     constexpr bool DBG = MODE != 0;
     extern __shared__ unsigned char smem_dyn[];
     // SWIZZLE_128B needs 1024 B alignment; both CTAs of the pair compute the same offsets (the MMA addresses the
@@ -437,7 +439,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
     // Tile sequence of a sweep: T0 seed tiles spread evenly over [t0, t1) (so the seed is an unbiased sample whatever
     // the item order), scanned without hand-offs, then every tile of [t0, t1) in order.
     const int ntl = (int)(t1 - t0);
-    const int T0 = (p.seed_tiles > 0 && ntl >= 4 * p.seed_tiles) ? p.seed_tiles : 0;
+    const int T0 = (p.seed_tiles > 0 && (p.seed_ext || ntl >= 4 * p.seed_tiles)) ? p.seed_tiles : 0;
     const int nseq = ntl + T0;
     const int seed_stride = T0 > 0 ? ntl / T0 : 1;
     auto tile_rel = [&](int tl) -> int { return tl < T0 ? tl * seed_stride : tl - T0; };
@@ -480,7 +482,11 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
             long long dbg_wait0 = 0;
             const long long dbg_t0 = tick<DBG>();
             for (int tl = 0; tl < nseq; ++tl) {
-                const int vrow = (int)((t0 + tile_rel(tl)) * FN) + (int)rank * B_HALF;
+                // (seed tiles of the first segment of a sharded sweep: a sample of the WHOLE table, so that the thresholds start where
+                //  a whole sweep's would -- nothing is collected from seed tiles, their columns do not matter)
+                const bool ext = p.seed_ext && tl < T0;
+                const CUtensorMap* const tmB = ext ? &tmS : &tmV;
+                const int vrow = (ext ? tl * p.seed_ext_stride * FN : (int)((t0 + tile_rel(tl)) * FN)) + (int)rank * B_HALF;
                 for (int j = 0; j < spt; ++j, ++it) {
                     const uint32_t s = it & smask, ph = (it >> sshift) & 1;
                     const long long w0 = tick<DBG>();
@@ -493,7 +499,7 @@ score_filter_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_consta
                     if (rank == 0) mbar_expect_tx(full + s, 2u * stage_bytes);
                     const uint32_t fbar = mapa_shared(smem_u32(full + s), 0);
                     for (int c = 0; c < cps; ++c)
-                        tma_load_2d_pair(sB + (size_t)s * stage_bytes + (size_t)c * B_CHUNK_BYTES, &tmV, fbar, (j * cps + c) * FK, vrow);
+                        tma_load_2d_pair(sB + (size_t)s * stage_bytes + (size_t)c * B_CHUNK_BYTES, tmB, fbar, (j * cps + c) * FK, vrow);
                 }
             }
             if (p.dbg) { long long* o = p.dbg + ((size_t)cta_lin * F_WARPS + warp) * 4; o[0] = tick<DBG>() - dbg_t0; o[1] = dbg_wait0; }
@@ -1033,16 +1039,40 @@ static int tc_run(const float* U, int64_t nu, const float* V, int64_t ni, int32_
         TKR_LAUNCH_CHECK();
     }
     if (seg != nullptr) { seg_scal_kernel<<<1, 32, 0, st>>>(seg->scal, scal, first); TKR_LAUNCH_CHECK(); }
+    // A sharded sweep that STARTS here seeds its thresholds on a sample of the whole table (BF16 copy at the end of the segment
+    // workspace, built with the shard's): a shard-only seed starts ~8x further down the ranking at 8 shards, and the first
+    // segment then paid for it in hand-offs (1.28 ms against 0.47 for a middle segment, profiles/r02_probe_segments.json).
+    __nv_bfloat16* Sbf = nullptr;
+    size_t seed_bytes = 0;
+    const int64_t ntiles_full = (ni_full + FN - 1) / FN;
+    if (seg != nullptr && V_full != nullptr && ni_full > ni && (bias == nullptr) == (bias_full == nullptr) && ntiles_full >= 256) {
+        seed_bytes = align_up((size_t)ni_full * P.dpad * 2, 1024) + 1024;
+        char* end = (char*)ws + ws_bytes;
+        if ((size_t)(end - (w + align_up(P.total, 1024))) >= seed_bytes + exact_rows_workspace_bytes(ni_full, k)) {
+            Sbf = (__nv_bfloat16*)(((uintptr_t)(end - seed_bytes) + 1023) & ~(uintptr_t)1023);
+            if (!items_prepared) {
+                convert_rows_kernel<<<(unsigned)((ni_full + 7) / 8), 256, 0, st>>>(V_full, ni_full, d, P.dpad, bias_full, 0, has_bias, Sbf, nullptr, nullptr, nullptr);
+                TKR_LAUNCH_CHECK();
+            }
+        } else seed_bytes = 0;                                 // (a workspace sized by an older caller: shard-only seeding)
+    }
 
-    CUtensorMap tmU, tmV;
+    CUtensorMap tmU, tmV, tmS;
     if (int rc = make_tmap(&tmU, Ubf, nu, P.dpad, FM)) return rc;
     if (int rc = make_tmap(&tmV, Vbf, ni, P.dpad, B_HALF)) return rc;
+    tmS = tmV;
+    if (Sbf != nullptr && first) { if (int rc = make_tmap(&tmS, Sbf, ni_full, P.dpad, B_HALF)) return rc; }
     FilterParams fp = {};
     fp.nu = nu; fp.ni = ni; fp.col_offset = col_offset; fp.kb = P.kb; fp.cps = P.cps; fp.stages = P.stages; fp.tiles_per_split = P.tps;
     fp.rated_indptr = rated_indptr; fp.rated_idx = rated_idx; fp.cand = cand;
     fp.out_idx = P.ns > 1 ? sidx : midx; fp.out_score = P.ns > 1 ? sscore : mscore;
     fp.dbg = g_filter_dbg;
     fp.seed_tiles = (seg != nullptr && !first) ? 0 : P.seed_tiles;
+    if (Sbf != nullptr && first) {                            // the whole table's own seeding: 1 / g_seed_div of its tiles
+        fp.seed_ext = 1;
+        fp.seed_tiles = (int)(ntiles_full / g_seed_div < 2048 ? ntiles_full / g_seed_div : 2048);
+        fp.seed_ext_stride = (int)(ntiles_full / fp.seed_tiles);
+    }
     fp.out_tau0 = seg ? seg->tau0 : (float*)(w + P.o_tau0);
     fp.resume = (seg != nullptr && !first) ? 1 : 0; fp.suspend = (seg != nullptr && !last) ? 1 : 0;
     fp.st_tau = seg ? seg->tau : nullptr; fp.st_cnt = seg ? seg->cnt : nullptr;
@@ -1055,7 +1085,7 @@ static int tc_run(const float* U, int64_t nu, const float* V, int64_t ni, int32_
 #define TKR_FILTER_LAUNCH(MODE)                                                                                                 \
     do {                                                                                                                        \
         TKR_CUDA(cudaFuncSetAttribute(score_filter_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem)); \
-        score_filter_kernel<MODE><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, fp);                                            \
+        score_filter_kernel<MODE><<<grid, F_THREADS, P.smem, st>>>(tmU, tmV, tmS, fp);                                       \
     } while (0)
     if (fp.dbg == nullptr) TKR_FILTER_LAUNCH(0);
     else if (g_filter_mode == 2) TKR_FILTER_LAUNCH(2);
@@ -1099,7 +1129,7 @@ static int tc_run(const float* U, int64_t nu, const float* V, int64_t ni, int32_
     size_t fbb = P.fb_bytes;
     if (seg != nullptr) {   // the fallback scratch of a segment workspace follows the shard-sized plan (it must hold the whole table's splits)
         fbp = w + align_up(P.total, 1024);
-        fbb = (size_t)((char*)ws + ws_bytes - fbp);
+        fbb = (size_t)((char*)ws + ws_bytes - fbp) - seed_bytes;   // (the seed table sits at the end)
     }
     if (fb_need > fbb) { set_error("score_topk_tc: workspace was sized for a smaller item table (fallback needs %zu bytes, has %zu)", fb_need, fbb); return TKR_ERR_WORKSPACE; }
     if (int rc = launch_exact_rows(U, nu, Vr, nir, d, br, rated_indptr, rated_idx, k, cor, fail, (const int32_t*)(scal + 2), out_idx, out_score, fbp, fbb, st)) return rc;
@@ -1128,7 +1158,10 @@ extern "C" int tkr_score_topk_tc(const float* U, int64_t nu, const float* V, int
 extern "C" size_t tkr_score_topk_tc_state_bytes(int64_t nu) { return nu > 0 ? seg_state(nullptr, nu).total : 0; }
 extern "C" size_t tkr_score_topk_tc_segment_workspace_bytes(int64_t nu, int64_t ni_shard, int64_t ni_full, int32_t d, int32_t k, int32_t has_bias) {
     const size_t a = tkr_score_topk_tc_workspace_bytes(nu, ni_shard, d, k, has_bias);
-    return a + exact_rows_workspace_bytes(ni_full, k) + 4096;
+    TcPlan P;
+    size_t seed = 0;                                          // BF16 copy of the whole table: the first segment's seed sample
+    if (tc_plan(nu, ni_shard, d, k, has_bias != 0, &P) && ni_full > ni_shard) seed = align_up((size_t)ni_full * P.dpad * 2, 1024) + 2048;
+    return a + exact_rows_workspace_bytes(ni_full, k) + 4096 + seed;
 }
 extern "C" int tkr_score_topk_tc_segment(const float* U, int64_t nu, const float* V_shard, int64_t ni_shard, int32_t d, const float* bias_shard,
                                          const int64_t* rated_indptr, const int32_t* rated_idx, int32_t k, int64_t col_offset, void* state,
