@@ -414,8 +414,10 @@ int tkr_topk_exchange_status(int64_t nu_cap, int32_t k, const tkr_peers* peers, 
  * the running state of the sweep -- every row's threshold, candidate buffer and count (tkr_score_topk_tc_state_bytes) --
  * travels from GPU to GPU; GPU g works on segment g of batch t - g while GPU g+1 works on batch t - g - 1.  Unlike independent
  * per-shard top-k lists (tkr_topk_exchange_*), the per-row selection work -- which hardly depends on the sweep length -- is then
- * paid once per batch instead of once per shard.  `first` = the sweep starts here (seeding), `last` = it ends here: only then
- * are the lists sorted out, re-scored exactly against V_full (the keys carry global columns) with the error-bound certificate,
+ * paid once per batch instead of once per shard.  `first` = the sweep starts here: its thresholds are seeded on a sample of
+ * the WHOLE table when V_full is given (tables of >= 65 536 items; a BF16 copy of V_full is kept in the workspace next to the
+ * shard's, built while items_prepared == 0 -- so V_full / bias_full must be the same table on every call that shares a
+ * workspace), else on the shard alone.  `last` = it ends here: only then are the lists sorted out, re-scored exactly against V_full (the keys carry global columns) with the error-bound certificate,
  * and the uncertified rows re-done by the exact engine.  Results are bit-identical to tkr_score_topk on the whole table.
  * The caller moves the state (a plain device-to-device copy into the next GPU's mapped buffer) and orders the segments with
  * tkr_peer_signal_to / tkr_peer_wait_from (flag block of tkr_peer_flag_bytes() at a caller-chosen offset of the exchange
