@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Where a ring slot's time goes, on ONE GPU: one sweep of 18 944 users x 1 M items (d=128, k=30) cut into G segments with
 tkr_score_topk_tc_segment (one workspace per shard so that every shard's BF16 table stays prepared, as on its own rank), each
-segment timed with CUDA events; against the unsegmented sweep.  usage: python profiles/probe_segments.py [G=8] [reps=20]"""
+segment timed with CUDA events; against the unsegmented sweep.  usage: python profiles/probe_segments.py [G=8] [reps=20] [seed_div]"""
 import json
 import os
 import sys
@@ -17,6 +17,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 20
 dev = torch.device("cuda", 0)
 nb, NI, D, k = 18944, 1 << 20, 128, 30
 L = topkrec.lib()
+if len(sys.argv) > 3:
+    L.tkr_debug_set_seed_div(int(sys.argv[3]))
 g = torch.Generator(device=dev); g.manual_seed(4)
 Vfull = torch.randn(NI, D, device=dev, generator=g) * 0.1
 U = [torch.randn(nb, D, device=dev, generator=g) * 0.1 for _ in range(4)]
@@ -51,5 +53,5 @@ for r in range(reps):
 e1.record(); torch.cuda.synchronize()
 whole = e0.elapsed_time(e1) / reps
 same = bool(torch.equal(out[0], wi) and torch.equal(out[1].view(torch.int32), wsc.view(torch.int32)))
-print(json.dumps({"segments": G, "segment_ms": [round(x, 4) for x in seg_ms], "sum_ms": round(sum(seg_ms), 4), "whole_sweep_ms": round(whole, 4),
+print(json.dumps({"seed_div": int(sys.argv[3]) if len(sys.argv) > 3 else 12, "segments": G, "segment_ms": [round(x, 4) for x in seg_ms], "sum_ms": round(sum(seg_ms), 4), "whole_sweep_ms": round(whole, 4),
                   "whole_over_G_ms": round(whole / G, 4), "last_batch_equals_whole_sweep_bitwise": same}))
