@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(256) flow_meta_kernel(const uint64_t* __restri
 // lanes 0..2 poll the version words of the triple's three rows at once (relaxed loads: the rows are read with ld.cg, issued
 // after the poll has seen the version, and the writer fenced between its stores and the version -- an acquire here would only
 // add an L1 invalidation per poll); the warp goes on when all three have arrived
-__device__ __forceinline__ void flow_wait3(const int32_t* p, int32_t need, bool waits) {
+__device__ __forceinline__ void flow_wait3(const int32_t* p, uint32_t need, bool waits) {
     constexpr unsigned FULL = 0xffffffffu;
     uint32_t spins = 0;
     bool ok = !waits;
@@ -449,7 +449,7 @@ __device__ __forceinline__ void flow_wait3(const int32_t* p, int32_t need, bool 
         if (!ok) {
             int32_t v;
             asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-            ok = v - need >= 0;
+            ok = (int32_t)((uint32_t)v - need) >= 0;          // (step numbers wrap after 2^32 steps: compare differences)
         }
         if (__all_sync(FULL, ok)) break;
         if (++spins > (1u << 22)) __trap();                   // a protocol bug traps instead of hanging the GPU
@@ -526,7 +526,7 @@ bpr_flow_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, f
     const bool rms = cfg.optimizer == TKR_OPT_RMSPROP;
     const bool want_loss = loss_out != nullptr;
     const int total = n_steps * B;
-    const int32_t base = (int32_t)__ldcg(fw.ctl + 1);
+    const uint32_t base = __ldcg(fw.ctl + 1);
     int32_t* const verU = fw.ver;
     int32_t* const verV = fw.ver + cfg.n_users;
     int n_next = 0;
@@ -542,7 +542,7 @@ bpr_flow_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, f
         const int2 dm = lane == 0 ? du : lane == 1 ? di : dj;
         int32_t* const my_ver = lane == 0 ? verU + u : verV + (lane == 1 ? i : j);
         int32_t* const my_cnt = lane == 0 ? ws.cntU + u : ws.cntV + (lane == 1 ? i : j);
-        flow_wait3(my_ver, base + dm.x + 1, lane < 3 && dm.x >= 0);
+        flow_wait3(my_ver, base + (uint32_t)(dm.x + 1), lane < 3 && dm.x >= 0);
         // rows that occur once in their step are updated in place by this warp (bit 0 / 1 / 2 <-> u / i / j)
         const int direct = (int)(du.y == 1) | (int)(di.y == 1) << 1 | (int)(dj.y == 1) << 2;
         Row<VW, NCH> ru, ri, rj, mu, mi, mj;
@@ -565,7 +565,7 @@ bpr_flow_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, f
         flow_fence();                                         // this warp's gradient contributions / in-place updates are performed ...
         __syncwarp();
         const bool is_direct = lane < 3 && ((direct >> lane) & 1);
-        if (is_direct) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_ver), "r"(base + t + 1) : "memory");   // ... before their versions
+        if (is_direct) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_ver), "r"(base + (uint32_t)t + 1u) : "memory");   // ... before their versions
         bool last = false;                                    // ... and before it arrives on the other rows' counters (one round trip;
         if (lane < 3 && !is_direct) last = atomicAdd(my_cnt, 1) == dm.y - 1;   //  i == j: two arrivals on one row, either can be the last)
         const int claim = (int)(__ballot_sync(FULL, last) & 7u);
@@ -599,7 +599,7 @@ bpr_flow_kernel(tkr_bpr_cfg cfg, float* __restrict__ U, float* __restrict__ V, f
             }
             flow_fence();                                     // rows, slots, re-zeroed accumulators and counters first, then the version
             __syncwarp();
-            if (lane < 3 && ((claim >> lane) & 1)) asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(my_ver), "r"(base + t + 1) : "memory");
+            if (lane < 3 && ((claim >> lane) & 1)) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(my_ver), "r"(base + (uint32_t)t + 1u) : "memory");
         }
         n_next = __shfl_sync(FULL, n_next, 0);
     }
