@@ -278,7 +278,7 @@ def test_bpr_step_dataflow_fused_sampler_chunks(mini, B, steps):
         _set_persist(-1)
     for n in a:
         assert _rel(a[n].cpu().numpy(), b2[n].cpu().numpy()) <= 2e-6, n
-        assert _rel(a[n].cpu().numpy(), c[n].cpu().numpy()) <= REL_TOL, n
+        assert _rel(a[n].cpu().numpy(), c[n].cpu().numpy()) <= 2 * REL_TOL, n      # (two routes, each within REL_TOL of the oracle)
     assert np.allclose(la.cpu().numpy(), lb.cpu().numpy(), rtol=1e-5)
     assert np.allclose(la.cpu().numpy(), lc.cpu().numpy(), rtol=1e-4)
     _assert_ws_clean(cfg, B, ws)
